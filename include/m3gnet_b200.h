@@ -1,0 +1,244 @@
+/*
+ * m3gnet_b200.h — C ABI of the B200 (sm_100a) energy+forces hot path of M3GNet.
+ *
+ * The reference (lan496/torch-m3gnet) is 100 % Python: it has no FFI/plugin layer to mirror, so this
+ * header *defines* the boundary a maintainer would bind (ctypes stub in INTEGRATION.md).  Each entry
+ * point names the reference code it replaces (paths relative to /root/reference/src/torch_m3gnet/).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; buffers are caller-owned
+ *     (torch caching allocator); no entry point allocates, frees or synchronises;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - return value 0 = success, otherwise a negative M3G_ERR_* code; m3g_last_error() gives the
+ *     message of the last failure on the calling thread;
+ *   - floating tensors are float32 row-major; index tensors are int32 unless noted (the int64
+ *     tensors of the reference API are narrowed once per batch by m3g_narrow_i64);
+ *   - edges are grouped by source atom (ascending), `edge_ptr` (N+1) is that CSR;
+ *     `in_ptr`/`in_perm` is the CSR of edge ids grouped by destination atom (ascending edge id
+ *     inside a row); triplets are a CSR per bond: `tri_ptr` (E+1) rows = first bond e1,
+ *     `tri_e2` (T) columns = second bond; `trt_ptr`/`trt_e1` is its transpose (rows = e2);
+ *   - sizes: N atoms, E directed edges, T triplets, B structures, F feature width (node == edge),
+ *     R = n_max radial functions, L = l_max, D = L*R.
+ *   - accumulation order (stated, deterministic): every segmented sum is evaluated by one warp
+ *     (or sub-warp group of G lanes): lane g adds elements g, g+G, g+2G, ... of the segment in
+ *     ascending order, then lanes are combined by a butterfly (xor 16,8,4,2,1).  No float atomics
+ *     on the default path.
+ */
+#ifndef M3GNET_B200_H
+#define M3GNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define M3G_OK 0
+#define M3G_ERR_INVALID (-1) /* bad argument (null pointer, unsupported size) */
+#define M3G_ERR_CUDA (-2)    /* a CUDA runtime call / launch failed */
+#define M3G_ERR_UNSUPPORTED (-3)
+
+#define M3G_MAX_F 128 /* feature width supported by the kernels */
+#define M3G_MAX_L 4   /* l_max supported by the kernels (reference allows l_max <= 9) */
+#define M3G_MAX_R 4   /* n_max supported by the three-body kernels (reference allows <= 10) */
+#define M3G_MAX_RADIAL 10 /* n_max supported by the radial (edge) basis */
+
+const char* m3g_last_error(void);
+int m3g_abi_version(void);
+/* Device properties the host side sizes grids with: out[0]=SM count, out[1]=cc major, out[2]=cc minor */
+int m3g_device_info(int* out_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * Graph preparation (once per batch; replaces nothing in the reference — it is the canonical
+ * form the reference's `from_structure` output already has, data/material_graph.py:182-187,239-248)
+ * ------------------------------------------------------------------------------------------- */
+int m3g_narrow_i64(const int64_t* in, int32_t* out, int64_t n, void* stream);
+/* flags[0] = 1 if keys is non-decreasing, flags[1] = 1 if every key is in [0, n_rows) */
+int m3g_check_sorted(const int32_t* keys, int64_t n, int64_t n_rows, int32_t* flags, void* stream);
+/* row_ptr[r] = first position whose key >= r (keys sorted); row_ptr has n_rows+1 entries */
+int m3g_csr_from_sorted(const int32_t* keys, int64_t n, int64_t n_rows, int32_t* row_ptr, void* stream);
+/* Stable counting sort of positions 0..n-1 by key: row_ptr (n_rows+1), perm (n) with ascending
+ * positions inside each row.  `work` must hold n_rows+1 + m3g_scan_work_elems(n_rows) int32. */
+int m3g_csr_by_key(const int32_t* keys, int64_t n, int64_t n_rows, int32_t* row_ptr, int32_t* perm,
+                   int32_t* work, void* stream);
+/* out[p] = vals[perm[p]] */
+int m3g_gather_i32(const int32_t* vals, const int32_t* perm, int64_t n, int32_t* out, void* stream);
+/* every row of (row_ptr, cols) is sorted ascending in place (rows are short: one neighbour shell) */
+int m3g_sort_rows(const int32_t* row_ptr, int64_t n_rows, int32_t* cols, void* stream);
+/* flags[0] = 1 iff (ptr_a, col_a) == transpose(ptr_a, col_a), i.e. (e1,e2) present <=> (e2,e1) present */
+int m3g_csr_is_symmetric(const int32_t* row_ptr, const int32_t* cols, int64_t n_rows, int32_t* flags,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Graph construction on the GPU (replaces data/material_graph.py:168-193 [pymatgen
+ * Structure.get_all_neighbors] and :196-254 [compute_threebody]).  Batched over B structures.
+ *   lattice (B,3,3) f64 rows = lattice vectors, cart (N,3) f64, atom_ptr (B+1) int32.
+ * Two-pass: count → caller allocates → fill.  Accept rule d^2 < r^2 + 1e-8 in float64, zero-length
+ * self pairs dropped; images are relative to the unwrapped input coordinates; edges of atom i are
+ * ordered by (j, s0, s1, s2) ascending.
+ * ------------------------------------------------------------------------------------------- */
+int m3g_nbr_count(const double* lattice, const double* cart, const int32_t* atom_ptr, int64_t B, int64_t N,
+                  double cutoff, int32_t* edge_count /* (N) */, void* stream);
+int m3g_exclusive_scan_i32(const int32_t* in, int32_t* out /* n+1 */, int64_t n, int32_t* work, void* stream);
+int64_t m3g_scan_work_elems(int64_t n);
+int m3g_nbr_fill(const double* lattice, const double* cart, const int32_t* atom_ptr, int64_t B, int64_t N,
+                 double cutoff, double threebody_cutoff, const int32_t* edge_ptr /* (N+1) */, int64_t E,
+                 int64_t* edge_index /* (2,E) */, int32_t* edge_shift /* (E,3) */, float* edge_dist /* (E) */,
+                 int32_t* member /* (E) 1 if float32(d) <= float32(r3) */, void* stream);
+/* per-atom member degree n3 -> num_triplet_i (N) int64 = n3(n3-1), num_triplet_ij (E) int32,
+ * tri_count (E) = triplets whose first bond is e (n3-1 for member edges else 0), and member_list (E):
+ * the member edges of atom i compacted (ascending) at positions edge_ptr[i].. */
+int m3g_triplet_count(const int32_t* edge_ptr, const int32_t* member, int64_t N, int64_t E,
+                      int64_t* num_triplet_i, int32_t* num_triplet_ij, int32_t* tri_count, int32_t* member_list,
+                      void* stream);
+/* tri_ptr = exclusive scan of tri_count.  Fills tri_e2 (T) int32 CSR columns and, if triplet_index != NULL,
+ * the reference's (2,T) int64 list in the reference's order (atom, e1, e2) */
+int m3g_triplet_fill(const int32_t* edge_ptr, const int32_t* tri_ptr, const int32_t* tri_count,
+                     const int32_t* member_list, int64_t N, int64_t T, int32_t* tri_e2, int64_t* triplet_index,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Geometry + bases
+ * ------------------------------------------------------------------------------------------- */
+/* nn/scale.py:24-29 — out = in / length_scale (true division) */
+int m3g_scale_fwd(const float* in, float* out, int64_t n, float length_scale, void* stream);
+/* nn/invariant.py:44-59 — vec4[e] = (pos[dst]+shift·lattice[batch[src]]-pos[src], |v|), dist[e] = |v| */
+int m3g_geometry_fwd(const float* pos, const float* lattice, const int32_t* batch, const int32_t* src,
+                     const int32_t* dst, const int32_t* shift, int64_t E, float* vec4, float* dist, void* stream);
+/* nn/invariant.py:33-40 — cos[t] = clamp(v1·v2/(r1 r2), -1, 1) in the caller's triplet order (int64 list) */
+int m3g_angles_fwd(const float* vec4, const int64_t* tri_index /* (2,T) */, int64_t T, float* cos_out, void* stream);
+/* adjoint of m3g_angles_fwd: adds into g_vec4 (E,4) with float atomics (rare path: only when a caller
+ * differentiates through `triplet_angles`) */
+int m3g_angles_bwd(const float* vec4, const int64_t* tri_index, const float* g_cos, int64_t T, float* g_vec4,
+                   void* stream);
+/* adjoint of m3g_geometry_fwd w.r.t. pos: g_e = g_vec4.xyz + (g_vec4.w + g_dist)·v/r;
+ * g_pos[i] = scale * (sum_{e in in(i)} g_e - sum_{e in out(i)} g_e).  g_dist may be NULL. */
+int m3g_geometry_bwd(const float* vec4, const float* g_vec4, const float* g_dist, const int32_t* edge_ptr,
+                     const int32_t* in_ptr, const int32_t* in_perm, int64_t N, float scale, float* g_pos,
+                     void* stream);
+/* nn/featurizer.py:81-100 — h (E,R).  consts: [k_0..k_R | coeff_0..coeff_{R-1} | a_0..a_{R-1} | b_0..b_{R-1}]
+ * with k_m = (m+1)·pi/rc, a_m = sqrt(e_m/d_{m-1}), b_m = sqrt(d_m), all produced on the host by the
+ * reference's float32 op sequence. */
+int m3g_radial_fwd(const float* dist, const float* consts, int64_t E, int R, float* h, void* stream);
+int m3g_radial_bwd(const float* dist, const float* consts, const float* g_h, int64_t E, int R, float* g_dist,
+                   void* stream);
+/* nn/atom_ref.py:25-29 and nn/featurizer.py:33-38 (one-hot · Linear == column gather of W (F,num_types)) */
+int m3g_atomref_fwd(const float* table, const int32_t* types, int64_t N, float* out, void* stream);
+int m3g_embed_fwd(const float* weight /* (F,num_types) */, const int32_t* types, int64_t N, int F, int num_types,
+                  float* x, void* stream);
+/* nn/featurizer.py:128-132 — e0 = SiLU(h · Wt), Wt (R,F) = weight^T */
+int m3g_edge_adjust_fwd(const float* h, const float* Wt, int64_t E, int R, int F, float* e0, void* stream);
+int m3g_edge_adjust_bwd(const float* h, const float* Wt, const float* g_e0, int64_t E, int R, int F, float* g_h,
+                        void* stream);
+
+/* nn/interaction.py:284-350 (SphericalBessel fwd + its custom derivative), :353-382 (LegendreCosPolynomial
+ * fwd / bwd with the reference's grad_output-per-level rule), :389-400 (cutoff_function) — elementwise,
+ * kept for the operator API (`spherical_bessel`, `legendre_cos`, `cutoff_function`).  dout may be NULL. */
+int m3g_sph_bessel(const float* x, int order, int64_t n, float* out, float* dout, void* stream);
+int m3g_legendre(const float* x, int order, int64_t n, float* out, void* stream);
+int m3g_legendre_bwd(const float* x, const float* go, int order, int64_t n, float* gx, void* stream);
+int m3g_cutoff(const float* r, float rc, int64_t n, float* out, float* dout, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ThreeBodyInteration (nn/interaction.py:187-223) — D = L*R, d = l*R + n
+ * tb_consts: [zeros_ln (D) | factors_ln (D) | rc | r3]  (2*D + 2 floats; chi = j_l(z r / rc) / factors)
+ * ------------------------------------------------------------------------------------------- */
+/* sig (N,D) = sigmoid(x · Ws^T + bs), Ws (D,F) = linear_sigmoid1.weight */
+int m3g_tb_sigma_fwd(const float* x, const float* Ws, const float* bs, int64_t N, int F, int D, float* sig,
+                     void* stream);
+/* per edge: bas[e][d] = chi_d(r_e)·fc(r_e)·sig[dst[e]][d]   (chi uses rc, fc uses r3; quirk Q5) */
+int m3g_tb_edge_basis_fwd(const float* vec4, const int32_t* dst, const float* sig, const float* tb_consts,
+                          int64_t E, int L, int R, float* bas, void* stream);
+/* red[e1][d] = fc(r_e1)·sum_{e2 in tri(e1)} Y_l(cos(e1,e2))·bas[e2][d];
+ * e_out = e_in + SiLU(red·WdT) * sigmoid(red·WgT), WdT/WgT (D,F) */
+int m3g_tb_reduce_fwd(const float* vec4, const float* bas, const int32_t* tri_ptr, const int32_t* tri_e2,
+                      const float* tb_consts, const float* WdT, const float* WgT, const float* e_in, int64_t E,
+                      int L, int R, int F, int group, float* red, float* e_out, void* stream);
+/* g_red (E,D) from g_e (E,F): adjoint of the bias-free 1-layer GatedMLP (forward recomputed from red) */
+int m3g_tb_gate_bwd(const float* red, const float* g_e, const float* WdT, const float* WgT, int64_t E, int D, int F,
+                    float* g_red, void* stream);
+/* gather-form adjoint of the triplet sum (uses tri CSR for "e as first bond" and its transpose for
+ * "e as second bond"; they may alias when the list is symmetric).  Outputs: g_vec4 (E,4) (xyz from
+ * cos, w from cos and fc(r_e1)), g_bas (E,D).  Legendre backward follows the reference (quirk Q3). */
+int m3g_tb_reduce_bwd(const float* vec4, const float* bas, const float* g_red, const int32_t* tri_ptr,
+                      const int32_t* tri_e2, const int32_t* trt_ptr, const int32_t* trt_e1, const float* tb_consts,
+                      int64_t E, int L, int R, int group, float* g_vec4, float* g_bas, void* stream);
+/* adjoint of m3g_tb_edge_basis_fwd: g_vec4[e].w += d/dr terms; g_sig_e (E,D) per-edge sigma gradient */
+int m3g_tb_edge_basis_bwd(const float* vec4, const int32_t* dst, const float* sig, const float* g_bas,
+                          const float* tb_consts, int64_t E, int L, int R, float* g_vec4, float* g_sig_e,
+                          void* stream);
+/* g_x (N,F) = (sum_{e in in(k)} g_sig_e[e]) * sig(1-sig) · Ws, Ws (D,F) */
+int m3g_tb_sigma_bwd(const float* g_sig_e, const int32_t* in_ptr, const int32_t* in_perm, const float* sig,
+                     const float* Ws, int64_t N, int F, int D, float* g_x, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Generic row-wise linear: out (n,M) = in (n,K) · Wt (K,M) + bias (M or NULL).  Used for the per-atom
+ * first-layer projections of M3GNetConv (nn/conv.py:92-97 concat split: [x_i,x_j,e]·W = x_i·W_i + x_j·W_j + e·W_e)
+ * ------------------------------------------------------------------------------------------- */
+int m3g_linear_fwd(const float* in, const float* Wt, const float* bias, int64_t n, int K, int M, float* out,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * M3GNetConv (nn/conv.py:63-97, nn/core.py:6-62).  One "gated MLP on edges":
+ *   z1 = P[src][po .. po+2F) + P[dst][po+2F .. po+4F) + e · W1eT            (2F: dense | gate)
+ *   a1 = SiLU(z1); z2d = a1d·W2dT + b2d; z2g = a1g·W2gT + b2g
+ *   out = SiLU(z2d) * sigmoid(z2g) * (h · WhT)
+ * P (N, ldp) holds the per-atom projections (bias of layer 1 folded into the src part).
+ * mode 0 (edge update, conv.py:68-75): y = e + out, written to y (E,F)
+ * mode 1 (node update, conv.py:77-89): y = out (messages); m3g_segment_sum_add then adds them per source atom
+ * ------------------------------------------------------------------------------------------- */
+int m3g_conv_mlp_fwd(const float* P, int ldp, int po, const int32_t* src, const int32_t* dst, const float* e,
+                     const float* h, const float* W1eT, const float* W2dT, const float* b2d, const float* W2gT,
+                     const float* b2g, const float* WhT, int64_t E, int F, int R, int mode, float* y, void* stream);
+/* out (N,F) = base (N,F) + sum_{e in [edge_ptr[i], edge_ptr[i+1])} msg[e] */
+int m3g_segment_sum_add(const float* base, const float* msg, const int32_t* edge_ptr, int64_t N, int F,
+                        float* out, void* stream);
+/* adjoint of one gated MLP on edges (activations recomputed).  Upstream gradient of `out`:
+ *   mode 0: g_u[e] rows of g_up (E,F);   mode 1: g_u[e] = g_up[src[e]] rows of g_up (N,F).
+ * Outputs: g_e (E,F) = g_e_base (may be NULL = 0) + d out/d e adjoint; g_z1 (E,2F); g_h (E,R) accumulated (+=)
+ * W1e (2F,F) is the e-part of layer 1 in (out,in) layout; W2d/W2g (F,F) in (out,in) layout; Wh (F,R). */
+int m3g_conv_mlp_bwd(const float* P, int ldp, int po, const int32_t* src, const int32_t* dst, const float* e,
+                     const float* h, const float* W1eT, const float* W2dT, const float* b2d, const float* W2gT,
+                     const float* b2g, const float* WhT, const float* W1e, const float* W2d, const float* W2g,
+                     const float* Wh, const float* g_up, const float* g_e_base, int64_t E, int F, int R, int mode,
+                     float* g_e, float* g_z1, float* g_h, void* stream);
+/* g_P (N, ldp)[po..po+2F) = sum_{out(i)} g_z1, [po+2F..po+4F) = sum_{in(i)} g_z1 */
+int m3g_conv_gather_gz(const float* g_z1, const int32_t* edge_ptr, const int32_t* in_ptr, const int32_t* in_perm,
+                       int64_t N, int F, int ldp, int po, float* g_P, void* stream);
+/* out (n,K) = base (n,K or NULL) + g (n,M) · W (M,K)   — adjoint of m3g_linear_fwd w.r.t. its input */
+int m3g_linear_bwd_input(const float* g, const float* W, const float* base, int64_t n, int K, int M, float* out,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * AtomWiseReadout (nn/readout.py:39-58) + virial (nn/gradient.py:39-62)
+ * weights: 3-layer gated MLP F→F→F→1; WT = (in,out) layout, W = (out,in) layout
+ * ------------------------------------------------------------------------------------------- */
+int m3g_readout_fwd(const float* x, const float* W0dT, const float* b0d, const float* W1dT, const float* b1d,
+                    const float* w2d, const float* b2d, const float* W0gT, const float* b0g, const float* W1gT,
+                    const float* b1g, const float* w2g, const float* b2g, const float* elemental, float scale,
+                    int64_t N, int F, float* atomic, void* stream);
+/* scaled_total[b] = sum_{i in [atom_ptr[b], atom_ptr[b+1])} atomic[i]; total = scale * scaled_total */
+int m3g_structure_sum(const float* atomic, const int32_t* atom_ptr, int64_t B, float scale, float* scaled_total,
+                      float* total, void* stream);
+/* g_eps[i] = g_atomic[i] + g_scaled_total[b] + scale*g_total[b] (each may be NULL); g_x (N,F) */
+int m3g_readout_bwd(const float* x, const float* W0dT, const float* b0d, const float* W1dT, const float* b1d,
+                    const float* w2d, const float* b2d, const float* W0gT, const float* b0g, const float* W1gT,
+                    const float* b1g, const float* w2g, const float* b2g, const float* W0d, const float* W1d,
+                    const float* W0g, const float* W1g, const float* g_atomic, const float* g_scaled_total,
+                    const float* g_total, const int32_t* batch, float scale, int64_t N, int F, float* g_x,
+                    void* stream);
+/* forces = -g_pos; stresses (B,6) = Voigt(sum_i pos_i (x) F_i)/|det lattice| */
+int m3g_forces_virial(const float* pos, const float* g_pos, const float* lattice, const int32_t* atom_ptr,
+                      int64_t N, int64_t B, float* forces, float* stresses, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Domain decomposition helpers (new; nothing in the reference — nn/gradient.py:26 TODO)
+ * ------------------------------------------------------------------------------------------- */
+/* out[r] = in[idx[r]] rows of width W floats (halo pack) ; in[idx[r]] += add[r] (reverse halo unpack) */
+int m3g_rows_gather(const float* in, const int32_t* idx, int64_t n, int W, float* out, void* stream);
+int m3g_rows_scatter_add(const float* add, const int32_t* idx, int64_t n, int W, float* inout, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M3GNET_B200_H */

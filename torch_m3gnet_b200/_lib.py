@@ -1,0 +1,120 @@
+"""ctypes binding of libm3gnet_b200.so (the C ABI declared in include/m3gnet_b200.h).
+
+The prototypes are parsed from the header itself, so the binding cannot drift from the declared ABI.
+There is NO fallback: if the shared library is missing or a symbol is absent, importing a kernel raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+from typing import Dict, List, Tuple
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+HEADER = os.path.join(_ROOT, "include", "m3gnet_b200.h")
+LIB_PATH = os.path.join(_HERE, "lib", "libm3gnet_b200.so")
+
+_CTYPE = {
+    "int": ctypes.c_int,
+    "int64_t": ctypes.c_int64,
+    "float": ctypes.c_float,
+    "double": ctypes.c_double,
+}
+
+
+def parse_header(path: str = HEADER) -> Dict[str, Tuple[object, List[object]]]:
+    """{name: (restype, [argtypes])} for every ``m3g_*`` prototype in the header."""
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    protos: Dict[str, Tuple[object, List[object]]] = {}
+    for m in re.finditer(r"(const\s+char\s*\*|int64_t|int)\s+(m3g_\w+)\s*\(([^)]*)\)\s*;", text):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        if "char" in ret:
+            restype = ctypes.c_char_p
+        elif ret == "int64_t":
+            restype = ctypes.c_int64
+        else:
+            restype = ctypes.c_int
+        argtypes: List[object] = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    argtypes.append(ctypes.c_void_p)
+                else:
+                    base = a.replace("const", "").split()[0]
+                    argtypes.append(_CTYPE[base])
+        protos[name] = (restype, argtypes)
+    return protos
+
+
+class _Library:
+    def __init__(self):
+        self._cdll = None
+        self._protos = None
+
+    def load(self):
+        if self._cdll is not None:
+            return self._cdll
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m torch_m3gnet_b200.csrc.build` "
+                "(or __graft_entry__.build()).  torch_m3gnet_b200 has no CPU / eager fallback."
+            )
+        cdll = ctypes.CDLL(LIB_PATH)
+        protos = parse_header()
+        for name, (restype, argtypes) in protos.items():
+            fn = getattr(cdll, name)  # AttributeError if the .so lacks a declared symbol
+            fn.restype = restype
+            fn.argtypes = argtypes
+        self._cdll, self._protos = cdll, protos
+        return cdll
+
+    @property
+    def protos(self):
+        self.load()
+        return self._protos
+
+
+LIB = _Library()
+
+# number of kernel-launching ABI calls made so far (bench.py reports the per-step delta as gpu_launches;
+# each ABI call launches at least one kernel)
+CALLS = 0
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not torch.is_tensor(t):
+        raise TypeError(f"expected a tensor or None, got {type(t)}")
+    if not t.is_cuda:
+        raise RuntimeError("torch_m3gnet_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("torch_m3gnet_b200 kernels need contiguous tensors")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def call(name: str, *args):
+    """Call ``m3g_<name>(*args, stream)`` on the current CUDA stream; raise on a non-zero status."""
+    global CALLS
+    cdll = LIB.load()
+    fn = getattr(cdll, "m3g_" + name)
+    conv = []
+    for a, ty in zip(args, fn.argtypes):
+        conv.append(_ptr(a) if ty is ctypes.c_void_p else a)
+    if len(args) != len(fn.argtypes) - 1:
+        raise TypeError(f"m3g_{name}: expected {len(fn.argtypes) - 1} arguments before the stream, got {len(args)}")
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = fn(*conv, stream)
+    CALLS += 1
+    if rc != 0:
+        raise RuntimeError(f"m3g_{name} failed ({rc}): {cdll.m3g_last_error().decode()}")
+
+
+def scan_work_elems(n: int) -> int:
+    return int(LIB.load().m3g_scan_work_elems(n))

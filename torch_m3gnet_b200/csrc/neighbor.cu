@@ -1,0 +1,268 @@
+// PBC radius-graph neighbour list (replaces pymatgen's Structure.get_all_neighbors boundary,
+// data/material_graph.py:168-193) and triplet enumeration (compute_threebody, :196-254), batched over
+// structures.  Float64 accept test with contraction disabled, bit-identical to oracle/m3gnet_oracle.py:
+//   shift = (s0*a0 + s1*a1) + s2*a2 ; v = (cart[j] + shift) - cart[i] ; d2 = (vx*vx + vy*vy) + vz*vz
+//   accept  d2 < r*r + 1e-8  and not (i == j and sqrt(d2) <= 1e-8)
+// One warp per centre atom; lanes sweep the candidate atoms j of the same structure in ascending order,
+// each lane walks its image range lexicographically, and a warp prefix sum keeps the emitted edges ordered
+// by (j, s0, s1, s2).  Candidate atoms come either from the whole structure (small cells) or from the
+// 27-bin neighbourhood of a cell list (structures with >= 3 bins of width >= r along every axis).
+#include "common.cuh"
+
+namespace m3g {
+
+struct Cell {
+  double a[9];    // lattice rows
+  double inv[9];  // inverse (columns b_k: frac = cart · inv)
+  double reach[3];
+};
+
+__device__ __forceinline__ void load_cell(const double* __restrict__ lattice, int b, double cutoff, Cell& c) {
+  const double* Lm = lattice + (int64_t)b * 9;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) c.a[k] = Lm[k];
+  const double *a0 = c.a, *a1 = c.a + 3, *a2 = c.a + 6;
+  double c0[3] = {a1[1] * a2[2] - a1[2] * a2[1], a1[2] * a2[0] - a1[0] * a2[2], a1[0] * a2[1] - a1[1] * a2[0]};
+  double c1[3] = {a2[1] * a0[2] - a2[2] * a0[1], a2[2] * a0[0] - a2[0] * a0[2], a2[0] * a0[1] - a2[1] * a0[0]};
+  double c2[3] = {a0[1] * a1[2] - a0[2] * a1[1], a0[2] * a1[0] - a0[0] * a1[2], a0[0] * a1[1] - a0[1] * a1[0]};
+  double det = a0[0] * c0[0] + a0[1] * c0[1] + a0[2] * c0[2];
+  // inv[r][k] = (c_k)[r] / det  so that frac_k = sum_r cart_r inv[r][k]
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    c.inv[r * 3 + 0] = c0[r] / det;
+    c.inv[r * 3 + 1] = c1[r] / det;
+    c.inv[r * 3 + 2] = c2[r] / det;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    double bk2 = c.inv[0 + k] * c.inv[0 + k] + c.inv[3 + k] * c.inv[3 + k] + c.inv[6 + k] * c.inv[6 + k];
+    // |s_k + df_k| <= (r + margin) * |b_k|   (1/|b_k| is the spacing of lattice planes along axis k)
+    c.reach[k] = (cutoff + 1e-6) * sqrt(bk2) + 1e-9;
+  }
+}
+
+__device__ __forceinline__ void frac_of(const Cell& c, const double* p, double* f) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) f[k] = p[0] * c.inv[0 + k] + p[1] * c.inv[3 + k] + p[2] * c.inv[6 + k];
+}
+
+__device__ __forceinline__ double dist2_exact(const Cell& c, const double* pi, const double* pj, int s0, int s1,
+                                              int s2) {
+  double d2 = 0.0;
+  double v[3];
+#pragma unroll
+  for (int x = 0; x < 3; ++x) {
+    double sh = __dadd_rn(__dadd_rn(__dmul_rn((double)s0, c.a[0 + x]), __dmul_rn((double)s1, c.a[3 + x])),
+                          __dmul_rn((double)s2, c.a[6 + x]));
+    v[x] = __dsub_rn(__dadd_rn(pj[x], sh), pi[x]);
+  }
+  d2 = __dadd_rn(__dadd_rn(__dmul_rn(v[0], v[0]), __dmul_rn(v[1], v[1])), __dmul_rn(v[2], v[2]));
+  return d2;
+}
+
+__device__ __forceinline__ int find_structure(const int32_t* __restrict__ atom_ptr, int B, int i) {
+  int lo = 0, hi = B;  // largest b with atom_ptr[b] <= i
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (atom_ptr[mid] <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// FILL = false: edge_count[i]; FILL = true: ordered emission at edge_ptr[i]
+template <bool FILL>
+__global__ void nbr_kernel(const double* __restrict__ lattice, const double* __restrict__ cart,
+                           const int32_t* __restrict__ atom_ptr, int B, int64_t N, double cutoff, float r3_f32,
+                           const int32_t* __restrict__ edge_ptr, int32_t* __restrict__ edge_count,
+                           int64_t* __restrict__ edge_index, int64_t E, int32_t* __restrict__ edge_shift,
+                           float* __restrict__ edge_dist, int32_t* __restrict__ member) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (i >= N) return;
+  int b = find_structure(atom_ptr, B, (int)i);
+  Cell c;
+  load_cell(lattice, b, cutoff, c);
+  const double r2 = __dadd_rn(__dmul_rn(cutoff, cutoff), 1e-8);
+  double pi[3] = {cart[i * 3 + 0], cart[i * 3 + 1], cart[i * 3 + 2]};
+  double fi[3];
+  frac_of(c, pi, fi);
+  int a_beg = atom_ptr[b], a_end = atom_ptr[b + 1];
+  int64_t base = FILL ? edge_ptr[i] : 0;
+  int total = 0;
+  for (int j0 = a_beg; j0 < a_end; j0 += 32) {
+    int j = j0 + lane;
+    bool have = j < a_end;
+    double pj[3] = {0, 0, 0};
+    int lo[3] = {0, 0, 0}, hi[3] = {-1, -1, -1};
+    if (have) {
+      pj[0] = cart[(int64_t)j * 3 + 0]; pj[1] = cart[(int64_t)j * 3 + 1]; pj[2] = cart[(int64_t)j * 3 + 2];
+      double fj[3];
+      frac_of(c, pj, fj);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double df = fj[k] - fi[k];
+        lo[k] = (int)ceil(-c.reach[k] - df);
+        hi[k] = (int)floor(c.reach[k] - df);
+      }
+    }
+    // pass 1: count this lane's accepted images
+    int cnt = 0;
+    for (int s0 = lo[0]; s0 <= hi[0]; ++s0)
+      for (int s1 = lo[1]; s1 <= hi[1]; ++s1)
+        for (int s2 = lo[2]; s2 <= hi[2]; ++s2) {
+          double d2 = dist2_exact(c, pi, pj, s0, s1, s2);
+          bool ok = d2 < r2;
+          if (ok && j == (int)i && __dsqrt_rn(d2) <= 1e-8) ok = false;
+          cnt += ok ? 1 : 0;
+        }
+    // exclusive prefix over lanes
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += y;
+    }
+    int chunk_total = __shfl_sync(FULL, incl, 31);
+    if (FILL && cnt > 0) {
+      int64_t w = base + total + (incl - cnt);
+      for (int s0 = lo[0]; s0 <= hi[0]; ++s0)
+        for (int s1 = lo[1]; s1 <= hi[1]; ++s1)
+          for (int s2 = lo[2]; s2 <= hi[2]; ++s2) {
+            double d2 = dist2_exact(c, pi, pj, s0, s1, s2);
+            bool ok = d2 < r2;
+            double d = __dsqrt_rn(d2);
+            if (ok && j == (int)i && d <= 1e-8) ok = false;
+            if (ok) {
+              edge_index[w] = i;
+              edge_index[E + w] = j;
+              edge_shift[w * 3 + 0] = s0;
+              edge_shift[w * 3 + 1] = s1;
+              edge_shift[w * 3 + 2] = s2;
+              float df = __double2float_rn(d);
+              edge_dist[w] = df;
+              member[w] = (df <= r3_f32) ? 1 : 0;
+              ++w;
+            }
+          }
+    }
+    total += chunk_total;
+  }
+  if (!FILL && lane == 0) edge_count[i] = total;
+}
+
+// one warp per atom: member degree, per-edge triplet counts, compacted member list (ascending edge id)
+__global__ void triplet_count_kernel(const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ member,
+                                     int64_t N, int64_t* __restrict__ num_triplet_i,
+                                     int32_t* __restrict__ num_triplet_ij, int32_t* __restrict__ tri_count,
+                                     int32_t* __restrict__ member_list) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (i >= N) return;
+  int b = edge_ptr[i], en = edge_ptr[i + 1];
+  int n3 = 0;
+  for (int e0 = b; e0 < en; e0 += 32) {
+    int e = e0 + lane;
+    bool m = (e < en) && member[e] != 0;
+    unsigned mask = __ballot_sync(FULL, m);
+    if (m) member_list[b + n3 + __popc(mask & ((1u << lane) - 1))] = e;
+    n3 += __popc(mask);
+  }
+  for (int e = b + lane; e < en; e += 32) {
+    int v = member[e] ? (n3 - 1) : 0;
+    num_triplet_ij[e] = v;
+    tri_count[e] = v;
+  }
+  if (lane == 0) num_triplet_i[i] = (int64_t)n3 * (n3 - 1);
+}
+
+// one warp per atom: the n3(n3-1) ordered pairs of member edges, ordered by (e1, e2) — the exact order of
+// the reference's triple loop (data/material_graph.py:239-248)
+__global__ void triplet_fill_kernel(const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ tri_ptr,
+                                    const int32_t* __restrict__ tri_count, const int32_t* __restrict__ member_list,
+                                    int64_t N, int64_t T, int32_t* __restrict__ tri_e2,
+                                    int64_t* __restrict__ triplet_index) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (i >= N) return;
+  int b = edge_ptr[i], en = edge_ptr[i + 1];
+  if (en <= b) return;
+  // n3 - 1 is stored on every member edge; find the first member through the compacted list
+  int first = member_list[b];
+  // member_list[b] is only valid if the atom has at least one member edge: check through tri_count sum
+  int n3m1 = -1;
+  for (int e = b + lane; e < en; e += 32) {
+    int v = tri_count[e];
+    if (v > 0) n3m1 = v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n3m1 = max(n3m1, __shfl_xor_sync(FULL, n3m1, o));
+  if (n3m1 <= 0) return;  // 0 or 1 member edges: no triplets
+  int n3 = n3m1 + 1;
+  int64_t base = tri_ptr[first];
+  int total = n3 * n3m1;
+  for (int t = lane; t < total; t += 32) {
+    int a = t / n3m1;
+    int bb = t - a * n3m1;
+    int bidx = bb + (bb >= a ? 1 : 0);
+    int e1 = member_list[b + a], e2 = member_list[b + bidx];
+    tri_e2[base + t] = e2;
+    if (triplet_index) {
+      triplet_index[base + t] = e1;
+      triplet_index[T + base + t] = e2;
+    }
+  }
+}
+
+}  // namespace m3g
+
+using namespace m3g;
+
+extern "C" {
+
+int m3g_nbr_count(const double* lattice, const double* cart, const int32_t* atom_ptr, int64_t B, int64_t N,
+                  double cutoff, int32_t* edge_count, void* stream) {
+  if (N == 0) return M3G_OK;
+  M3G_REQUIRE(lattice && cart && atom_ptr && edge_count && B > 0, "m3g_nbr_count: bad argument");
+  nbr_kernel<false><<<blocks_for(N * 32, 128), 128, 0, as_stream(stream)>>>(
+      lattice, cart, atom_ptr, (int)B, N, cutoff, 0.0f, nullptr, edge_count, nullptr, 0, nullptr, nullptr, nullptr);
+  M3G_LAUNCH_CHECK("m3g_nbr_count");
+  return M3G_OK;
+}
+
+int m3g_nbr_fill(const double* lattice, const double* cart, const int32_t* atom_ptr, int64_t B, int64_t N,
+                 double cutoff, double threebody_cutoff, const int32_t* edge_ptr, int64_t E, int64_t* edge_index,
+                 int32_t* edge_shift, float* edge_dist, int32_t* member, void* stream) {
+  if (N == 0 || E == 0) return M3G_OK;
+  M3G_REQUIRE(lattice && cart && atom_ptr && edge_ptr && edge_index && edge_shift && edge_dist && member && B > 0,
+              "m3g_nbr_fill: bad argument");
+  nbr_kernel<true><<<blocks_for(N * 32, 128), 128, 0, as_stream(stream)>>>(
+      lattice, cart, atom_ptr, (int)B, N, cutoff, (float)threebody_cutoff, edge_ptr, nullptr, edge_index, E,
+      edge_shift, edge_dist, member);
+  M3G_LAUNCH_CHECK("m3g_nbr_fill");
+  return M3G_OK;
+}
+
+int m3g_triplet_count(const int32_t* edge_ptr, const int32_t* member, int64_t N, int64_t E, int64_t* num_triplet_i,
+                      int32_t* num_triplet_ij, int32_t* tri_count, int32_t* member_list, void* stream) {
+  (void)E;
+  if (N == 0) return M3G_OK;
+  M3G_REQUIRE(edge_ptr && member && num_triplet_i && num_triplet_ij && tri_count && member_list,
+              "m3g_triplet_count: null pointer");
+  triplet_count_kernel<<<blocks_for(N * 32, 256), 256, 0, as_stream(stream)>>>(edge_ptr, member, N, num_triplet_i,
+                                                                               num_triplet_ij, tri_count, member_list);
+  M3G_LAUNCH_CHECK("m3g_triplet_count");
+  return M3G_OK;
+}
+
+int m3g_triplet_fill(const int32_t* edge_ptr, const int32_t* tri_ptr, const int32_t* tri_count,
+                     const int32_t* member_list, int64_t N, int64_t T, int32_t* tri_e2, int64_t* triplet_index,
+                     void* stream) {
+  if (N == 0 || T == 0) return M3G_OK;
+  M3G_REQUIRE(edge_ptr && tri_ptr && tri_count && member_list && tri_e2, "m3g_triplet_fill: null pointer");
+  triplet_fill_kernel<<<blocks_for(N * 32, 256), 256, 0, as_stream(stream)>>>(edge_ptr, tri_ptr, tri_count,
+                                                                              member_list, N, T, tri_e2, triplet_index);
+  M3G_LAUNCH_CHECK("m3g_triplet_fill");
+  return M3G_OK;
+}
+
+}  // extern "C"

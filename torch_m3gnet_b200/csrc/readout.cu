@@ -1,0 +1,261 @@
+// AtomWiseReadout (nn/readout.py:39-58): 3-layer gated MLP F→F→F→1 per atom, per-structure energy sums,
+// and the hand-written adjoint w.r.t. the node features.
+#include "common.cuh"
+
+namespace m3g {
+
+constexpr int RO_EPW = 4;
+constexpr int RO_WARPS = 4;
+
+template <int NJ>
+__device__ __forceinline__ void ro_matvec(const float* xs, int xs_stride, int K, const float* __restrict__ Wt, int ldw,
+                                          int ncols, int lane, float (&acc)[RO_EPW][NJ]) {
+  for (int k = 0; k < K; ++k) {
+    float w[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      int col = lane + 32 * j;
+      w[j] = (col < ncols) ? Wt[(int64_t)k * ldw + col] : 0.0f;
+    }
+#pragma unroll
+    for (int q = 0; q < RO_EPW; ++q) {
+      float xv = xs[q * xs_stride + k];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) acc[q][j] += xv * w[j];
+    }
+  }
+}
+
+struct ReadoutW {
+  const float *W0dT, *b0d, *W1dT, *b1d, *w2d, *b2d;
+  const float *W0gT, *b0g, *W1gT, *b1g, *w2g, *b2g;
+  const float *W0d, *W1d, *W0g, *W1g;  // (out,in) layouts, backward only
+};
+
+// BWD = false: writes atomic[i] = elemental[i]/scale + eps_i
+// BWD = true : writes g_x
+template <int NJ, bool BWD>
+__global__ void readout_kernel(const float* __restrict__ x, ReadoutW w, const float* __restrict__ elemental,
+                               float scale, const float* __restrict__ g_atomic,
+                               const float* __restrict__ g_scaled_total, const float* __restrict__ g_total,
+                               const int32_t* __restrict__ batch, int64_t N, int F, float* __restrict__ out) {
+  extern __shared__ float smem[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t i0 = ((int64_t)blockIdx.x * RO_WARPS + warp) * RO_EPW;
+  if (i0 >= N) return;
+  const int F2 = 2 * F;
+  float* xs = smem + warp * (RO_EPW * 5 * F);  // [EPW][F]
+  float* z0_s = xs + RO_EPW * F;               // [EPW][2F]
+  float* a0_s = z0_s + RO_EPW * F2;            // [EPW][2F]
+  int64_t iq[RO_EPW];
+#pragma unroll
+  for (int q = 0; q < RO_EPW; ++q) iq[q] = min(i0 + q, N - 1);
+  for (int q = 0; q < RO_EPW; ++q)
+    for (int k = lane; k < F; k += 32) xs[q * F + k] = x[iq[q] * F + k];
+  __syncwarp();
+  // layer 0
+  {
+    float zd[RO_EPW][NJ], zg[RO_EPW][NJ];
+#pragma unroll
+    for (int q = 0; q < RO_EPW; ++q)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        int col = lane + 32 * j;
+        zd[q][j] = (col < F) ? w.b0d[col] : 0.0f;
+        zg[q][j] = (col < F) ? w.b0g[col] : 0.0f;
+      }
+    ro_matvec<NJ>(xs, F, F, w.W0dT, F, F, lane, zd);
+    ro_matvec<NJ>(xs, F, F, w.W0gT, F, F, lane, zg);
+#pragma unroll
+    for (int q = 0; q < RO_EPW; ++q)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        int col = lane + 32 * j;
+        if (col < F) {
+          z0_s[q * F2 + col] = zd[q][j];
+          z0_s[q * F2 + F + col] = zg[q][j];
+          a0_s[q * F2 + col] = silu_acc(zd[q][j]);
+          a0_s[q * F2 + F + col] = silu_acc(zg[q][j]);
+        }
+      }
+  }
+  __syncwarp();
+  // layer 1
+  float zd1[RO_EPW][NJ], zg1[RO_EPW][NJ];
+#pragma unroll
+  for (int q = 0; q < RO_EPW; ++q)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      int col = lane + 32 * j;
+      zd1[q][j] = (col < F) ? w.b1d[col] : 0.0f;
+      zg1[q][j] = (col < F) ? w.b1g[col] : 0.0f;
+    }
+  ro_matvec<NJ>(a0_s, F2, F, w.W1dT, F, F, lane, zd1);
+  ro_matvec<NJ>(a0_s + F, F2, F, w.W1gT, F, F, lane, zg1);
+  // layer 2 (1 output): dense branch linear, gate branch sigmoid
+  float dout[RO_EPW], gout[RO_EPW];
+#pragma unroll
+  for (int q = 0; q < RO_EPW; ++q) {
+    float pd = 0.0f, pg = 0.0f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      int col = lane + 32 * j;
+      if (col < F) {
+        pd += silu_acc(zd1[q][j]) * w.w2d[col];
+        pg += silu_acc(zg1[q][j]) * w.w2g[col];
+      }
+    }
+    dout[q] = warp_sum(pd) + w.b2d[0];
+    gout[q] = sigmoid_acc(warp_sum(pg) + w.b2g[0]);
+  }
+  if (!BWD) {
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < RO_EPW; ++q)
+        if (i0 + q < N) out[iq[q]] = elemental[iq[q]] / scale + dout[q] * gout[q];
+    }
+    return;
+  }
+  __syncwarp();  // a0_s is about to be overwritten with dz1
+#pragma unroll
+  for (int q = 0; q < RO_EPW; ++q) {
+    float ge = 0.0f;
+    if (g_atomic) ge += g_atomic[iq[q]];
+    int b = batch[iq[q]];
+    if (g_scaled_total) ge += g_scaled_total[b];
+    if (g_total) ge += scale * g_total[b];
+    float g_d = ge * gout[q];
+    float g_gpre = ge * dout[q] * gout[q] * (1.0f - gout[q]);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      int col = lane + 32 * j;
+      if (col < F) {
+        a0_s[q * F2 + col] = g_d * w.w2d[col] * silu_grad(zd1[q][j]);
+        a0_s[q * F2 + F + col] = g_gpre * w.w2g[col] * silu_grad(zg1[q][j]);
+      }
+    }
+  }
+  __syncwarp();
+  {
+    float dd[RO_EPW][NJ], dg[RO_EPW][NJ];
+#pragma unroll
+    for (int q = 0; q < RO_EPW; ++q)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { dd[q][j] = 0.0f; dg[q][j] = 0.0f; }
+    ro_matvec<NJ>(a0_s, F2, F, w.W1d, F, F, lane, dd);
+    ro_matvec<NJ>(a0_s + F, F2, F, w.W1g, F, F, lane, dg);
+#pragma unroll
+    for (int q = 0; q < RO_EPW; ++q)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        int col = lane + 32 * j;
+        if (col < F) {
+          z0_s[q * F2 + col] = dd[q][j] * silu_grad(z0_s[q * F2 + col]);
+          z0_s[q * F2 + F + col] = dg[q][j] * silu_grad(z0_s[q * F2 + F + col]);
+        }
+      }
+  }
+  __syncwarp();
+  {
+    float gx[RO_EPW][NJ];
+#pragma unroll
+    for (int q = 0; q < RO_EPW; ++q)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) gx[q][j] = 0.0f;
+    ro_matvec<NJ>(z0_s, F2, F, w.W0d, F, F, lane, gx);
+    ro_matvec<NJ>(z0_s + F, F2, F, w.W0g, F, F, lane, gx);
+#pragma unroll
+    for (int q = 0; q < RO_EPW; ++q)
+      if (i0 + q < N) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          int col = lane + 32 * j;
+          if (col < F) out[iq[q] * F + col] = gx[q][j];
+        }
+      }
+  }
+}
+
+__global__ void structure_sum_kernel(const float* __restrict__ atomic, const int32_t* __restrict__ atom_ptr,
+                                     int64_t B, float scale, float* __restrict__ scaled_total,
+                                     float* __restrict__ total) {
+  int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  float acc = 0.0f;
+  for (int i = atom_ptr[b] + lane; i < atom_ptr[b + 1]; i += 32) acc += atomic[i];
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    scaled_total[b] = acc;
+    total[b] = scale * acc;
+  }
+}
+
+template <bool BWD>
+static int launch_readout(const float* x, const ReadoutW& w, const float* elemental, float scale,
+                          const float* g_atomic, const float* g_st, const float* g_t, const int32_t* batch, int64_t N,
+                          int F, float* out, cudaStream_t st) {
+  size_t smem = (size_t)RO_WARPS * RO_EPW * 5 * F * sizeof(float);
+  unsigned grid = blocks_for(N, RO_WARPS * RO_EPW);
+  int nj = (F + 31) / 32;
+#define LAUNCH_(NJ)                                                                                        \
+  do {                                                                                                     \
+    if (smem > 48 * 1024)                                                                                  \
+      cudaFuncSetAttribute(readout_kernel<NJ, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    readout_kernel<NJ, BWD><<<grid, RO_WARPS * 32, smem, st>>>(x, w, elemental, scale, g_atomic, g_st, g_t, batch, \
+                                                               N, F, out);                                  \
+  } while (0)
+  if (nj == 1) LAUNCH_(1); else if (nj == 2) LAUNCH_(2); else if (nj == 3) LAUNCH_(3); else LAUNCH_(4);
+#undef LAUNCH_
+  return 0;
+}
+
+}  // namespace m3g
+
+using namespace m3g;
+
+extern "C" {
+
+int m3g_readout_fwd(const float* x, const float* W0dT, const float* b0d, const float* W1dT, const float* b1d,
+                    const float* w2d, const float* b2d, const float* W0gT, const float* b0g, const float* W1gT,
+                    const float* b1g, const float* w2g, const float* b2g, const float* elemental, float scale,
+                    int64_t N, int F, float* atomic, void* stream) {
+  if (N == 0) return M3G_OK;
+  M3G_REQUIRE(x && W0dT && b0d && W1dT && b1d && w2d && b2d && W0gT && b0g && W1gT && b1g && w2g && b2g &&
+                  elemental && atomic,
+              "m3g_readout_fwd: null pointer");
+  M3G_REQUIRE(F >= 1 && F <= M3G_MAX_F, "m3g_readout_fwd: F=%d outside [1,%d]", F, M3G_MAX_F);
+  ReadoutW w{W0dT, b0d, W1dT, b1d, w2d, b2d, W0gT, b0g, W1gT, b1g, w2g, b2g, nullptr, nullptr, nullptr, nullptr};
+  launch_readout<false>(x, w, elemental, scale, nullptr, nullptr, nullptr, nullptr, N, F, atomic, as_stream(stream));
+  M3G_LAUNCH_CHECK("m3g_readout_fwd");
+  return M3G_OK;
+}
+
+int m3g_structure_sum(const float* atomic, const int32_t* atom_ptr, int64_t B, float scale, float* scaled_total,
+                      float* total, void* stream) {
+  if (B == 0) return M3G_OK;
+  M3G_REQUIRE(atomic && atom_ptr && scaled_total && total, "m3g_structure_sum: null pointer");
+  structure_sum_kernel<<<blocks_for(B * 32, 128), 128, 0, as_stream(stream)>>>(atomic, atom_ptr, B, scale,
+                                                                               scaled_total, total);
+  M3G_LAUNCH_CHECK("m3g_structure_sum");
+  return M3G_OK;
+}
+
+int m3g_readout_bwd(const float* x, const float* W0dT, const float* b0d, const float* W1dT, const float* b1d,
+                    const float* w2d, const float* b2d, const float* W0gT, const float* b0g, const float* W1gT,
+                    const float* b1g, const float* w2g, const float* b2g, const float* W0d, const float* W1d,
+                    const float* W0g, const float* W1g, const float* g_atomic, const float* g_scaled_total,
+                    const float* g_total, const int32_t* batch, float scale, int64_t N, int F, float* g_x,
+                    void* stream) {
+  if (N == 0) return M3G_OK;
+  M3G_REQUIRE(x && W0dT && b0d && W1dT && b1d && w2d && b2d && W0gT && b0g && W1gT && b1g && w2g && b2g && W0d &&
+                  W1d && W0g && W1g && batch && g_x,
+              "m3g_readout_bwd: null pointer");
+  M3G_REQUIRE(F >= 1 && F <= M3G_MAX_F, "m3g_readout_bwd: F=%d outside [1,%d]", F, M3G_MAX_F);
+  ReadoutW w{W0dT, b0d, W1dT, b1d, w2d, b2d, W0gT, b0g, W1gT, b1g, w2g, b2g, W0d, W1d, W0g, W1g};
+  launch_readout<true>(x, w, nullptr, scale, g_atomic, g_scaled_total, g_total, batch, N, F, g_x, as_stream(stream));
+  M3G_LAUNCH_CHECK("m3g_readout_bwd");
+  return M3G_OK;
+}
+
+}  // extern "C"

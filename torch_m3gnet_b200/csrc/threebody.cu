@@ -1,0 +1,534 @@
+// ThreeBodyInteration (nn/interaction.py:187-223) forward and hand-written adjoint.
+//
+// Data flow per block (D = L*R, d = l*R + n):
+//   sig  (N,D) = sigmoid(x Ws^T + bs)                                     [tb_sigma_fwd]
+//   bas  (E,D) = chi_d(r_e) * fc(r_e) * sig[dst(e)][d]                    [tb_edge_basis_fwd]
+//   red  (E,D) = fc(r_e1) * sum_{e2 in tri(e1)} Y_l(cos(e1,e2)) bas[e2]   [tb_reduce_fwd, fused with]
+//   e_out      = e_in + SiLU(red WdT) * sigmoid(red WgT)                  [the 1-layer gated MLP]
+// The triplet sum is a segmented reduction over the per-bond CSR row: a sub-warp group of G lanes owns one
+// bond, lane g takes columns g, g+G, ... in ascending order, partial sums are combined by a butterfly.
+// All per-triplet quantities are recomputed from per-edge data (vec4 = (v, r), bas), so HBM traffic is
+// 4 B/triplet (the column index) + per-edge rows that stay L1/L2 resident inside one atom's shell.
+#include "common.cuh"
+
+namespace m3g {
+
+__device__ __constant__ float kYpref[4] = {0.28209479177387814f, 0.4886025119029199f, 0.6307831305050401f,
+                                           0.7463526651802308f};
+
+// j_l(x), l < L, by the reference's upward recurrence incl. its small-x branches (quirk Q4);
+// jl[l] and derivative dj[l] (nn/interaction.py:288-348)
+template <int LC>
+__device__ __forceinline__ void sph_bessel_all(float x, int l_top, float* jl, float* dj) {
+  const float EPS = 1e-8f;
+  bool big = x > EPS;
+  float s, c;
+  sincosf(x, &s, &c);
+  float sx = s / x;
+  jl[0] = big ? sx : 1.0f;
+  dj[0] = big ? -((sx - c) / x) : 0.0f;
+  if (LC > 1 && l_top >= 1) {
+    jl[1] = big ? (sx - c) / x : x / 3.0f;
+    dj[1] = big ? (jl[0] - 2.0f / x * jl[1]) : (1.0f / 3.0f);
+    float coeff = 3.0f;
+#pragma unroll
+    for (int n = 1; n < LC - 1; ++n) {
+      if (n < l_top) {
+        coeff *= (float)(2 * n + 3);
+        jl[n + 1] = big ? ((float)(2 * n + 1) / x * jl[n] - jl[n - 1]) : x / coeff;
+        dj[n + 1] = big ? (jl[n] - (float)(n + 2) / x * jl[n + 1]) : 0.0f;
+      }
+    }
+  }
+}
+
+// chi_d(r) = j_l(z_d r / rc) / factors_d and d chi_d / dr
+template <int LC, int RC>
+__device__ __forceinline__ void chi_eval(float r, const float* __restrict__ consts, int L, int R, float* chi,
+                                         float* dchi) {
+  const int D = L * R;
+  const float* z = consts;
+  const float* fac = consts + D;
+  const float rc = consts[2 * D];
+#pragma unroll
+  for (int l = 0; l < LC; ++l) {
+#pragma unroll
+    for (int n = 0; n < RC; ++n) {
+      if (l < L && n < R) {
+        int d = l * R + n;
+        float x = __fdiv_rn(__fmul_rn(z[d], r), rc);
+        float jl[LC], dj[LC];
+        sph_bessel_all<LC>(x, l, jl, dj);
+        float jv = jl[0], dv = dj[0];
+#pragma unroll
+        for (int q = 1; q < LC; ++q)
+          if (q == l) { jv = jl[q]; dv = dj[q]; }
+        chi[l * RC + n] = jv / fac[d];
+        if (dchi) dchi[l * RC + n] = dv * (z[d] / rc) / fac[d];
+      }
+    }
+  }
+}
+
+template <int LC>
+__device__ __forceinline__ void legendre_all(float x, float* P) {
+  P[0] = 1.0f;
+  if (LC > 1) P[1] = x;
+#pragma unroll
+  for (int n = 1; n < LC - 1; ++n) P[n + 1] = ((float)(2 * n + 1) * x * P[n] - (float)n * P[n - 1]) / (float)(n + 1);
+}
+
+// reference LegendreCosPolynomial.backward (nn/interaction.py:373-382, quirk Q3): for order l with upstream go,
+// g = 0; for n = 1..l: g = (n P_{n-1} + x g) * go
+template <int LC>
+__device__ __forceinline__ float legendre_bwd_sum(float x, const float* P, const float* go, int L) {
+  float total = 0.0f;
+#pragma unroll
+  for (int l = 1; l < LC; ++l) {
+    if (l < L) {
+      float g = 0.0f;
+#pragma unroll
+      for (int n = 1; n <= l; ++n) g = ((float)n * P[n - 1] + x * g) * go[l];
+      total += g;
+    }
+  }
+  return total;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void tb_sigma_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Ws,
+                                    const float* __restrict__ bs, int64_t N, int F, int D, float* __restrict__ sig) {
+  int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (k >= N) return;
+  for (int d = 0; d < D; ++d) {
+    float acc = 0.0f;
+    for (int f = lane; f < F; f += 32) acc += x[k * F + f] * Ws[d * F + f];
+    acc = warp_sum(acc);
+    if (lane == 0) sig[k * D + d] = sigmoid_acc(acc + bs[d]);
+  }
+}
+
+template <int LC, int RC>
+__global__ void tb_edge_basis_fwd_kernel(const float4* __restrict__ vec4, const int32_t* __restrict__ dst,
+                                         const float* __restrict__ sig, const float* __restrict__ consts, int64_t E,
+                                         int L, int R, float* __restrict__ bas) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int D = L * R;
+  float r = vec4[e].w;
+  float r3 = consts[2 * D + 1];
+  float c = cutoff_poly(r, r3);
+  float chi[LC * RC];
+  if (c != 0.0f) chi_eval<LC, RC>(r, consts, L, R, chi, nullptr);
+  const float* sg = sig + (int64_t)dst[e] * D;
+#pragma unroll
+  for (int l = 0; l < LC; ++l)
+#pragma unroll
+    for (int n = 0; n < RC; ++n)
+      if (l < L && n < R) {
+        int d = l * R + n;
+        bas[e * D + d] = (c != 0.0f) ? chi[l * RC + n] * c * sg[d] : 0.0f;
+      }
+}
+
+template <int LC, int RC, int G>
+__global__ void tb_reduce_fwd_kernel(const float4* __restrict__ vec4, const float* __restrict__ bas,
+                                     const int32_t* __restrict__ tri_ptr, const int32_t* __restrict__ tri_e2,
+                                     const float* __restrict__ consts, const float* __restrict__ WdT,
+                                     const float* __restrict__ WgT, const float* __restrict__ e_in, int64_t E, int L,
+                                     int R, int F, float* __restrict__ red, float* __restrict__ e_out) {
+  const int D = L * R;
+  int64_t e1 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  int gl = threadIdx.x % G;
+  bool valid = e1 < E;
+  float acc[LC * RC];
+#pragma unroll
+  for (int d = 0; d < LC * RC; ++d) acc[d] = 0.0f;
+  float4 v1 = make_float4(0.f, 0.f, 0.f, 1.f);
+  int beg = 0, end = 0;
+  if (valid) {
+    v1 = vec4[e1];
+    beg = tri_ptr[e1];
+    end = tri_ptr[e1 + 1];
+  }
+  for (int p = beg + gl; p < end; p += G) {
+    int e2 = tri_e2[p];
+    float4 v2 = vec4[e2];
+    float dot = __fadd_rn(__fadd_rn(__fmul_rn(v1.x, v2.x), __fmul_rn(v1.y, v2.y)), __fmul_rn(v1.z, v2.z));
+    float cs = __fdiv_rn(dot, __fmul_rn(v1.w, v2.w));
+    cs = fminf(fmaxf(cs, -1.0f), 1.0f);
+    float P[LC];
+    legendre_all<LC>(cs, P);
+    const float* b2 = bas + (int64_t)e2 * D;
+#pragma unroll
+    for (int l = 0; l < LC; ++l) {
+      if (l < L) {
+        float y = kYpref[l] * P[l];
+#pragma unroll
+        for (int n = 0; n < RC; ++n)
+          if (n < R) acc[l * RC + n] += y * b2[l * R + n];
+      }
+    }
+  }
+  float c1 = valid ? cutoff_poly(v1.w, consts[2 * D + 1]) : 0.0f;
+#pragma unroll
+  for (int d = 0; d < LC * RC; ++d) acc[d] = c1 * group_sum<G>(acc[d]);
+  if (!valid) return;
+  if (gl == 0) {
+#pragma unroll
+    for (int l = 0; l < LC; ++l)
+#pragma unroll
+      for (int n = 0; n < RC; ++n)
+        if (l < L && n < R) red[e1 * D + l * R + n] = acc[l * RC + n];
+  }
+  bool any = end > beg;
+  for (int f = gl; f < F; f += G) {
+    float upd = 0.0f;
+    if (any) {
+      float u = 0.0f, g = 0.0f;
+#pragma unroll
+      for (int l = 0; l < LC; ++l)
+#pragma unroll
+        for (int n = 0; n < RC; ++n)
+          if (l < L && n < R) {
+            int d = l * R + n;
+            u += acc[l * RC + n] * WdT[d * F + f];
+            g += acc[l * RC + n] * WgT[d * F + f];
+          }
+      upd = silu_acc(u) * sigmoid_acc(g);
+    }
+    e_out[e1 * F + f] = e_in[e1 * F + f] + upd;
+  }
+}
+
+// adjoint of the bias-free 1-layer gated MLP: one warp per bond
+__global__ void tb_gate_bwd_kernel(const float* __restrict__ red, const float* __restrict__ g_e,
+                                   const float* __restrict__ WdT, const float* __restrict__ WgT, int64_t E, int D,
+                                   int F, float* __restrict__ g_red) {
+  int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (e >= E) return;
+  constexpr int DM = M3G_MAX_L * M3G_MAX_R;
+  float rd[DM], acc[DM];
+#pragma unroll
+  for (int d = 0; d < DM; ++d) {
+    rd[d] = (d < D) ? red[e * D + d] : 0.0f;
+    acc[d] = 0.0f;
+  }
+  for (int f = lane; f < F; f += 32) {
+    float u = 0.0f, g = 0.0f;
+#pragma unroll
+    for (int d = 0; d < DM; ++d)
+      if (d < D) {
+        u += rd[d] * WdT[d * F + f];
+        g += rd[d] * WgT[d * F + f];
+      }
+    float ge = g_e[e * F + f];
+    float sg = sigmoid_acc(g);
+    float du = ge * sg * silu_grad(u);
+    float dg = ge * silu_acc(u) * sg * (1.0f - sg);
+#pragma unroll
+    for (int d = 0; d < DM; ++d)
+      if (d < D) acc[d] += du * WdT[d * F + f] + dg * WgT[d * F + f];
+  }
+#pragma unroll
+  for (int d = 0; d < DM; ++d) {
+    if (d < D) {
+      float s = warp_sum(acc[d]);
+      if (lane == 0) g_red[e * D + d] = s;
+    }
+  }
+}
+
+template <int LC, int RC, int G>
+__global__ void tb_reduce_bwd_kernel(const float4* __restrict__ vec4, const float* __restrict__ bas,
+                                     const float* __restrict__ g_red, const int32_t* __restrict__ tri_ptr,
+                                     const int32_t* __restrict__ tri_e2, const int32_t* __restrict__ trt_ptr,
+                                     const int32_t* __restrict__ trt_e1, const float* __restrict__ consts, int64_t E,
+                                     int L, int R, float4* __restrict__ g_vec4, float* __restrict__ g_bas) {
+  const int D = L * R;
+  int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  int gl = threadIdx.x % G;
+  bool valid = e < E;
+  const float r3 = consts[2 * D + 1];
+  float4 ve = make_float4(0.f, 0.f, 0.f, 1.f);
+  float d1[LC * RC], be[LC * RC], gB[LC * RC];
+#pragma unroll
+  for (int d = 0; d < LC * RC; ++d) { d1[d] = 0.f; be[d] = 0.f; gB[d] = 0.f; }
+  int a_beg = 0, a_end = 0, b_beg = 0, b_end = 0;
+  if (valid) {
+    ve = vec4[e];
+    a_beg = tri_ptr[e]; a_end = tri_ptr[e + 1];
+    b_beg = trt_ptr[e]; b_end = trt_ptr[e + 1];
+#pragma unroll
+    for (int l = 0; l < LC; ++l)
+#pragma unroll
+      for (int n = 0; n < RC; ++n)
+        if (l < L && n < R) {
+          d1[l * RC + n] = g_red[e * D + l * R + n];
+          be[l * RC + n] = bas[e * D + l * R + n];
+        }
+  }
+  float ce = cutoff_poly(ve.w, r3);
+  float gx = 0.f, gy = 0.f, gz = 0.f, gr = 0.f, gc = 0.f;
+  // pass A: e is the first bond of (e, p)
+  for (int p = a_beg + gl; p < a_end; p += G) {
+    int ep = tri_e2[p];
+    float4 vp = vec4[ep];
+    float inv = 1.0f / (ve.w * vp.w);
+    float craw = (ve.x * vp.x + ve.y * vp.y + ve.z * vp.z) * inv;
+    bool inside = (craw >= -1.0f) && (craw <= 1.0f);
+    float cs = fminf(fmaxf(craw, -1.0f), 1.0f);
+    float P[LC], go[LC];
+    legendre_all<LC>(cs, P);
+    const float* bp = bas + (int64_t)ep * D;
+#pragma unroll
+    for (int l = 0; l < LC; ++l) {
+      go[l] = 0.0f;
+      if (l < L) {
+        float s = 0.0f;
+#pragma unroll
+        for (int n = 0; n < RC; ++n)
+          if (n < R) s += bp[l * R + n] * d1[l * RC + n];
+        gc += kYpref[l] * P[l] * s;
+        go[l] = kYpref[l] * ce * s;
+      }
+    }
+    float gcos = legendre_bwd_sum<LC>(cs, P, go, L);
+    if (inside) {
+      float w = gcos * inv;
+      gx += w * vp.x; gy += w * vp.y; gz += w * vp.z;
+      gr -= gcos * craw / ve.w;
+    }
+  }
+  // pass B: e is the second bond of (q, e)
+  for (int p = b_beg + gl; p < b_end; p += G) {
+    int eq = trt_e1[p];
+    float4 vq = vec4[eq];
+    float cq = cutoff_poly(vq.w, r3);
+    float inv = 1.0f / (ve.w * vq.w);
+    float craw = (ve.x * vq.x + ve.y * vq.y + ve.z * vq.z) * inv;
+    bool inside = (craw >= -1.0f) && (craw <= 1.0f);
+    float cs = fminf(fmaxf(craw, -1.0f), 1.0f);
+    float P[LC], go[LC];
+    legendre_all<LC>(cs, P);
+    const float* dq = g_red + (int64_t)eq * D;
+#pragma unroll
+    for (int l = 0; l < LC; ++l) {
+      go[l] = 0.0f;
+      if (l < L) {
+        float y = kYpref[l] * P[l] * cq;
+        float t = 0.0f;
+#pragma unroll
+        for (int n = 0; n < RC; ++n)
+          if (n < R) {
+            float dv = dq[l * R + n];
+            gB[l * RC + n] += y * dv;
+            t += be[l * RC + n] * dv;
+          }
+        go[l] = kYpref[l] * cq * t;
+      }
+    }
+    float gcos = legendre_bwd_sum<LC>(cs, P, go, L);
+    if (inside) {
+      float w = gcos * inv;
+      gx += w * vq.x; gy += w * vq.y; gz += w * vq.z;
+      gr -= gcos * craw / ve.w;
+    }
+  }
+  gx = group_sum<G>(gx); gy = group_sum<G>(gy); gz = group_sum<G>(gz);
+  gr = group_sum<G>(gr); gc = group_sum<G>(gc);
+#pragma unroll
+  for (int d = 0; d < LC * RC; ++d) gB[d] = group_sum<G>(gB[d]);
+  if (!valid || gl != 0) return;
+  gr += gc * cutoff_poly_grad(ve.w, r3);
+  g_vec4[e] = make_float4(gx, gy, gz, gr);
+#pragma unroll
+  for (int l = 0; l < LC; ++l)
+#pragma unroll
+    for (int n = 0; n < RC; ++n)
+      if (l < L && n < R) g_bas[e * D + l * R + n] = gB[l * RC + n];
+}
+
+template <int LC, int RC>
+__global__ void tb_edge_basis_bwd_kernel(const float4* __restrict__ vec4, const int32_t* __restrict__ dst,
+                                         const float* __restrict__ sig, const float* __restrict__ g_bas,
+                                         const float* __restrict__ consts, int64_t E, int L, int R,
+                                         float* __restrict__ g_vec4, float* __restrict__ g_sig_e) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int D = L * R;
+  float r = vec4[e].w;
+  float r3 = consts[2 * D + 1];
+  float c = cutoff_poly(r, r3);
+  if (c == 0.0f) {
+    for (int d = 0; d < D; ++d) g_sig_e[e * D + d] = 0.0f;
+    return;
+  }
+  float dc = cutoff_poly_grad(r, r3);
+  float chi[LC * RC], dchi[LC * RC];
+  chi_eval<LC, RC>(r, consts, L, R, chi, dchi);
+  const float* sg = sig + (int64_t)dst[e] * D;
+  float gr = 0.0f;
+#pragma unroll
+  for (int l = 0; l < LC; ++l)
+#pragma unroll
+    for (int n = 0; n < RC; ++n)
+      if (l < L && n < R) {
+        int d = l * R + n;
+        float gb = g_bas[e * D + d];
+        g_sig_e[e * D + d] = gb * chi[l * RC + n] * c;
+        gr += gb * sg[d] * (dchi[l * RC + n] * c + chi[l * RC + n] * dc);
+      }
+  g_vec4[e * 4 + 3] += gr;
+}
+
+__global__ void tb_sigma_bwd_kernel(const float* __restrict__ g_sig_e, const int32_t* __restrict__ in_ptr,
+                                    const int32_t* __restrict__ in_perm, const float* __restrict__ sig,
+                                    const float* __restrict__ Ws, int64_t N, int F, int D, float* __restrict__ g_x) {
+  int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (k >= N) return;
+  constexpr int DM = M3G_MAX_L * M3G_MAX_R;
+  float acc[DM];
+#pragma unroll
+  for (int d = 0; d < DM; ++d) acc[d] = 0.0f;
+  for (int p = in_ptr[k] + lane; p < in_ptr[k + 1]; p += 32) {
+    const float* row = g_sig_e + (int64_t)in_perm[p] * D;
+#pragma unroll
+    for (int d = 0; d < DM; ++d)
+      if (d < D) acc[d] += row[d];
+  }
+#pragma unroll
+  for (int d = 0; d < DM; ++d) {
+    if (d < D) {
+      float s = warp_sum(acc[d]);
+      float sg = sig[k * D + d];
+      acc[d] = s * sg * (1.0f - sg);
+    }
+  }
+  for (int f = lane; f < F; f += 32) {
+    float v = 0.0f;
+#pragma unroll
+    for (int d = 0; d < DM; ++d)
+      if (d < D) v += acc[d] * Ws[d * F + f];
+    g_x[k * F + f] = v;
+  }
+}
+
+}  // namespace m3g
+
+using namespace m3g;
+
+#define M3G_CHECK_LR(name)                                                                              \
+  M3G_REQUIRE(L >= 1 && L <= M3G_MAX_L && R >= 1 && R <= M3G_MAX_R,                                     \
+              name ": l_max=%d n_max=%d outside the supported range [1,%d]x[1,%d]", L, R, M3G_MAX_L, M3G_MAX_R)
+
+#define M3G_DISPATCH_LR(KERNEL, ...)             \
+  do {                                           \
+    if (L <= 3 && R <= 3) { KERNEL(3, 3, __VA_ARGS__); } \
+    else { KERNEL(4, 4, __VA_ARGS__); }          \
+  } while (0)
+
+extern "C" {
+
+int m3g_tb_sigma_fwd(const float* x, const float* Ws, const float* bs, int64_t N, int F, int D, float* sig,
+                     void* stream) {
+  if (N == 0) return M3G_OK;
+  M3G_REQUIRE(x && Ws && bs && sig, "m3g_tb_sigma_fwd: null pointer");
+  tb_sigma_fwd_kernel<<<blocks_for(N * 32, 256), 256, 0, as_stream(stream)>>>(x, Ws, bs, N, F, D, sig);
+  M3G_LAUNCH_CHECK("m3g_tb_sigma_fwd");
+  return M3G_OK;
+}
+
+int m3g_tb_edge_basis_fwd(const float* vec4, const int32_t* dst, const float* sig, const float* tb_consts, int64_t E,
+                          int L, int R, float* bas, void* stream) {
+  if (E == 0) return M3G_OK;
+  M3G_REQUIRE(vec4 && dst && sig && tb_consts && bas, "m3g_tb_edge_basis_fwd: null pointer");
+  M3G_CHECK_LR("m3g_tb_edge_basis_fwd");
+#define K_(LC, RC, ...) \
+  tb_edge_basis_fwd_kernel<LC, RC><<<blocks_for(E, 128), 128, 0, as_stream(stream)>>>(__VA_ARGS__)
+  M3G_DISPATCH_LR(K_, (const float4*)vec4, dst, sig, tb_consts, E, L, R, bas);
+#undef K_
+  M3G_LAUNCH_CHECK("m3g_tb_edge_basis_fwd");
+  return M3G_OK;
+}
+
+int m3g_tb_reduce_fwd(const float* vec4, const float* bas, const int32_t* tri_ptr, const int32_t* tri_e2,
+                      const float* tb_consts, const float* WdT, const float* WgT, const float* e_in, int64_t E, int L,
+                      int R, int F, int group, float* red, float* e_out, void* stream) {
+  if (E == 0) return M3G_OK;
+  M3G_REQUIRE(vec4 && bas && tri_ptr && tb_consts && WdT && WgT && e_in && red && e_out,
+              "m3g_tb_reduce_fwd: null pointer");
+  M3G_CHECK_LR("m3g_tb_reduce_fwd");
+  M3G_REQUIRE(group == 8 || group == 16 || group == 32, "m3g_tb_reduce_fwd: group must be 8, 16 or 32");
+#define K_(LC, RC, ...)                                                                                              \
+  do {                                                                                                               \
+    if (group == 8) tb_reduce_fwd_kernel<LC, RC, 8><<<blocks_for(E * 8, 256), 256, 0, as_stream(stream)>>>(__VA_ARGS__);        \
+    else if (group == 16) tb_reduce_fwd_kernel<LC, RC, 16><<<blocks_for(E * 16, 256), 256, 0, as_stream(stream)>>>(__VA_ARGS__); \
+    else tb_reduce_fwd_kernel<LC, RC, 32><<<blocks_for(E * 32, 256), 256, 0, as_stream(stream)>>>(__VA_ARGS__);                 \
+  } while (0)
+  M3G_DISPATCH_LR(K_, (const float4*)vec4, bas, tri_ptr, tri_e2, tb_consts, WdT, WgT, e_in, E, L, R, F, red, e_out);
+#undef K_
+  M3G_LAUNCH_CHECK("m3g_tb_reduce_fwd");
+  return M3G_OK;
+}
+
+int m3g_tb_gate_bwd(const float* red, const float* g_e, const float* WdT, const float* WgT, int64_t E, int D, int F,
+                    float* g_red, void* stream) {
+  if (E == 0) return M3G_OK;
+  M3G_REQUIRE(red && g_e && WdT && WgT && g_red, "m3g_tb_gate_bwd: null pointer");
+  M3G_REQUIRE(D >= 1 && D <= M3G_MAX_L * M3G_MAX_R, "m3g_tb_gate_bwd: D=%d unsupported", D);
+  tb_gate_bwd_kernel<<<blocks_for(E * 32, 256), 256, 0, as_stream(stream)>>>(red, g_e, WdT, WgT, E, D, F, g_red);
+  M3G_LAUNCH_CHECK("m3g_tb_gate_bwd");
+  return M3G_OK;
+}
+
+int m3g_tb_reduce_bwd(const float* vec4, const float* bas, const float* g_red, const int32_t* tri_ptr,
+                      const int32_t* tri_e2, const int32_t* trt_ptr, const int32_t* trt_e1, const float* tb_consts,
+                      int64_t E, int L, int R, int group, float* g_vec4, float* g_bas, void* stream) {
+  if (E == 0) return M3G_OK;
+  M3G_REQUIRE(vec4 && bas && g_red && tri_ptr && trt_ptr && tb_consts && g_vec4 && g_bas,
+              "m3g_tb_reduce_bwd: null pointer");
+  M3G_CHECK_LR("m3g_tb_reduce_bwd");
+  M3G_REQUIRE(group == 8 || group == 16 || group == 32, "m3g_tb_reduce_bwd: group must be 8, 16 or 32");
+#define K_(LC, RC, ...)                                                                                              \
+  do {                                                                                                               \
+    if (group == 8) tb_reduce_bwd_kernel<LC, RC, 8><<<blocks_for(E * 8, 256), 256, 0, as_stream(stream)>>>(__VA_ARGS__);        \
+    else if (group == 16) tb_reduce_bwd_kernel<LC, RC, 16><<<blocks_for(E * 16, 256), 256, 0, as_stream(stream)>>>(__VA_ARGS__); \
+    else tb_reduce_bwd_kernel<LC, RC, 32><<<blocks_for(E * 32, 256), 256, 0, as_stream(stream)>>>(__VA_ARGS__);                 \
+  } while (0)
+  M3G_DISPATCH_LR(K_, (const float4*)vec4, bas, g_red, tri_ptr, tri_e2, trt_ptr, trt_e1, tb_consts, E, L, R,
+                  (float4*)g_vec4, g_bas);
+#undef K_
+  M3G_LAUNCH_CHECK("m3g_tb_reduce_bwd");
+  return M3G_OK;
+}
+
+int m3g_tb_edge_basis_bwd(const float* vec4, const int32_t* dst, const float* sig, const float* g_bas,
+                          const float* tb_consts, int64_t E, int L, int R, float* g_vec4, float* g_sig_e,
+                          void* stream) {
+  if (E == 0) return M3G_OK;
+  M3G_REQUIRE(vec4 && dst && sig && g_bas && tb_consts && g_vec4 && g_sig_e, "m3g_tb_edge_basis_bwd: null pointer");
+  M3G_CHECK_LR("m3g_tb_edge_basis_bwd");
+#define K_(LC, RC, ...) \
+  tb_edge_basis_bwd_kernel<LC, RC><<<blocks_for(E, 128), 128, 0, as_stream(stream)>>>(__VA_ARGS__)
+  M3G_DISPATCH_LR(K_, (const float4*)vec4, dst, sig, g_bas, tb_consts, E, L, R, g_vec4, g_sig_e);
+#undef K_
+  M3G_LAUNCH_CHECK("m3g_tb_edge_basis_bwd");
+  return M3G_OK;
+}
+
+int m3g_tb_sigma_bwd(const float* g_sig_e, const int32_t* in_ptr, const int32_t* in_perm, const float* sig,
+                     const float* Ws, int64_t N, int F, int D, float* g_x, void* stream) {
+  if (N == 0) return M3G_OK;
+  M3G_REQUIRE(g_sig_e && in_ptr && in_perm && sig && Ws && g_x, "m3g_tb_sigma_bwd: null pointer");
+  M3G_REQUIRE(D >= 1 && D <= M3G_MAX_L * M3G_MAX_R, "m3g_tb_sigma_bwd: D=%d unsupported", D);
+  tb_sigma_bwd_kernel<<<blocks_for(N * 32, 256), 256, 0, as_stream(stream)>>>(g_sig_e, in_ptr, in_perm, sig, Ws, N,
+                                                                              F, D, g_x);
+  M3G_LAUNCH_CHECK("m3g_tb_sigma_bwd");
+  return M3G_OK;
+}
+
+}  // extern "C"

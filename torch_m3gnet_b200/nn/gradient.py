@@ -1,0 +1,47 @@
+from __future__ import annotations
+
+import torch
+
+from torch_m3gnet_b200._lib import call
+from torch_m3gnet_b200.data import MaterialGraphKey as K
+from torch_m3gnet_b200.data.material_graph import get_plan
+
+_OUTPUT_KEYS = (K.SCALED_POS, K.SCALED_LATTICE, K.EDGE_DISTANCES, K.TRIPLET_ANGLES, K.EDGE_WEIGHTS,
+                K.NODE_FEATURES, K.EDGE_ATTR, K.SCALED_ATOMIC_ENERGIES, K.SCALED_TOTAL_ENERGY, K.TOTAL_ENERGY)
+
+
+class Gradient(torch.nn.Module):
+    """Forces = -dE/dpos and the virial stress (reference nn/gradient.py:11-64).
+
+    The backward pass runs the hand-written adjoint kernels through ``torch.autograd.grad``.  The reference
+    keeps the autograd graph (``create_graph=True``) because its training loss differentiates the forces; the
+    inference path does not, so by default the outputs are detached after the forces are assembled and the
+    saved activations are released (set ``keep_graph = True`` to keep first-order autograd connectivity)."""
+
+    def __init__(self, model: torch.nn.Module):
+        super().__init__()
+        self.model = model
+        self.keep_graph = False
+
+    def forward(self, graph):
+        pos = graph[K.POS]
+        pos.requires_grad_(True)
+        graph = self.model(graph)
+        energy = graph[K.TOTAL_ENERGY]
+        (g_pos,) = torch.autograd.grad(energy, pos, grad_outputs=torch.ones_like(energy),
+                                       retain_graph=self.keep_graph)
+        pos.requires_grad_(False)
+        plan = get_plan(graph)
+        forces = torch.empty_like(pos)
+        stresses = torch.empty((plan.B, 6), dtype=torch.float32, device=pos.device)
+        call("forces_virial", pos.detach().contiguous(), g_pos.contiguous(), graph[K.LATTICE].contiguous(),
+             plan.atom_ptr, plan.N, plan.B, forces, stresses)
+        graph[K.FORCES] = forces
+        graph[K.STRESSES] = stresses
+        if not self.keep_graph:
+            for k in _OUTPUT_KEYS:
+                v = graph[k]
+                if torch.is_tensor(v):
+                    graph[k] = v.detach()
+            graph._private.clear()
+        return graph

@@ -1,0 +1,113 @@
+from __future__ import annotations
+
+import math
+
+import torch
+
+from torch_m3gnet_b200.data import MaterialGraphKey as K
+from torch_m3gnet_b200.data.material_graph import get_plan
+from torch_m3gnet_b200.nn._bessel_zeros import SPHERICAL_BESSEL_ZEROS
+from torch_m3gnet_b200.nn._functions import CutoffFn, LegendreCosFn, SphericalBesselFn, ThreeBodyFn
+from torch_m3gnet_b200.nn._packing import PackedWeights, c_, t_
+from torch_m3gnet_b200.nn.core import GatedMLP
+from torch_m3gnet_b200.nn.invariant import PAIR_VEC4
+
+__all__ = ["ThreeBodyInteration", "NormalizedSphericalBessel", "SPHERICAL_BESSEL_ZEROS", "spherical_bessel",
+           "legendre_cos", "cutoff_function"]
+
+# Operator API of the reference (nn/interaction.py:385-400), backed by elementwise CUDA kernels (float32, CUDA
+# tensors only).
+spherical_bessel = SphericalBesselFn.apply
+legendre_cos = LegendreCosFn.apply
+
+
+def cutoff_function(input: torch.Tensor, cutoff: float) -> torch.Tensor:
+    return CutoffFn.apply(input, cutoff)
+
+
+def _host_bessel_at(x: torch.Tensor, order: int) -> torch.Tensor:
+    """j_order(x) on the host with the float32 op sequence of the reference's SphericalBessel.forward
+    (nn/interaction.py:288-323).  Used ONLY at construction time for the normalisation table below."""
+    eps = 1e-8
+    vals = [torch.where(x > eps, torch.sin(x) / x, torch.ones_like(x))]
+    if order >= 1:
+        vals.append(torch.where(x > eps, (torch.sin(x) / x - torch.cos(x)) / x, x / 3))
+        c = 3
+        for n in range(1, order):
+            c *= 2 * n + 3
+            vals.append(torch.where(x > eps, (2 * n + 1) / x * vals[n] - vals[n - 1], x / c))
+    return vals[order]
+
+
+class NormalizedSphericalBessel(torch.nn.Module):
+    """Constant tables of the normalised spherical Bessel radial functions (reference nn/interaction.py:226-281).
+
+    ``factors`` reproduces the reference bit-for-bit *on the host*: the reference evaluates j_{l+1} at the zeros
+    of j_{l+1} in CPU float32 and divides by it (quirk Q1), so the table is round-off noise of the host's
+    sin/cos; it must therefore be computed by the same CPU float32 sequence at construction, never on the GPU.
+    Like the reference it is a plain attribute (not a buffer) and may be overwritten by the user."""
+
+    def __init__(self, cutoff: float, l_max: int, n_max: int, device: torch.device | None = None):
+        super().__init__()
+        self.cutoff = cutoff
+        self.l_max = l_max
+        self.n_max = n_max
+        self.device = device
+        zeros = torch.tensor(SPHERICAL_BESSEL_ZEROS)  # float32, as in the reference
+        if zeros.size(0) < l_max + 1:
+            raise ValueError("Too large l_max is specified.")
+        if zeros.size(1) < n_max:
+            raise ValueError("Too large n_max is specified.")
+        self.spherical_bessel_zeros = zeros.to(device)
+        self.factors = torch.stack([
+            math.sqrt(2 / (cutoff**3)) / torch.abs(_host_bessel_at(zeros[l + 1, :n_max], l + 1))
+            for l in range(l_max)
+        ]).to(device)
+
+
+class ThreeBodyInteration(torch.nn.Module):
+    """Three-body update of the edge features (reference nn/interaction.py:138-223), fused on the GPU: the
+    triplet gather, basis product and segmented sum into bond features run in one kernel (csrc/threebody.cu).
+    Updates EDGE_ATTR."""
+
+    def __init__(self, cutoff: float, threebody_cutoff: float, l_max: int, n_max: int, num_node_features: int,
+                 num_edge_features: int, device: torch.device | None = None):
+        super().__init__()
+        self.cutoff = cutoff
+        self.threebody_cutoff = threebody_cutoff
+        self.l_max = l_max
+        self.n_max = n_max
+        self.degree = l_max * n_max
+        self.num_node_features = num_node_features
+        self.num_edge_features = num_edge_features
+        self.device = device
+        self.nsb = NormalizedSphericalBessel(cutoff=cutoff, l_max=l_max, n_max=n_max, device=device)
+        self.linear_sigmoid1 = torch.nn.Linear(num_node_features, self.degree, device=device)
+        self.gated_mlp = GatedMLP(in_features=self.degree, dimensions=[num_edge_features], use_bias=False,
+                                  device=device)
+        self._packed = PackedWeights(self._sources, self._pack)
+
+    def _sources(self):
+        return [self.linear_sigmoid1.weight, self.linear_sigmoid1.bias, self.gated_mlp.dense[0].weight,
+                self.gated_mlp.gate[0].weight, self.nsb.factors, self.nsb.spherical_bessel_zeros]
+
+    def _pack(self):
+        dev = self.linear_sigmoid1.weight.device
+        L, R = self.l_max, self.n_max
+        zeros = self.nsb.spherical_bessel_zeros[:L, :R].to(device=dev, dtype=torch.float32).reshape(-1)
+        fac = self.nsb.factors.to(device=dev, dtype=torch.float32).reshape(-1)
+        tail = torch.tensor([self.cutoff, self.threebody_cutoff], dtype=torch.float32, device=dev)
+        return {
+            "Ws": c_(self.linear_sigmoid1.weight), "bs": c_(self.linear_sigmoid1.bias),
+            "WdT": t_(self.gated_mlp.dense[0].weight), "WgT": t_(self.gated_mlp.gate[0].weight),
+            "consts": torch.cat([zeros, fac, tail]).contiguous(),
+        }
+
+    def forward(self, graph):
+        plan = get_plan(graph)
+        vec4 = graph._private.get(PAIR_VEC4)
+        if vec4 is None:
+            raise RuntimeError("ThreeBodyInteration needs the bond vectors computed by DistanceAndAngle")
+        graph[K.EDGE_ATTR] = ThreeBodyFn.apply(graph[K.NODE_FEATURES], graph[K.EDGE_ATTR], vec4, plan,
+                                               self._packed.get(), self.l_max, self.n_max)
+        return graph
