@@ -1,0 +1,105 @@
+"""GPU: neighbour list + triplet enumeration — index sets must match the oracle exactly (bit-exact integers)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import m3gnet_oracle as O
+from tests.util import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _structure(lat, cart, z):
+    from torch_m3gnet_b200.data.structure import Structure
+
+    return Structure(lat, [int(v) for v in z], cart, coords_are_cartesian=True)
+
+
+def _compare(structs, cutoff, r3, device):
+    from torch_m3gnet_b200.data.material_graph import Batch
+
+    b = Batch.from_structures([_structure(*s) for s in structs], cutoff, r3, device=device)
+    ref = O.collate([O.build_graph(lat, cart, z, cutoff, r3) for (lat, cart, z) in structs])
+    for k in ("edge_index", "edge_cell_shift", "triplet_edge_index", "num_triplet_i", "num_triplet_ij", "batch",
+              "atom_types"):
+        got, want = b[k].cpu(), ref[k]
+        assert got.shape == want.shape, f"{k}: {tuple(got.shape)} vs {tuple(want.shape)}"
+        assert got.dtype == want.dtype, f"{k}: dtype {got.dtype} vs {want.dtype}"
+        assert torch.equal(got, want), f"{k} differs"
+    assert torch.equal(b["pos"].cpu(), ref["pos"]) and torch.equal(b["lattice"].cpu(), ref["lattice"])
+    return b, ref
+
+
+def test_fcc_bcc_known_answers(device):
+    """reference tests/test_data.py:10-23."""
+    r_nn = 3.0
+    lat_al = r_nn * np.sqrt(2) * np.eye(3)
+    fr_al = np.array([[0, 0, 0], [0, 0.5, 0.5], [0.5, 0, 0.5], [0.5, 0.5, 0]])
+    lat_na = r_nn / np.sqrt(3) * 2 * np.eye(3)
+    fr_na = np.array([[0, 0, 0], [0.5, 0.5, 0.5]])
+    rc = r_nn + 1e-4
+    b, _ = _compare([(lat_al, fr_al @ lat_al, [13] * 4), (lat_na, fr_na @ lat_na, [11] * 2)], rc, rc, device)
+    assert b["batch"].tolist() == [0, 0, 0, 0, 1, 1] and b.num_nodes == 6
+    assert b["num_triplet_i"].tolist() == [132, 132, 132, 132, 56, 56]
+
+
+def test_unit_cube_self_images(device):
+    """reference tests/test_nn.py:16-30: a = 1 Å, r = 1 Å → self-image edges."""
+    lat = np.eye(3)
+    frac = np.array([[0, 0, 0], [0.5, 0.5, 0.5], [0.5, 0, 0], [0, 0.5, 0.5]])
+    b, _ = _compare([(lat, frac @ lat, [3, 3, 1, 1])], 1.0, 1.0, device)
+    ei = b["edge_index"].cpu()
+    assert int((ei[0] == ei[1]).sum()) == 24
+
+
+def test_c1_c2_like_and_triclinic(device):
+    structs = [O.fcc_supercell(2, jitter=0.05, seed=0), O.fcc_supercell(3, jitter=0.1, seed=1)]
+    # sheared (triclinic) Ti8O24 cell with unwrapped coordinates (some atoms outside [0,1) fractional)
+    g = golden("tio2_default")
+    lat = g["g.lattice"][0].astype(np.float64) @ (np.eye(3) + 0.1 * np.array([[0, 1, 0], [1, 0, 0], [0, 0, 1.0]]))
+    cart = g["g.pos"].astype(np.float64) + np.array([0.0, 9.0, -3.0])
+    structs.append((lat, cart, np.array([22] * 8 + [8] * 24)))
+    _compare(structs, 5.0, 4.0, device)
+
+
+def test_mpf_like_ragged_batch(device):
+    structs = [O.mpf_like_structure(s) for s in range(6)]
+    b, ref = _compare(structs, 5.0, 4.0, device)
+    print("[graph] ragged batch: N=%d E=%d T=%d" % (b.num_nodes, b["edge_index"].shape[1],
+                                                     b["triplet_edge_index"].shape[1]))
+
+
+def test_builder_plan_equals_generic_plan(device):
+    """The plan seeded by the builder and the plan derived from the public tensors agree."""
+    from torch_m3gnet_b200.data.material_graph import Batch, GraphPlan
+
+    structs = [O.fcc_supercell(2, jitter=0.05, seed=0), O.mpf_like_structure(3)]
+    b = Batch.from_structures([_structure(*s) for s in structs], 5.0, 4.0, device=device)
+    p1 = b._plan
+    p2 = GraphPlan.build(b)
+    for name in ("src", "dst", "edge_ptr", "in_ptr", "tri_ptr", "atom_ptr", "batch", "types"):
+        assert torch.equal(getattr(p1, name), getattr(p2, name)), name
+    assert torch.equal(p1.in_perm[:p1.E], p2.in_perm[:p2.E])
+    assert torch.equal(p1.tri_e2[:p1.T], p2.tri_e2[:p2.T])
+    assert p2.tri_symmetric
+
+
+def test_model_on_gpu_built_graph_matches_oracle(device):
+    from torch_m3gnet_b200 import build_model
+    from torch_m3gnet_b200.data.material_graph import Batch, MaterialGraph
+    from tests.util import state_dict_of
+
+    c1 = golden("c1_default")
+    sd = {k: (v * 3 if k.endswith("weight") else v) for k, v in state_dict_of(c1).items()}
+    model = build_model(5.0, 4.0, 3, 3, 95, 64, 3, device=device)
+    model.load_state_dict(sd)
+    structs = [O.mpf_like_structure(1), O.fcc_supercell(2, jitter=0.08, seed=9)]
+    graphs = [MaterialGraph.from_structure(_structure(*s), 5.0, 4.0).to(device) for s in structs]
+    out = model(Batch.from_data_list(graphs))
+    ref_g = O.collate([O.build_graph(lat, cart, z, 5.0, 4.0) for (lat, cart, z) in structs])
+    ref = O.forward(sd, O.HyperParams(), ref_g, create_graph=False)
+    n = ref_g["pos"].shape[0]
+    dE = (out["total_energy"].cpu() - ref["total_energy"]).abs().max().item()
+    dF = (out["forces"].cpu() - ref["forces"]).abs().max().item()
+    print(f"[parity] gpu-built graphs: |dE|={dE:.3e} (N={n}) max|dF|={dF:.3e} max|F|={ref['forces'].abs().max():.3e}")
+    assert dE / n <= 1e-5 and dF <= 1e-4

@@ -82,9 +82,13 @@ class _Library:
 
 LIB = _Library()
 
-# number of kernel-launching ABI calls made so far (bench.py reports the per-step delta as gpu_launches;
-# each ABI call launches at least one kernel)
+# kernel launches issued through the ABI so far (bench.py reports the per-step delta as gpu_launches)
 CALLS = 0
+LAUNCHES = 0
+_KERNELS_PER_CALL = {"exclusive_scan_i32": 3, "csr_by_key": 7, "check_sorted": 2, "csr_is_symmetric": 2,
+                     "forces_virial": 2}
+# when set to a dict, every call is bracketed by CUDA events on the launching stream: {name: [(start, end), ...]}
+PROFILE = None
 
 
 def _ptr(t):
@@ -101,7 +105,7 @@ def _ptr(t):
 
 def call(name: str, *args):
     """Call ``m3g_<name>(*args, stream)`` on the current CUDA stream; raise on a non-zero status."""
-    global CALLS
+    global CALLS, LAUNCHES
     cdll = LIB.load()
     fn = getattr(cdll, "m3g_" + name)
     conv = []
@@ -110,8 +114,16 @@ def call(name: str, *args):
     if len(args) != len(fn.argtypes) - 1:
         raise TypeError(f"m3g_{name}: expected {len(fn.argtypes) - 1} arguments before the stream, got {len(args)}")
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    rc = fn(*conv, stream)
+    if PROFILE is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        rc = fn(*conv, stream)
+        ev1.record()
+        PROFILE.setdefault(name, []).append((ev0, ev1))
+    else:
+        rc = fn(*conv, stream)
     CALLS += 1
+    LAUNCHES += _KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         raise RuntimeError(f"m3g_{name} failed ({rc}): {cdll.m3g_last_error().decode()}")
 

@@ -14,13 +14,16 @@ class AtomRef(torch.nn.Module):
     def __init__(self, elemental_energies: torch.Tensor, device: torch.device | None = None):
         super().__init__()
         self.elemental_energies = elemental_energies.to(device)
+        self._table_cache = None
 
     def forward(self, graph):
         plan = get_plan(graph)
-        table = self.elemental_energies
-        if table.dtype != torch.float32 or table.device != plan.device:
-            table = table.to(device=plan.device, dtype=torch.float32)
+        src = self.elemental_energies
+        sig = (src.data_ptr(), src._version, plan.device)
+        if self._table_cache is None or self._table_cache[0] != sig:
+            self._table_cache = (sig, src.detach().to(device=plan.device, dtype=torch.float32).contiguous())
+        table = self._table_cache[1]
         out = torch.empty(plan.N, dtype=torch.float32, device=plan.device)
-        call("atomref_fwd", table.contiguous(), plan.types, plan.N, out)
+        call("atomref_fwd", table, plan.types, plan.N, out)
         graph[K.ELEMENTAL_ENERGIES] = out
         return graph
