@@ -210,6 +210,30 @@ int m3g_linear_bwd_input(const float* g, const float* W, const float* base, int6
                          void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Tensor-core path of the same gated MLP for F = 64 (csrc/conv_tc.cu): tcgen05.mma kind::tf32 with the 3xTF32
+ * split (passes = 3; passes = 1 is plain TF32), accumulators in TMEM, weight images resident in shared memory.
+ * m3g_tc_pack_b writes the hi / lo SWIZZLE_128B operand images of a (rows x cols) row-major weight matrix
+ * (rows % 8 == 0, cols % 32 == 0; each image rows*cols floats).  wimg = [W1e hi | W1e lo | W2d hi | W2d lo |
+ * W2g hi | W2g lo] with W1e (128 x 64) = rows [dense | gate] of the e-part of layer 1, W2d/W2g (64 x 64), all in
+ * the reference's (out,in) orientation.  n_sm = number of SMs (persistent grid).
+ * ------------------------------------------------------------------------------------------- */
+int m3g_tc_pack_b(const float* W, int rows, int cols, float* img_hi, float* img_lo, void* stream);
+/* UMMA plumbing self test on one 128-row tile: out (128 x rows) = A (128 x cols) · W^T, W given as its image */
+int m3g_tc_selftest(const float* A, const float* img_hi, const float* img_lo, int rows, int cols, int passes,
+                    float* out, void* stream);
+int m3g_conv_tc_fwd(const float* P, int ldp, int po, const int32_t* src, const int32_t* dst, const float* e,
+                    const float* h, const float* wimg, const float* b2d, const float* b2g, const float* WhT, int64_t E,
+                    int R, int mode, int passes, int n_sm, float* y, void* stream);
+
+/* adjoint of m3g_conv_tc_fwd (same outputs as m3g_conv_mlp_bwd; forward recomputed on the tensor cores).
+ * wimgT = [W2d^T hi|lo, W2g^T hi|lo, W1e_dense^T hi|lo, W1e_gate^T hi|lo]: four 64x64 image pairs from
+ * m3g_tc_pack_b of the transposed matrices (W1e_dense = rows 0..63 of W1e, W1e_gate = rows 64..127). R <= 3. */
+int m3g_conv_tc_bwd(const float* P, int ldp, int po, const int32_t* src, const int32_t* dst, const float* e,
+                    const float* h, const float* wimg, const float* wimgT, const float* b2d, const float* b2g,
+                    const float* WhT, const float* g_up, const float* g_e_base, int64_t E, int R, int mode, int passes,
+                    int n_sm, float* g_e, float* g_z1, float* g_h, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * AtomWiseReadout (nn/readout.py:39-58) + virial (nn/gradient.py:39-62)
  * weights: 3-layer gated MLP F→F→F→1; WT = (in,out) layout, W = (out,in) layout
  * ------------------------------------------------------------------------------------------- */

@@ -1,0 +1,717 @@
+// M3GNetConv gated MLP on edges for F = 64 on the 5th-gen tensor cores (tcgen05.mma kind::tf32, accumulators in
+// TMEM), fp32-faithful through the 3xTF32 split  a·b ≈ a_hi·b_hi + a_lo·b_hi + a_hi·b_lo  (hi = top 19 bits).
+//
+// One persistent CTA per SM walks tiles of 128 edges.  Per tile (forward):
+//   e rows -> smem X (hi|lo, K-major SWIZZLE_128B)      GEMM1: D1[128x128] = X · W1e^T      (dense | gate halves)
+//   epilogue: z1 = D1 + P[src] + P[dst] -> SiLU -> X    GEMM2d: D2d[128x64] = a1d · W2d^T
+//                                        (gate half)    GEMM2g: D2g[128x64] = a1g · W2g^T
+//   epilogue: SiLU(D2d + b) * sigmoid(D2g + b) * (h · Wh^T) (+ e) -> y
+// The weight images (hi|lo for W1e, W2d, W2g = 128 KB) stay resident in shared memory for the whole kernel; the
+// activation operand buffer X (64 KB) is reused by the three GEMMs; MMA completion is tracked with one mbarrier.
+// The backward kernel recomputes the forward GEMMs and runs the transposed products (dz2·W2, dz1·W1e) against
+// K-major images of the transposed weights that are staged per tile through a 32 KB buffer (tf32 operands
+// only admit the 32B-atom swizzle in MN-major form, so the forward images cannot be reused transposed).
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace m3g {
+
+using namespace umma;
+
+constexpr int TC_F = 64;
+constexpr int TILE_M = 128;
+constexpr int TC_THREADS = 256;
+
+// image sizes in floats
+constexpr int IMG_W1 = 128 * 64;  // W1e: 128 rows (dense|gate outputs) x 64 (e features)
+constexpr int IMG_W2 = 64 * 64;
+constexpr int WIMG_FLOATS = 2 * IMG_W1 + 4 * IMG_W2;  // 32768 floats = 128 KB
+
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+
+__device__ __forceinline__ float silu_fast(float z) { return __fdividef(z, 1.0f + __expf(-z)); }
+__device__ __forceinline__ float sigmoid_fast(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
+
+// split 4 consecutive k of row r into the hi / lo operand images
+__device__ __forceinline__ void store_split4(char* x_hi, char* x_lo, int r, int k, float4 v) {
+  uint32_t off = sw128_offset(r, k, TILE_M);
+  float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+  float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+  *reinterpret_cast<float4*>(x_hi + off) = hi;
+  *reinterpret_cast<float4*>(x_lo + off) = lo;
+}
+
+// D[128 x N] (+)= A[128 x K] · Bimg^T with A a K-major image (128 rows) and B a K-major image with N rows:
+//   D[m][n] += sum_k A[m][k] * Bimg[n][k]        (3 passes: hi·hi, lo·hi, hi·lo).  Issued by ONE thread.
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                           uint32_t b_lo, int N, int K, bool accumulate, int passes) {
+  const uint32_t idesc = make_idesc_tf32(TILE_M, N, 0);
+  for (int pass = 0; pass < passes; ++pass) {
+    uint32_t a = (pass == 1) ? a_lo : a_hi;
+    uint32_t b = (pass == 2) ? b_lo : b_hi;
+    for (int kk = 0; kk < K / 8; ++kk) {
+      uint64_t da = make_desc(a + (kk >> 2) * (TILE_M * 128) + (kk & 3) * 32, 16, 1024);
+      uint64_t db = make_desc(b + (kk >> 2) * (N * 128) + (kk & 3) * 32, 16, 1024);
+      mma_tf32(tmem_d, da, db, idesc, (accumulate || pass > 0 || kk > 0) ? 1u : 0u);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// weight image packing: W (rows x cols) row-major -> hi / lo SWIZZLE_128B images
+__global__ void tc_pack_kernel(const float* __restrict__ W, int rows, int cols, float* __restrict__ img_hi,
+                               float* __restrict__ img_lo) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  int r = idx / cols, k = idx - r * cols;
+  float v = W[idx];
+  float hi = tf32_hi(v);
+  uint32_t off = sw128_offset(r, k, rows) >> 2;
+  img_hi[off] = hi;
+  img_lo[off] = v - hi;
+}
+
+// --------------------------------------------------------------------------------------------------------
+// self test of the UMMA plumbing: one 128-row tile.
+//   out[128 x rows] = A[128 x cols] · W^T   (W given as its packed K-major image, rows x cols)
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ img_hi, const float* __restrict__ img_lo,
+                   int rows, int cols, int passes, float* __restrict__ out) {
+  extern __shared__ __align__(1024) char smem_raw[];
+  char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  char* b_hi = smem;
+  char* b_lo = smem + rows * cols * 4;
+  char* x_hi = smem + 2 * rows * cols * 4;
+  const int K = cols;
+  const int N = rows;
+  char* x_lo = x_hi + TILE_M * K * 4;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < rows * cols / 4; i += TC_THREADS) {
+    reinterpret_cast<float4*>(b_hi)[i] = reinterpret_cast<const float4*>(img_hi)[i];
+    reinterpret_cast<float4*>(b_lo)[i] = reinterpret_cast<const float4*>(img_lo)[i];
+  }
+  for (int i = tid; i < TILE_M * K / 4; i += TC_THREADS) {
+    int r = i / (K / 4), c = i - r * (K / 4);
+    float4 v = reinterpret_cast<const float4*>(A)[i];
+    // A image with K columns: generic offset (K may be 64 or 128)
+    uint32_t off = sw128_offset(r, 4 * c, TILE_M);
+    float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    *reinterpret_cast<float4*>(x_hi + off) = hi;
+    *reinterpret_cast<float4*>(x_lo + off) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+  }
+  if (warp == 0) tmem_alloc<128>(&tmem_slot);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    issue_gemm(tmem, smem_u32(x_hi), smem_u32(x_lo), smem_u32(b_hi), smem_u32(b_lo), N, K, false, passes);
+    commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  fence_after_sync();
+  int q = warp & 3, hsel = warp >> 2;
+  int r = 32 * q + lane;
+  for (int c0 = 32 * hsel; c0 < N; c0 += 64) {
+    float v[32];
+    tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 32; ++c) out[r * N + c0 + c] = v[c];
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<128>(tmem);
+}
+
+// --------------------------------------------------------------------------------------------------------
+struct ConvTcParams {
+  const float* P; int ldp; int po;
+  const int32_t* src; const int32_t* dst;
+  const float* e; const float* h;
+  const float* wimg;  // [W1 hi | W1 lo | W2d hi | W2d lo | W2g hi | W2g lo]
+  const float* b2d; const float* b2g; const float* WhT;
+  int64_t E; int R; int mode; int passes;
+  float* y;
+};
+
+constexpr int SMEM_W_BYTES = WIMG_FLOATS * 4;         // 131072
+constexpr int SMEM_X_BYTES = 2 * TILE_M * TC_F * 4;   // 65536 (hi | lo)
+constexpr int SMEM_MISC_FLOATS = 64 + 64 + M3G_MAX_RADIAL * 64;
+constexpr int SMEM_FWD_BYTES = SMEM_W_BYTES + SMEM_X_BYTES + SMEM_MISC_FLOATS * 4 + 1024;
+
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(ConvTcParams p) {
+  extern __shared__ __align__(1024) char smem_raw[];
+  char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  char* w1_hi = smem;
+  char* w1_lo = w1_hi + IMG_W1 * 4;
+  char* w2d_hi = w1_lo + IMG_W1 * 4;
+  char* w2d_lo = w2d_hi + IMG_W2 * 4;
+  char* w2g_hi = w2d_lo + IMG_W2 * 4;
+  char* w2g_lo = w2g_hi + IMG_W2 * 4;
+  char* x_hi = smem + SMEM_W_BYTES;
+  char* x_lo = x_hi + TILE_M * TC_F * 4;
+  float* b2d_s = reinterpret_cast<float*>(smem + SMEM_W_BYTES + SMEM_X_BYTES);
+  float* b2g_s = b2d_s + 64;
+  float* wh_s = b2g_s + 64;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, hsel = warp >> 2;
+  const int row = 32 * q + lane;
+
+  for (int i = tid; i < WIMG_FLOATS / 4; i += TC_THREADS)
+    reinterpret_cast<float4*>(smem)[i] = reinterpret_cast<const float4*>(p.wimg)[i];
+  if (tid < 64) { b2d_s[tid] = p.b2d[tid]; b2g_s[tid] = p.b2g[tid]; }
+  for (int i = tid; i < p.R * 64; i += TC_THREADS) wh_s[i] = p.WhT[i];
+  if (warp == 0) tmem_alloc<256>(&tmem_slot);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+  const uint32_t D1 = 0, D2D = 128, D2G = 192;
+  uint32_t phase = 0;
+  const uint32_t xh = smem_u32(x_hi), xl = smem_u32(x_lo);
+
+  const int64_t n_tiles = (p.E + TILE_M - 1) / TILE_M;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t e0 = tile * TILE_M;
+    // ---- P0: e rows -> X (hi | lo) ----
+#pragma unroll
+    for (int i = 0; i < (TILE_M * TC_F / 4) / TC_THREADS; ++i) {
+      int idx = tid + TC_THREADS * i;
+      int r = idx >> 4, c = idx & 15;
+      int64_t eg = e0 + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (eg < p.E) v = __ldg(reinterpret_cast<const float4*>(p.e + eg * TC_F) + c);
+      store_split4(x_hi, x_lo, r, 4 * c, v);
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_gemm(tmem + D1, xh, xl, smem_u32(w1_hi), smem_u32(w1_lo), 128, 64, false, p.passes);
+      commit(&bar);
+    }
+    const int64_t eg = min(e0 + row, p.E - 1);
+    const bool live = (e0 + row) < p.E;
+    const float* Pi = p.P + (int64_t)p.src[eg] * p.ldp + p.po;
+    const float* Pj = p.P + (int64_t)p.dst[eg] * p.ldp + p.po + 128;
+    // ---- P2: dense half of layer 1 -> X ----
+    mbar_wait(&bar, phase); phase ^= 1;
+    fence_after_sync();
+    {
+      float v[32];
+      tmem_ld32(t_lane + D1 + 32 * hsel, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(Pi + 32 * hsel + c));
+        float4 b = __ldg(reinterpret_cast<const float4*>(Pj + 32 * hsel + c));
+        float4 z = make_float4(silu_fast(v[c] + a.x + b.x), silu_fast(v[c + 1] + a.y + b.y),
+                               silu_fast(v[c + 2] + a.z + b.z), silu_fast(v[c + 3] + a.w + b.w));
+        store_split4(x_hi, x_lo, row, 32 * hsel + c, z);
+      }
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_gemm(tmem + D2D, xh, xl, smem_u32(w2d_hi), smem_u32(w2d_lo), 64, 64, false, p.passes);
+      commit(&bar);
+    }
+    // ---- P4: gate half of layer 1 (overlaps GEMM2d), then -> X ----
+    float ag[32];
+    {
+      float v[32];
+      tmem_ld32(t_lane + D1 + 64 + 32 * hsel, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(Pi + 64 + 32 * hsel + c));
+        float4 b = __ldg(reinterpret_cast<const float4*>(Pj + 64 + 32 * hsel + c));
+        ag[c] = silu_fast(v[c] + a.x + b.x);
+        ag[c + 1] = silu_fast(v[c + 1] + a.y + b.y);
+        ag[c + 2] = silu_fast(v[c + 2] + a.z + b.z);
+        ag[c + 3] = silu_fast(v[c + 3] + a.w + b.w);
+      }
+    }
+    mbar_wait(&bar, phase); phase ^= 1;  // GEMM2d has consumed X
+    fence_after_sync();
+#pragma unroll
+    for (int c = 0; c < 32; c += 4)
+      store_split4(x_hi, x_lo, row, 32 * hsel + c, make_float4(ag[c], ag[c + 1], ag[c + 2], ag[c + 3]));
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_gemm(tmem + D2G, xh, xl, smem_u32(w2g_hi), smem_u32(w2g_lo), 64, 64, false, p.passes);
+      commit(&bar);
+    }
+    // ---- P6: output stage (dense branch overlaps GEMM2g) ----
+    float sd[32];
+    {
+      float v[32];
+      tmem_ld32(t_lane + D2D + 32 * hsel, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 32; ++c) sd[c] = silu_fast(v[c] + b2d_s[32 * hsel + c]);
+    }
+    float hm[M3G_MAX_RADIAL];
+#pragma unroll
+    for (int m = 0; m < M3G_MAX_RADIAL; ++m) hm[m] = (m < p.R) ? p.h[eg * p.R + m] : 0.0f;
+    mbar_wait(&bar, phase); phase ^= 1;
+    fence_after_sync();
+    {
+      float v[32];
+      tmem_ld32(t_lane + D2G + 32 * hsel, v);
+      tmem_ld_wait();
+      if (live) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          float o[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            int col = 32 * hsel + c + u;
+            float s = 0.0f;
+#pragma unroll
+            for (int m = 0; m < M3G_MAX_RADIAL; ++m)
+              if (m < p.R) s += hm[m] * wh_s[m * 64 + col];
+            o[u] = sd[c + u] * sigmoid_fast(v[c + u] + b2g_s[col]) * s;
+          }
+          float4 res = make_float4(o[0], o[1], o[2], o[3]);
+          if (p.mode == 0) {
+            float4 ev = __ldg(reinterpret_cast<const float4*>(p.e + eg * TC_F + 32 * hsel + c));
+            res.x += ev.x; res.y += ev.y; res.z += ev.z; res.w += ev.w;
+          }
+          *reinterpret_cast<float4*>(p.y + eg * TC_F + 32 * hsel + c) = res;
+        }
+      }
+    }
+    fence_before_sync();
+    __syncthreads();  // TMEM and X are free for the next tile
+  }
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+// --------------------------------------------------------------------------------------------------------
+// Backward of one gated MLP on edges (forward recomputed on the tensor cores).
+struct ConvTcBwdParams {
+  const float* P; int ldp; int po;
+  const int32_t* src; const int32_t* dst;
+  const float* e; const float* h;
+  const float* wimg;   // forward images (resident)
+  const float* wimgT;  // [W2d^T hi|lo, W2g^T hi|lo, W1e_dense^T hi|lo, W1e_gate^T hi|lo], each 64x64 image pair (staged)
+  const float* b2d; const float* b2g; const float* WhT;
+  const float* g_up; const float* g_e_base;
+  int64_t E; int R; int mode; int passes;
+  float* g_e; float* g_z1; float* g_h;
+};
+
+constexpr int SMEM_S_BYTES = 2 * IMG_W2 * 4;  // 32768: one staged 64x64 image pair
+constexpr int TC_BWD_MAX_R = 3;
+constexpr int SMEM_BWD_MISC = TILE_M * TC_BWD_MAX_R * 4 + 16;
+constexpr int SMEM_BWD_BYTES = SMEM_W_BYTES + SMEM_X_BYTES + SMEM_S_BYTES + SMEM_BWD_MISC + 1024;
+static_assert(SMEM_BWD_BYTES <= 232448, "backward kernel exceeds the 227 KB shared-memory limit");
+
+__device__ __forceinline__ float silu_grad_fast(float z) {
+  float s = sigmoid_fast(z);
+  return s * (1.0f + z * (1.0f - s));
+}
+
+__device__ __forceinline__ void stage_image(char* dst, const float* __restrict__ src, int tid) {
+#pragma unroll
+  for (int i = 0; i < (SMEM_S_BYTES / 16) / TC_THREADS; ++i)
+    reinterpret_cast<float4*>(dst)[tid + TC_THREADS * i] = __ldg(reinterpret_cast<const float4*>(src) + tid + TC_THREADS * i);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_bwd_kernel(ConvTcBwdParams p) {
+  extern __shared__ __align__(1024) char smem_raw[];
+  char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  char* w1_hi = smem;
+  char* w1_lo = w1_hi + IMG_W1 * 4;
+  char* w2d_hi = w1_lo + IMG_W1 * 4;
+  char* w2d_lo = w2d_hi + IMG_W2 * 4;
+  char* w2g_hi = w2d_lo + IMG_W2 * 4;
+  char* w2g_lo = w2g_hi + IMG_W2 * 4;
+  char* x_hi = smem + SMEM_W_BYTES;
+  char* x_lo = x_hi + TILE_M * TC_F * 4;
+  char* s_hi = smem + SMEM_W_BYTES + SMEM_X_BYTES;
+  char* s_lo = s_hi + IMG_W2 * 4;
+  float* gh_s = reinterpret_cast<float*>(smem + SMEM_W_BYTES + SMEM_X_BYTES + SMEM_S_BYTES);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(gh_s + TILE_M * TC_BWD_MAX_R);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, hsel = warp >> 2;
+  const int row = 32 * q + lane;
+  const int R = p.R;
+
+  for (int i = tid; i < WIMG_FLOATS / 4; i += TC_THREADS)
+    reinterpret_cast<float4*>(smem)[i] = reinterpret_cast<const float4*>(p.wimg)[i];
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+  const uint32_t D1 = 0, D2D = 128, D2G = 192, D3D = 256, D3G = 320, D4 = 384;
+  uint32_t phase = 0;
+  const uint32_t xh = smem_u32(x_hi), xl = smem_u32(x_lo), sh = smem_u32(s_hi), sl = smem_u32(s_lo);
+  const int c0 = 32 * hsel;  // this thread's 32-column slice of every 64-column block
+
+  const int64_t n_tiles = (p.E + TILE_M - 1) / TILE_M;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t e0 = tile * TILE_M;
+    // ---- e rows -> X ; GEMM1 ----
+#pragma unroll
+    for (int i = 0; i < (TILE_M * TC_F / 4) / TC_THREADS; ++i) {
+      int idx = tid + TC_THREADS * i;
+      int r = idx >> 4, c = idx & 15;
+      int64_t eg = e0 + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (eg < p.E) v = __ldg(reinterpret_cast<const float4*>(p.e + eg * TC_F) + c);
+      store_split4(x_hi, x_lo, r, 4 * c, v);
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_gemm(tmem + D1, xh, xl, smem_u32(w1_hi), smem_u32(w1_lo), 128, 64, false, p.passes);
+      commit(bar);
+    }
+    const int64_t eg = min(e0 + row, p.E - 1);
+    const bool live = (e0 + row) < p.E;
+    const int s_atom = p.src[eg];
+    const float* Pi = p.P + (int64_t)s_atom * p.ldp + p.po;
+    const float* Pj = p.P + (int64_t)p.dst[eg] * p.ldp + p.po + 128;
+    // ---- a1 dense -> X ; GEMM2d ----
+    mbar_wait(bar, phase); phase ^= 1;
+    fence_after_sync();
+    {
+      float v[32];
+      tmem_ld32(t_lane + D1 + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(Pi + c0 + c));
+        float4 b = __ldg(reinterpret_cast<const float4*>(Pj + c0 + c));
+        store_split4(x_hi, x_lo, row, c0 + c,
+                     make_float4(silu_fast(v[c] + a.x + b.x), silu_fast(v[c + 1] + a.y + b.y),
+                                 silu_fast(v[c + 2] + a.z + b.z), silu_fast(v[c + 3] + a.w + b.w)));
+      }
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_gemm(tmem + D2D, xh, xl, smem_u32(w2d_hi), smem_u32(w2d_lo), 64, 64, false, p.passes);
+      commit(bar);
+    }
+    // ---- a1 gate (regs) ; stage W2d^T ; -> X ; GEMM2g ----
+    float ra[32];
+    {
+      float v[32];
+      tmem_ld32(t_lane + D1 + 64 + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(Pi + 64 + c0 + c));
+        float4 b = __ldg(reinterpret_cast<const float4*>(Pj + 64 + c0 + c));
+        ra[c] = silu_fast(v[c] + a.x + b.x);
+        ra[c + 1] = silu_fast(v[c + 1] + a.y + b.y);
+        ra[c + 2] = silu_fast(v[c + 2] + a.z + b.z);
+        ra[c + 3] = silu_fast(v[c + 3] + a.w + b.w);
+      }
+    }
+    stage_image(s_hi, p.wimgT + 0 * 2 * IMG_W2, tid);  // S is free: the previous tile's last GEMM has completed
+    mbar_wait(bar, phase); phase ^= 1;                 // GEMM2d has consumed X
+    fence_after_sync();
+#pragma unroll
+    for (int c = 0; c < 32; c += 4)
+      store_split4(x_hi, x_lo, row, c0 + c, make_float4(ra[c], ra[c + 1], ra[c + 2], ra[c + 3]));
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_gemm(tmem + D2G, xh, xl, smem_u32(w2g_hi), smem_u32(w2g_lo), 64, 64, false, p.passes);
+      commit(bar);
+    }
+    // ---- output-stage adjoint ----
+    float sd[32], dzg[32];
+    {
+      float v[32];
+      tmem_ld32(t_lane + D2D + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        float zd = v[c] + __ldg(p.b2d + c0 + c);
+        sd[c] = silu_fast(zd);
+        ra[c] = silu_grad_fast(zd);  // ra now holds SiLU'(z2d)
+      }
+    }
+    float hm[TC_BWD_MAX_R], ghp[TC_BWD_MAX_R];
+#pragma unroll
+    for (int m = 0; m < TC_BWD_MAX_R; ++m) {
+      hm[m] = (m < R) ? p.h[eg * R + m] : 0.0f;
+      ghp[m] = 0.0f;
+    }
+    const float* gu_row = (p.mode == 0) ? p.g_up + eg * TC_F : p.g_up + (int64_t)s_atom * TC_F;
+    mbar_wait(bar, phase); phase ^= 1;  // GEMM2g done: D2g valid, X free
+    fence_after_sync();
+    {
+      float v[32];
+      tmem_ld32(t_lane + D2G + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        float4 gu4 = __ldg(reinterpret_cast<const float4*>(gu_row + c0 + c));
+        float gu[4] = {gu4.x, gu4.y, gu4.z, gu4.w};
+        float dzd[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          int col = c0 + c + u;
+          float sg = sigmoid_fast(v[c + u] + __ldg(p.b2g + col));
+          float s = 0.0f;
+          float wh[TC_BWD_MAX_R];
+#pragma unroll
+          for (int m = 0; m < TC_BWD_MAX_R; ++m) {
+            wh[m] = (m < R) ? __ldg(p.WhT + m * 64 + col) : 0.0f;
+            s += hm[m] * wh[m];
+          }
+          float gs = gu[u] * sd[c + u] * sg;
+#pragma unroll
+          for (int m = 0; m < TC_BWD_MAX_R; ++m) ghp[m] += gs * wh[m];
+          float gphi = gu[u] * s;
+          dzd[u] = gphi * sg * ra[c + u];
+          dzg[c + u] = gphi * sd[c + u] * sg * (1.0f - sg);
+        }
+        store_split4(x_hi, x_lo, row, c0 + c, make_float4(dzd[0], dzd[1], dzd[2], dzd[3]));
+      }
+    }
+    if (hsel == 1) {
+#pragma unroll
+      for (int m = 0; m < TC_BWD_MAX_R; ++m) gh_s[row * TC_BWD_MAX_R + m] = ghp[m];
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_gemm(tmem + D3D, xh, xl, sh, sl, 64, 64, false, p.passes);  // da1d = dz2d · W2d  (B = image of W2d^T)
+      commit(bar);
+    }
+    if (hsel == 0 && live) {
+#pragma unroll
+      for (int m = 0; m < TC_BWD_MAX_R; ++m)
+        if (m < R) p.g_h[eg * R + m] += ghp[m] + gh_s[row * TC_BWD_MAX_R + m];
+    }
+    // ---- GEMM3g ----
+    mbar_wait(bar, phase); phase ^= 1;  // GEMM3d done: X and S free
+    fence_after_sync();
+    stage_image(s_hi, p.wimgT + 1 * 2 * IMG_W2, tid);
+#pragma unroll
+    for (int c = 0; c < 32; c += 4)
+      store_split4(x_hi, x_lo, row, c0 + c, make_float4(dzg[c], dzg[c + 1], dzg[c + 2], dzg[c + 3]));
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_gemm(tmem + D3G, xh, xl, sh, sl, 64, 64, false, p.passes);
+      commit(bar);
+    }
+    // dz1 dense = da1d * SiLU'(z1 dense)   (overlaps GEMM3g)
+    {
+      float v[32], z[32];
+      tmem_ld32(t_lane + D3D + c0, v);
+      tmem_ld32(t_lane + D1 + c0, z);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(Pi + c0 + c));
+        float4 b = __ldg(reinterpret_cast<const float4*>(Pj + c0 + c));
+        sd[c] = v[c] * silu_grad_fast(z[c] + a.x + b.x);
+        sd[c + 1] = v[c + 1] * silu_grad_fast(z[c + 1] + a.y + b.y);
+        sd[c + 2] = v[c + 2] * silu_grad_fast(z[c + 2] + a.z + b.z);
+        sd[c + 3] = v[c + 3] * silu_grad_fast(z[c + 3] + a.w + b.w);
+        if (live)
+          *reinterpret_cast<float4*>(p.g_z1 + eg * 128 + c0 + c) = make_float4(sd[c], sd[c + 1], sd[c + 2], sd[c + 3]);
+      }
+    }
+    // ---- GEMM4a ----
+    mbar_wait(bar, phase); phase ^= 1;  // GEMM3g done
+    fence_after_sync();
+    stage_image(s_hi, p.wimgT + 2 * 2 * IMG_W2, tid);
+#pragma unroll
+    for (int c = 0; c < 32; c += 4)
+      store_split4(x_hi, x_lo, row, c0 + c, make_float4(sd[c], sd[c + 1], sd[c + 2], sd[c + 3]));
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_gemm(tmem + D4, xh, xl, sh, sl, 64, 64, false, p.passes);  // g_e = dz1d · W1e[dense rows]
+      commit(bar);
+    }
+    // dz1 gate (overlaps GEMM4a)
+    {
+      float v[32], z[32];
+      tmem_ld32(t_lane + D3G + c0, v);
+      tmem_ld32(t_lane + D1 + 64 + c0, z);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(Pi + 64 + c0 + c));
+        float4 b = __ldg(reinterpret_cast<const float4*>(Pj + 64 + c0 + c));
+        sd[c] = v[c] * silu_grad_fast(z[c] + a.x + b.x);
+        sd[c + 1] = v[c + 1] * silu_grad_fast(z[c + 1] + a.y + b.y);
+        sd[c + 2] = v[c + 2] * silu_grad_fast(z[c + 2] + a.z + b.z);
+        sd[c + 3] = v[c + 3] * silu_grad_fast(z[c + 3] + a.w + b.w);
+        if (live)
+          *reinterpret_cast<float4*>(p.g_z1 + eg * 128 + 64 + c0 + c) = make_float4(sd[c], sd[c + 1], sd[c + 2], sd[c + 3]);
+      }
+    }
+    // ---- GEMM4b ----
+    mbar_wait(bar, phase); phase ^= 1;  // GEMM4a done
+    fence_after_sync();
+    stage_image(s_hi, p.wimgT + 3 * 2 * IMG_W2, tid);
+#pragma unroll
+    for (int c = 0; c < 32; c += 4)
+      store_split4(x_hi, x_lo, row, c0 + c, make_float4(sd[c], sd[c + 1], sd[c + 2], sd[c + 3]));
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_gemm(tmem + D4, xh, xl, sh, sl, 64, 64, true, p.passes);  // += dz1g · W1e[gate rows]
+      commit(bar);
+    }
+    // ---- g_e ----
+    mbar_wait(bar, phase); phase ^= 1;
+    fence_after_sync();
+    {
+      float v[32];
+      tmem_ld32(t_lane + D4 + c0, v);
+      tmem_ld_wait();
+      if (live) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          float4 r4 = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+          if (p.g_e_base) {
+            float4 b4 = __ldg(reinterpret_cast<const float4*>(p.g_e_base + eg * TC_F + c0 + c));
+            r4.x += b4.x; r4.y += b4.y; r4.z += b4.z; r4.w += b4.w;
+          }
+          *reinterpret_cast<float4*>(p.g_e + eg * TC_F + c0 + c) = r4;
+        }
+      }
+    }
+    fence_before_sync();
+    __syncthreads();
+  }
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace m3g
+
+using namespace m3g;
+
+extern "C" {
+
+int m3g_tc_pack_b(const float* W, int rows, int cols, float* img_hi, float* img_lo, void* stream) {
+  M3G_REQUIRE(W && img_hi && img_lo, "m3g_tc_pack_b: null pointer");
+  M3G_REQUIRE(rows % 8 == 0 && cols % 32 == 0, "m3g_tc_pack_b: rows %% 8 and cols %% 32 must be 0");
+  tc_pack_kernel<<<blocks_for((int64_t)rows * cols, 256), 256, 0, as_stream(stream)>>>(W, rows, cols, img_hi, img_lo);
+  M3G_LAUNCH_CHECK("m3g_tc_pack_b");
+  return M3G_OK;
+}
+
+int m3g_tc_selftest(const float* A, const float* img_hi, const float* img_lo, int rows, int cols, int passes,
+                    float* out, void* stream) {
+  M3G_REQUIRE(A && img_hi && img_lo && out, "m3g_tc_selftest: null pointer");
+  M3G_REQUIRE((rows == 64 || rows == 128) && (cols == 64 || cols == 128), "m3g_tc_selftest: rows/cols in {64,128}");
+  M3G_REQUIRE(passes == 1 || passes == 3, "m3g_tc_selftest: passes must be 1 or 3");
+  size_t smem = 2 * (size_t)rows * cols * 4 + 2 * (size_t)TILE_M * cols * 4 + 1024;
+  cudaError_t err = cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) {
+    set_error("m3g_tc_selftest: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+    return M3G_ERR_CUDA;
+  }
+  tc_selftest_kernel<<<1, TC_THREADS, smem, as_stream(stream)>>>(A, img_hi, img_lo, rows, cols, passes, out);
+  M3G_LAUNCH_CHECK("m3g_tc_selftest");
+  return M3G_OK;
+}
+
+int m3g_conv_tc_fwd(const float* P, int ldp, int po, const int32_t* src, const int32_t* dst, const float* e,
+                    const float* h, const float* wimg, const float* b2d, const float* b2g, const float* WhT, int64_t E,
+                    int R, int mode, int passes, int n_sm, float* y, void* stream) {
+  if (E == 0) return M3G_OK;
+  M3G_REQUIRE(P && src && dst && e && h && wimg && b2d && b2g && WhT && y, "m3g_conv_tc_fwd: null pointer");
+  M3G_REQUIRE(R >= 1 && R <= M3G_MAX_RADIAL, "m3g_conv_tc_fwd: R=%d unsupported", R);
+  M3G_REQUIRE(passes == 1 || passes == 3, "m3g_conv_tc_fwd: passes must be 1 or 3");
+  M3G_REQUIRE(ldp % 4 == 0 && po % 4 == 0, "m3g_conv_tc_fwd: P rows must be 16-byte aligned");
+  cudaError_t err =
+      cudaFuncSetAttribute(conv_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD_BYTES);
+  if (err != cudaSuccess) {
+    set_error("m3g_conv_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+    return M3G_ERR_CUDA;
+  }
+  ConvTcParams p{P, ldp, po, src, dst, e, h, wimg, b2d, b2g, WhT, E, R, mode, passes, y};
+  int64_t n_tiles = (E + TILE_M - 1) / TILE_M;
+  unsigned grid = (unsigned)((n_tiles < n_sm) ? n_tiles : n_sm);
+  conv_tc_fwd_kernel<<<grid, TC_THREADS, SMEM_FWD_BYTES, as_stream(stream)>>>(p);
+  M3G_LAUNCH_CHECK("m3g_conv_tc_fwd");
+  return M3G_OK;
+}
+
+int m3g_conv_tc_bwd(const float* P, int ldp, int po, const int32_t* src, const int32_t* dst, const float* e,
+                    const float* h, const float* wimg, const float* wimgT, const float* b2d, const float* b2g,
+                    const float* WhT, const float* g_up, const float* g_e_base, int64_t E, int R, int mode, int passes,
+                    int n_sm, float* g_e, float* g_z1, float* g_h, void* stream) {
+  if (E == 0) return M3G_OK;
+  M3G_REQUIRE(P && src && dst && e && h && wimg && wimgT && b2d && b2g && WhT && g_up && g_e && g_z1 && g_h,
+              "m3g_conv_tc_bwd: null pointer");
+  M3G_REQUIRE(R >= 1 && R <= TC_BWD_MAX_R, "m3g_conv_tc_bwd: R=%d unsupported (max %d)", R, TC_BWD_MAX_R);
+  M3G_REQUIRE(passes == 1 || passes == 3, "m3g_conv_tc_bwd: passes must be 1 or 3");
+  M3G_REQUIRE(ldp % 4 == 0 && po % 4 == 0, "m3g_conv_tc_bwd: P rows must be 16-byte aligned");
+  cudaError_t err =
+      cudaFuncSetAttribute(conv_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES);
+  if (err != cudaSuccess) {
+    set_error("m3g_conv_tc_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+    return M3G_ERR_CUDA;
+  }
+  ConvTcBwdParams p{P, ldp, po, src, dst, e, h, wimg, wimgT, b2d, b2g, WhT, g_up, g_e_base, E, R, mode, passes,
+                    g_e, g_z1, g_h};
+  int64_t n_tiles = (E + TILE_M - 1) / TILE_M;
+  unsigned grid = (unsigned)((n_tiles < n_sm) ? n_tiles : n_sm);
+  conv_tc_bwd_kernel<<<grid, TC_THREADS, SMEM_BWD_BYTES, as_stream(stream)>>>(p);
+  M3G_LAUNCH_CHECK("m3g_conv_tc_bwd");
+  return M3G_OK;
+}
+
+}  // extern "C"

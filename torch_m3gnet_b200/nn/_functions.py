@@ -12,6 +12,22 @@ from torch.autograd import Function
 from torch_m3gnet_b200._lib import call
 
 
+_SM_COUNT = {}
+
+
+def sm_count(device) -> int:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SM_COUNT[idx]
+
+
+def conv_path() -> str:
+    from torch_m3gnet_b200.nn import conv
+
+    return conv.CONV_PATH
+
+
 def _c(t):
     return None if t is None else t.contiguous()
 
@@ -166,13 +182,21 @@ class ConvFn(Function):
         P = _empty((N, 8 * F), x)
         call("linear_fwd", x, w["WpT"], w["bp"], N, F, 8 * F, P)
         e2 = torch.empty_like(e)
-        ed = w["edge"]
-        call("conv_mlp_fwd", P, 8 * F, 0, plan.src, plan.dst, e, h, ed["W1eT"], ed["W2dT"], ed["b2d"], ed["W2gT"],
-             ed["b2g"], ed["WhT"], E, F, R, 0, e2)
         msg = torch.empty_like(e)
-        nd = w["node"]
-        call("conv_mlp_fwd", P, 8 * F, 4 * F, plan.src, plan.dst, e2, h, nd["W1eT"], nd["W2dT"], nd["b2d"], nd["W2gT"],
-             nd["b2g"], nd["WhT"], E, F, R, 1, msg)
+        ed, nd = w["edge"], w["node"]
+        path = conv_path()
+        if F == 64 and "wimg" in ed and path in ("tc3", "tc1"):
+            passes = 3 if path == "tc3" else 1
+            n_sm = sm_count(x.device)
+            call("conv_tc_fwd", P, 8 * F, 0, plan.src, plan.dst, e, h, ed["wimg"], ed["b2d"], ed["b2g"], ed["WhT"], E, R,
+                 0, passes, n_sm, e2)
+            call("conv_tc_fwd", P, 8 * F, 4 * F, plan.src, plan.dst, e2, h, nd["wimg"], nd["b2d"], nd["b2g"], nd["WhT"],
+                 E, R, 1, passes, n_sm, msg)
+        else:
+            call("conv_mlp_fwd", P, 8 * F, 0, plan.src, plan.dst, e, h, ed["W1eT"], ed["W2dT"], ed["b2d"], ed["W2gT"],
+                 ed["b2g"], ed["WhT"], E, F, R, 0, e2)
+            call("conv_mlp_fwd", P, 8 * F, 4 * F, plan.src, plan.dst, e2, h, nd["W1eT"], nd["W2dT"], nd["b2d"],
+                 nd["W2gT"], nd["b2g"], nd["WhT"], E, F, R, 1, msg)
         x2 = torch.empty_like(x)
         call("segment_sum_add", x, msg, plan.edge_ptr, N, F, x2)
         ctx.plan, ctx.w = plan, w
@@ -192,12 +216,23 @@ class ConvFn(Function):
         nd, ed = w["node"], w["edge"]
         ge2 = torch.empty_like(e)
         gz_node = _empty((E, 2 * F), x)
-        call("conv_mlp_bwd", P, 8 * F, 4 * F, plan.src, plan.dst, e2, h, nd["W1eT"], nd["W2dT"], nd["b2d"], nd["W2gT"],
-             nd["b2g"], nd["WhT"], nd["W1e"], nd["W2d"], nd["W2g"], nd["Wh"], g_x2, g_e2, E, F, R, 1, ge2, gz_node, g_h)
         g_e = torch.empty_like(e)
         gz_edge = _empty((E, 2 * F), x)
-        call("conv_mlp_bwd", P, 8 * F, 0, plan.src, plan.dst, e, h, ed["W1eT"], ed["W2dT"], ed["b2d"], ed["W2gT"],
-             ed["b2g"], ed["WhT"], ed["W1e"], ed["W2d"], ed["W2g"], ed["Wh"], ge2, ge2, E, F, R, 0, g_e, gz_edge, g_h)
+        path = conv_path()
+        if F == 64 and "wimgT" in ed and path in ("tc3", "tc1") and R <= 3:
+            passes = 3 if path == "tc3" else 1
+            n_sm = sm_count(x.device)
+            call("conv_tc_bwd", P, 8 * F, 4 * F, plan.src, plan.dst, e2, h, nd["wimg"], nd["wimgT"], nd["b2d"], nd["b2g"],
+                 nd["WhT"], g_x2, g_e2, E, R, 1, passes, n_sm, ge2, gz_node, g_h)
+            call("conv_tc_bwd", P, 8 * F, 0, plan.src, plan.dst, e, h, ed["wimg"], ed["wimgT"], ed["b2d"], ed["b2g"],
+                 ed["WhT"], ge2, ge2, E, R, 0, passes, n_sm, g_e, gz_edge, g_h)
+        else:
+            call("conv_mlp_bwd", P, 8 * F, 4 * F, plan.src, plan.dst, e2, h, nd["W1eT"], nd["W2dT"], nd["b2d"],
+                 nd["W2gT"], nd["b2g"], nd["WhT"], nd["W1e"], nd["W2d"], nd["W2g"], nd["Wh"], g_x2, g_e2, E, F, R, 1,
+                 ge2, gz_node, g_h)
+            call("conv_mlp_bwd", P, 8 * F, 0, plan.src, plan.dst, e, h, ed["W1eT"], ed["W2dT"], ed["b2d"], ed["W2gT"],
+                 ed["b2g"], ed["WhT"], ed["W1e"], ed["W2d"], ed["W2g"], ed["Wh"], ge2, ge2, E, F, R, 0, g_e, gz_edge,
+                 g_h)
         gP = _empty((N, 8 * F), x)
         call("conv_gather_gz", gz_edge, plan.edge_ptr, plan.in_ptr, plan.in_perm, N, F, 8 * F, 0, gP)
         call("conv_gather_gz", gz_node, plan.edge_ptr, plan.in_ptr, plan.in_perm, N, F, 8 * F, 4 * F, gP)

@@ -1,12 +1,40 @@
 from __future__ import annotations
 
+import os
+
 import torch
 
+from torch_m3gnet_b200._lib import call
 from torch_m3gnet_b200.data import MaterialGraphKey as K
 from torch_m3gnet_b200.data.material_graph import get_plan
 from torch_m3gnet_b200.nn._functions import ConvFn
 from torch_m3gnet_b200.nn._packing import PackedWeights, c_, t_
 from torch_m3gnet_b200.nn.core import GatedMLP
+
+
+# "tc3": tcgen05 3xTF32 (fp32-faithful, default for F = 64 on CUDA), "tc1": plain TF32, "fma": generic fp32 kernels
+CONV_PATH = os.environ.get("M3G_CONV_PATH", "tc3")
+
+
+def _tc_images(w1e: torch.Tensor, w2d: torch.Tensor, w2g: torch.Tensor) -> torch.Tensor:
+    """hi/lo SWIZZLE_128B operand images of the three weight matrices of one gated MLP (csrc/conv_tc.cu)."""
+    out = torch.empty(2 * 128 * 64 + 4 * 64 * 64, dtype=torch.float32, device=w1e.device)
+    with torch.cuda.device(w1e.device):
+        call("tc_pack_b", w1e.contiguous(), 128, 64, out[0:8192], out[8192:16384])
+        call("tc_pack_b", w2d.contiguous(), 64, 64, out[16384:20480], out[20480:24576])
+        call("tc_pack_b", w2g.contiguous(), 64, 64, out[24576:28672], out[28672:32768])
+    return out
+
+
+def _tc_images_transposed(w1eT: torch.Tensor, w2dT: torch.Tensor, w2gT: torch.Tensor) -> torch.Tensor:
+    """Images of the transposed weights for the adjoint GEMMs: [W2d^T, W2g^T, W1e_dense^T, W1e_gate^T] (hi|lo each)."""
+    out = torch.empty(8 * 64 * 64, dtype=torch.float32, device=w1eT.device)
+    mats = [w2dT, w2gT, w1eT[:, :64], w1eT[:, 64:]]
+    with torch.cuda.device(w1eT.device):
+        for i, m in enumerate(mats):
+            base = i * 8192
+            call("tc_pack_b", m.contiguous(), 64, 64, out[base:base + 4096], out[base + 4096:base + 8192])
+    return out
 
 
 class M3GNetConv(torch.nn.Module):
@@ -39,12 +67,16 @@ class M3GNetConv(torch.nn.Module):
         d0, d1 = mlp.linears("dense")
         g0, g1 = mlp.linears("gate")
         w1e = torch.cat([d0.weight[:, 2 * F:], g0.weight[:, 2 * F:]], dim=0).detach()  # (2F, F) (out,in)
-        return {
+        packed = {
             "W1e": w1e.contiguous(), "W1eT": w1e.t().contiguous(),
             "W2d": c_(d1.weight), "W2dT": t_(d1.weight), "b2d": c_(d1.bias),
             "W2g": c_(g1.weight), "W2gT": t_(g1.weight), "b2g": c_(g1.bias),
             "Wh": c_(lin.weight), "WhT": t_(lin.weight),
-        }, d0, g0
+        }
+        if F == 64 and w1e.is_cuda:
+            packed["wimg"] = _tc_images(packed["W1e"], packed["W2d"], packed["W2g"])
+            packed["wimgT"] = _tc_images_transposed(packed["W1eT"], packed["W2dT"], packed["W2gT"])
+        return packed, d0, g0
 
     def _pack(self):
         F = self.num_node_features
