@@ -154,9 +154,10 @@ int m3g_tb_edge_basis_fwd(const float* vec4, const int32_t* dst, const float* si
 int m3g_tb_reduce_fwd(const float* vec4, const float* bas, const int32_t* tri_ptr, const int32_t* tri_e2,
                       const float* tb_consts, const float* WdT, const float* WgT, const float* e_in, int64_t E,
                       int L, int R, int F, int group, float* red, float* e_out, void* stream);
-/* g_red (E,D) from g_e (E,F): adjoint of the bias-free 1-layer GatedMLP (forward recomputed from red) */
-int m3g_tb_gate_bwd(const float* red, const float* g_e, const float* WdT, const float* WgT, int64_t E, int D, int F,
-                    float* g_red, void* stream);
+/* g_red (E,D) from g_e (E,F): adjoint of the bias-free 1-layer GatedMLP (forward recomputed from red); rows
+ * of bonds without triplets (tri_ptr[e+1] == tri_ptr[e]) are zero */
+int m3g_tb_gate_bwd(const float* red, const float* g_e, const float* WdT, const float* WgT, const int32_t* tri_ptr,
+                    int64_t E, int D, int F, float* g_red, void* stream);
 /* gather-form adjoint of the triplet sum (uses tri CSR for "e as first bond" and its transpose for
  * "e as second bond"; they may alias when the list is symmetric).  Outputs: g_vec4 (E,4) (xyz from
  * cos, w from cos and fc(r_e1)), g_bas (E,D).  Legendre backward follows the reference (quirk Q3). */

@@ -202,41 +202,54 @@ __global__ void tb_reduce_fwd_kernel(const float4* __restrict__ vec4, const floa
   }
 }
 
-// adjoint of the bias-free 1-layer gated MLP: one warp per bond
+// adjoint of the bias-free 1-layer gated MLP: 8 lanes per bond (lane g owns features g, g+8, ...), weights staged
+// in shared memory; bonds that are not the first bond of any triplet are skipped (their g_red row is never read
+// as "first bond" data; it is zero-filled so that stale memory cannot leak).
+constexpr int GATE_G = 8;
 __global__ void tb_gate_bwd_kernel(const float* __restrict__ red, const float* __restrict__ g_e,
-                                   const float* __restrict__ WdT, const float* __restrict__ WgT, int64_t E, int D,
-                                   int F, float* __restrict__ g_red) {
-  int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (e >= E) return;
+                                   const float* __restrict__ WdT, const float* __restrict__ WgT,
+                                   const int32_t* __restrict__ tri_ptr, int64_t E, int D, int F,
+                                   float* __restrict__ g_red) {
+  extern __shared__ float w_s[];  // [2][D][F]
   constexpr int DM = M3G_MAX_L * M3G_MAX_R;
+  for (int i = threadIdx.x; i < D * F; i += blockDim.x) {
+    w_s[i] = WdT[i];
+    w_s[D * F + i] = WgT[i];
+  }
+  __syncthreads();
+  int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GATE_G;
+  int gl = threadIdx.x % GATE_G;
+  bool valid = e < E;
+  bool work = valid && (tri_ptr[e + 1] > tri_ptr[e]);
   float rd[DM], acc[DM];
 #pragma unroll
   for (int d = 0; d < DM; ++d) {
-    rd[d] = (d < D) ? red[e * D + d] : 0.0f;
+    rd[d] = (work && d < D) ? red[e * D + d] : 0.0f;
     acc[d] = 0.0f;
   }
-  for (int f = lane; f < F; f += 32) {
-    float u = 0.0f, g = 0.0f;
+  if (work) {
+    for (int f = gl; f < F; f += GATE_G) {
+      float u = 0.0f, g = 0.0f;
 #pragma unroll
-    for (int d = 0; d < DM; ++d)
-      if (d < D) {
-        u += rd[d] * WdT[d * F + f];
-        g += rd[d] * WgT[d * F + f];
-      }
-    float ge = g_e[e * F + f];
-    float sg = sigmoid_acc(g);
-    float du = ge * sg * silu_grad(u);
-    float dg = ge * silu_acc(u) * sg * (1.0f - sg);
+      for (int d = 0; d < DM; ++d)
+        if (d < D) {
+          u += rd[d] * w_s[d * F + f];
+          g += rd[d] * w_s[D * F + d * F + f];
+        }
+      float ge = g_e[e * F + f];
+      float sg = sigmoid_acc(g);
+      float du = ge * sg * silu_grad(u);
+      float dg = ge * silu_acc(u) * sg * (1.0f - sg);
 #pragma unroll
-    for (int d = 0; d < DM; ++d)
-      if (d < D) acc[d] += du * WdT[d * F + f] + dg * WgT[d * F + f];
+      for (int d = 0; d < DM; ++d)
+        if (d < D) acc[d] += du * w_s[d * F + f] + dg * w_s[D * F + d * F + f];
+    }
   }
 #pragma unroll
   for (int d = 0; d < DM; ++d) {
     if (d < D) {
-      float s = warp_sum(acc[d]);
-      if (lane == 0) g_red[e * D + d] = s;
+      float s = group_sum<GATE_G>(acc[d]);
+      if (valid && gl == (d % GATE_G)) g_red[e * D + d] = s;
     }
   }
 }
@@ -475,12 +488,14 @@ int m3g_tb_reduce_fwd(const float* vec4, const float* bas, const int32_t* tri_pt
   return M3G_OK;
 }
 
-int m3g_tb_gate_bwd(const float* red, const float* g_e, const float* WdT, const float* WgT, int64_t E, int D, int F,
-                    float* g_red, void* stream) {
+int m3g_tb_gate_bwd(const float* red, const float* g_e, const float* WdT, const float* WgT, const int32_t* tri_ptr,
+                    int64_t E, int D, int F, float* g_red, void* stream) {
   if (E == 0) return M3G_OK;
-  M3G_REQUIRE(red && g_e && WdT && WgT && g_red, "m3g_tb_gate_bwd: null pointer");
+  M3G_REQUIRE(red && g_e && WdT && WgT && tri_ptr && g_red, "m3g_tb_gate_bwd: null pointer");
   M3G_REQUIRE(D >= 1 && D <= M3G_MAX_L * M3G_MAX_R, "m3g_tb_gate_bwd: D=%d unsupported", D);
-  tb_gate_bwd_kernel<<<blocks_for(E * 32, 256), 256, 0, as_stream(stream)>>>(red, g_e, WdT, WgT, E, D, F, g_red);
+  size_t smem = (size_t)2 * D * F * sizeof(float);
+  tb_gate_bwd_kernel<<<blocks_for(E * GATE_G, 256), 256, smem, as_stream(stream)>>>(red, g_e, WdT, WgT, tri_ptr, E, D,
+                                                                                    F, g_red);
   M3G_LAUNCH_CHECK("m3g_tb_gate_bwd");
   return M3G_OK;
 }

@@ -1,0 +1,289 @@
+"""Spatial domain decomposition of one large periodic cell across ranks (BASELINE.json config 4).
+
+Nothing in the reference corresponds to this (nn/gradient.py:26 "TODO: current implementation cannot be used with
+spatial decomposition").  Scheme (SURVEY.md §7 "scheme B"): every rank owns the atoms of one box of a
+(gx, gy, gz) grid in fractional space and imports one r_c-wide ghost shell.  Every directed edge i→j and every
+triplet is owned by its source / centre atom, so edge features never cross ranks; only node features of ghost
+atoms do:
+
+  per step     ghost positions are part of the local structure (owner position + image shift)
+  per block    forward halo:  x[ghost] <- x[owner]            (N_ghost x F floats, after every M3GNetConv but the last)
+               reverse halo:  dE/dx[owner] += dE/dx[ghost]    (in the backward pass)
+  per step     reverse halo of dE/dpos, then forces of the owned atoms; energies are summed with all_reduce.
+
+The exchange is an ``all_to_all_single`` over NCCL (NVLink / NVSwitch); messages are small (≤ ~1 MB), so the cost
+is latency, not bandwidth.  The same plan drives an in-process emulation of all ranks on one GPU
+(``evaluate_emulated``), which is what the single-GPU test-suite checks against the undecomposed model.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from torch_m3gnet_b200.data import MaterialGraphKey as K
+from torch_m3gnet_b200.data.material_graph import Batch
+from torch_m3gnet_b200.nn.conv import M3GNetConv
+
+
+class DomainPlan:
+    """Host-side partition of one structure: owners, ghosts (atom, image) and the send/recv lists of every rank."""
+
+    def __init__(self, lattice: np.ndarray, cart: np.ndarray, atomic_numbers: np.ndarray, grid: Sequence[int],
+                 cutoff: float):
+        lattice = np.asarray(lattice, dtype=np.float64).reshape(3, 3)
+        cart = np.asarray(cart, dtype=np.float64).reshape(-1, 3)
+        self.lattice, self.cart, self.z = lattice, cart, np.asarray(atomic_numbers, dtype=np.int64)
+        self.grid = tuple(int(g) for g in grid)
+        self.world = int(np.prod(self.grid))
+        self.cutoff = float(cutoff)
+        inv = np.linalg.inv(lattice)
+        heights = 1.0 / np.linalg.norm(inv, axis=0)
+        margin = (cutoff + 1e-6) / heights  # ghost-shell width in fractional units
+        for k in range(3):
+            if 1.0 / self.grid[k] < margin[k] and self.grid[k] > 1:
+                raise ValueError(f"domain width along axis {k} is smaller than the cutoff")
+            if margin[k] >= 1.0:
+                raise ValueError("cell is thinner than the cutoff: use structure sharding, not domain decomposition")
+        frac = cart @ inv
+        wrap = np.floor(frac)
+        f0 = frac - wrap  # in [0,1)
+        cell = np.minimum((f0 * np.array(self.grid)).astype(np.int64), np.array(self.grid) - 1)
+        owner = (cell[:, 0] * self.grid[1] + cell[:, 1]) * self.grid[2] + cell[:, 2]
+        self.owner = owner
+        self.owned: List[np.ndarray] = [np.nonzero(owner == r)[0] for r in range(self.world)]
+        local_of = np.empty(len(cart), dtype=np.int64)
+        for r in range(self.world):
+            local_of[self.owned[r]] = np.arange(len(self.owned[r]))
+        shifts = np.stack(np.meshgrid(*[np.arange(-1, 2)] * 3, indexing="ij"), axis=-1).reshape(-1, 3)
+        # ghosts[r] = list of (atom, image) ordered by (owner rank, position in the owner's send list)
+        self.ghost_atom: List[np.ndarray] = []
+        self.ghost_image: List[np.ndarray] = []
+        self.recv_counts = np.zeros((self.world, self.world), dtype=np.int64)  # [r][q]: r receives from q
+        self.send_index: List[List[np.ndarray]] = [[None] * self.world for _ in range(self.world)]  # [q][r]
+        for r in range(self.world):
+            c = np.array([r // (self.grid[1] * self.grid[2]), (r // self.grid[2]) % self.grid[1], r % self.grid[2]])
+            lo = c / np.array(self.grid) - margin
+            hi = (c + 1) / np.array(self.grid) + margin
+            atoms, images = [], []
+            for s in shifts:
+                fs = f0 + s  # position of the image in fractional units (wrapped coordinates)
+                inside = np.all((fs >= lo) & (fs < hi), axis=1)
+                if not s.any():
+                    inside &= owner != r
+                idx = np.nonzero(inside)[0]
+                if idx.size:
+                    atoms.append(idx)
+                    # image relative to the UNWRAPPED input coordinate of the atom
+                    images.append(np.broadcast_to(s, (idx.size, 3)) - wrap[idx].astype(np.int64))
+            atoms = np.concatenate(atoms) if atoms else np.zeros(0, np.int64)
+            images = np.concatenate(images) if images else np.zeros((0, 3), np.int64)
+            order = np.lexsort((images[:, 2], images[:, 1], images[:, 0], atoms, owner[atoms])) if atoms.size else \
+                np.zeros(0, np.int64)
+            atoms, images = atoms[order], images[order]
+            self.ghost_atom.append(atoms)
+            self.ghost_image.append(images)
+            for q in range(self.world):
+                sel = owner[atoms] == q
+                self.recv_counts[r, q] = int(sel.sum())
+                self.send_index[q][r] = local_of[atoms[sel]]
+        self.wrap = wrap.astype(np.int64)
+
+    def local_arrays(self, r: int) -> Tuple[np.ndarray, np.ndarray, int]:
+        """Positions (owned first, unwrapped-in-place; ghosts = atom + image·lattice) and atomic numbers of rank r."""
+        own = self.owned[r]
+        # owned atoms are used at their wrapped position so that the local cloud is compact
+        own_pos = self.cart[own] - self.wrap[own] @ self.lattice
+        g_atoms, g_img = self.ghost_atom[r], self.ghost_image[r]
+        ghost_pos = self.cart[g_atoms] + g_img @ self.lattice
+        pos = np.concatenate([own_pos, ghost_pos]) if len(g_atoms) else own_pos
+        z = np.concatenate([self.z[own], self.z[g_atoms]]) if len(g_atoms) else self.z[own]
+        return pos, z, len(own)
+
+    def send_concat(self, q: int) -> Tuple[np.ndarray, List[int]]:
+        """Rows rank q packs (ordered by destination rank) and the per-destination counts."""
+        parts = [self.send_index[q][r] for r in range(self.world)]
+        counts = [len(p) for p in parts]
+        return (np.concatenate(parts) if sum(counts) else np.zeros(0, np.int64)), counts
+
+
+class DomainBatch:
+    """The local graph of one rank: owned + ghost atoms in one non-periodic structure, edges of owned sources only."""
+
+    def _exchange_fields(self, dev):
+        plan, rank = self.plan, self.rank
+        send, send_counts = plan.send_concat(rank)
+        self.send_idx = torch.as_tensor(send, dtype=torch.long, device=dev)
+        self.send_counts = [int(c) for c in send_counts]
+        self.recv_counts = [int(c) for c in plan.recv_counts[rank]]
+        self.global_owned = torch.as_tensor(plan.owned[rank], dtype=torch.long, device=dev)
+
+    @classmethod
+    def exchange_only(cls, plan: DomainPlan, rank: int, device="cpu") -> "DomainBatch":
+        """Only the halo-exchange bookkeeping (no graph): used by the host-side (gloo) tests of the exchange."""
+        self = object.__new__(cls)
+        self.plan, self.rank = plan, rank
+        self.n_own = len(plan.owned[rank])
+        self.n_local = self.n_own + len(plan.ghost_atom[rank])
+        self.graph = None
+        self._exchange_fields(torch.device(device))
+        return self
+
+    def __init__(self, plan: DomainPlan, rank: int, cutoff: float, threebody_cutoff: float, device):
+        self.plan, self.rank = plan, rank
+        pos, z, n_own = plan.local_arrays(rank)
+        self.n_own, self.n_local = n_own, len(pos)
+        span = pos.max(axis=0) - pos.min(axis=0) if len(pos) else np.ones(3)
+        box = np.diag(span + 4.0 * cutoff + 1.0)  # no periodic image of the cloud lies within the cutoff
+        full = Batch.from_arrays(box[None], pos, z, [len(pos)], cutoff, threebody_cutoff, device=device)
+        fp = full._plan
+        e_keep = int(fp.edge_ptr[n_own].item())
+        t_keep = int(fp.tri_ptr[e_keep].item()) if e_keep > 0 else 0
+        n_ghost = self.n_local - n_own
+        dev = full[K.POS].device
+        g = Batch(pos=full[K.POS], atom_types=full[K.ATOM_TYPES], num_triplet_i=full[K.NUM_TRIPLET_I],
+                  edge_index=full[K.EDGE_INDEX][:, :e_keep].contiguous(),
+                  edge_cell_shift=full[K.EDGE_CELL_SHIFT][:e_keep].contiguous(),
+                  num_triplet_ij=full[K.NUM_TRIPLET_IJ][:e_keep].contiguous(),
+                  triplet_edge_index=full[K.TRIPLET_EDGE_INDEX][:, :t_keep].contiguous(),
+                  lattice=torch.stack([full[K.LATTICE][0], full[K.LATTICE][0]]))
+        # two "structures": 0 = owned atoms (energy counted), 1 = ghosts (energy discarded)
+        g[K.BATCH] = torch.cat([torch.zeros(n_own, dtype=torch.long, device=dev),
+                                torch.ones(n_ghost, dtype=torch.long, device=dev)])
+        self.graph = g
+        self._exchange_fields(dev)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# halo exchange as autograd functions
+# ----------------------------------------------------------------------------------------------------------------
+class DistHaloFn(torch.autograd.Function):
+    """One rank's view: ghost rows of ``x`` are replaced by the owners' rows (all_to_all_single); the backward adds
+    the ghost-row gradients into the owners' rows."""
+
+    @staticmethod
+    def forward(ctx, x, dbatch: DomainBatch, group):
+        import torch.distributed as dist
+
+        send = x.index_select(0, dbatch.send_idx).contiguous()
+        recv = x.new_empty((sum(dbatch.recv_counts),) + tuple(x.shape[1:]))
+        dist.all_to_all_single(recv, send, dbatch.recv_counts, dbatch.send_counts, group=group)
+        out = x.clone()
+        out[dbatch.n_own:] = recv
+        ctx.dbatch, ctx.group = dbatch, group
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        import torch.distributed as dist
+
+        d = ctx.dbatch
+        g_ghost = g[d.n_own:].contiguous()
+        back = g.new_empty((sum(d.send_counts),) + tuple(g.shape[1:]))
+        dist.all_to_all_single(back, g_ghost, d.send_counts, d.recv_counts, group=ctx.group)
+        g_in = g.clone()
+        g_in[d.n_own:] = 0
+        g_in.index_add_(0, d.send_idx, back)
+        return g_in, None, None
+
+
+class EmulatedHaloFn(torch.autograd.Function):
+    """All ranks in one process (single-GPU emulation of the exchange; same plan, same ordering)."""
+
+    @staticmethod
+    def forward(ctx, dbatches, *xs):
+        outs = [x.clone() for x in xs]
+        world = len(xs)
+        for r in range(world):
+            off = dbatches[r].n_own
+            for q in range(world):
+                cnt = dbatches[r].recv_counts[q]
+                if cnt:
+                    s0 = sum(dbatches[q].send_counts[:r])
+                    outs[r][off:off + cnt] = xs[q].index_select(0, dbatches[q].send_idx[s0:s0 + cnt])
+                off += cnt
+        ctx.dbatches = dbatches
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        dbatches = ctx.dbatches
+        world = len(gs)
+        g_in = []
+        for r in range(world):
+            t = gs[r].clone()
+            t[dbatches[r].n_own:] = 0
+            g_in.append(t)
+        for r in range(world):
+            off = dbatches[r].n_own
+            for q in range(world):
+                cnt = dbatches[r].recv_counts[q]
+                if cnt:
+                    s0 = sum(dbatches[q].send_counts[:r])
+                    g_in[q].index_add_(0, dbatches[q].send_idx[s0:s0 + cnt], gs[r][off:off + cnt])
+                off += cnt
+        return (None,) + tuple(g_in)
+
+
+def _modules_of(model):
+    seq = model.model if hasattr(model, "model") else model
+    mods = list(seq)
+    last_conv = max(i for i, m in enumerate(mods) if isinstance(m, M3GNetConv))
+    return mods, last_conv
+
+
+def evaluate_distributed(model, dbatch: DomainBatch, group=None) -> Dict[str, torch.Tensor]:
+    """Energy (global, all-reduced) and forces of the atoms this rank owns.  One process per GPU."""
+    import torch.distributed as dist
+
+    mods, last_conv = _modules_of(model)
+    graph = dbatch.graph
+    pos = graph[K.POS]
+    pos.requires_grad_(True)
+    for i, m in enumerate(mods):
+        graph = m(graph)
+        if isinstance(m, M3GNetConv) and i != last_conv:
+            graph[K.NODE_FEATURES] = DistHaloFn.apply(graph[K.NODE_FEATURES], dbatch, group)
+    energy = graph[K.TOTAL_ENERGY]
+    weight = torch.tensor([1.0, 0.0], device=energy.device)
+    (g_pos,) = torch.autograd.grad(energy, pos, grad_outputs=weight)
+    pos.requires_grad_(False)
+    # reverse halo of dE/dpos: ghost gradients go home
+    back = g_pos.new_empty((sum(dbatch.send_counts), 3))
+    dist.all_to_all_single(back, g_pos[dbatch.n_own:].contiguous(), dbatch.send_counts, dbatch.recv_counts, group=group)
+    g_own = g_pos[:dbatch.n_own].clone()
+    g_own.index_add_(0, dbatch.send_idx, back)
+    e_total = energy[0:1].detach().clone()
+    dist.all_reduce(e_total, group=group)
+    graph._private.clear()
+    return {"total_energy": e_total, "forces": -g_own, "owned": dbatch.global_owned,
+            "local_energy": energy[0:1].detach()}
+
+
+def evaluate_emulated(model, dbatches: List[DomainBatch]) -> Dict[str, torch.Tensor]:
+    """All ranks of a plan evaluated in lockstep on one GPU; returns the global energy and forces in atom order."""
+    mods, last_conv = _modules_of(model)
+    graphs = [d.graph for d in dbatches]
+    for g in graphs:
+        g[K.POS].requires_grad_(True)
+    for i, m in enumerate(mods):
+        graphs = [m(g) for g in graphs]
+        if isinstance(m, M3GNetConv) and i != last_conv:
+            xs = EmulatedHaloFn.apply(dbatches, *[g[K.NODE_FEATURES] for g in graphs])
+            for g, x in zip(graphs, xs):
+                g[K.NODE_FEATURES] = x
+    energies = [g[K.TOTAL_ENERGY] for g in graphs]
+    total = sum(e[0] for e in energies)
+    grads = torch.autograd.grad(total, [g[K.POS] for g in graphs])
+    n_atoms = len(dbatches[0].plan.cart)
+    forces = torch.zeros((n_atoms, 3), dtype=torch.float32, device=grads[0].device)
+    plan = dbatches[0].plan
+    for r, (d, gp) in enumerate(zip(dbatches, grads)):
+        graphs[r][K.POS].requires_grad_(False)
+        forces.index_add_(0, d.global_owned, -gp[: d.n_own])
+        if len(plan.ghost_atom[r]):
+            ghost_global = torch.as_tensor(plan.ghost_atom[r], dtype=torch.long, device=gp.device)
+            forces.index_add_(0, ghost_global, -gp[d.n_own:])
+        graphs[r]._private.clear()
+    return {"total_energy": total.detach().reshape(1), "forces": forces}

@@ -158,7 +158,7 @@ class ThreeBodyFn(Function):
         E, N, D = plan.E, plan.N, L * R
         g_e = g_e.contiguous()
         g_red = torch.empty_like(red)
-        call("tb_gate_bwd", red, g_e, w["WdT"], w["WgT"], E, D, F, g_red)
+        call("tb_gate_bwd", red, g_e, w["WdT"], w["WgT"], plan.tri_ptr, E, D, F, g_red)
         g_vec4 = torch.empty_like(vec4)
         g_bas = torch.empty_like(bas)
         call("tb_reduce_bwd", vec4, bas, g_red, plan.tri_ptr, plan.tri_e2, plan.trt_ptr, plan.trt_e1, w["consts"], E,
