@@ -172,6 +172,19 @@ int m3g_tb_edge_basis_bwd(const float* vec4, const int32_t* dst, const float* si
 int m3g_tb_sigma_bwd(const float* g_sig_e, const int32_t* in_ptr, const int32_t* in_perm, const float* sig,
                      const float* Ws, int64_t N, int F, int D, float* g_x, void* stream);
 
+/* Specialised variants for the default model shape l_max = n_max = 3, F = 64 (compile-time loops, gated-MLP
+ * weights in shared memory, vector row I/O, persistent grid of 8 x n_sm blocks).  Same results and buffers as
+ * the generic entry points above; r3 = three-body cutoff.  m3g_tb_reduce_bwd_sym requires a symmetric triplet
+ * list ((e1,e2) present <=> (e2,e1) present — always true for graphs from from_structure). */
+int m3g_tb_reduce_fwd_fast(const float* vec4, const float* bas, const int32_t* tri_ptr, const int32_t* tri_e2,
+                           float r3, const float* WdT, const float* WgT, const float* e_in, int64_t E, int group,
+                           int n_sm, float* red, float* e_out, void* stream);
+int m3g_tb_gate_bwd_fast(const float* red, const float* g_e, const float* WdT, const float* WgT,
+                         const int32_t* tri_ptr, int64_t E, int n_sm, float* g_red, void* stream);
+int m3g_tb_reduce_bwd_sym(const float* vec4, const float* bas, const float* g_red, const int32_t* tri_ptr,
+                          const int32_t* tri_e2, float r3, int64_t E, int group, int n_sm, float* g_vec4, float* g_bas,
+                          void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Generic row-wise linear: out (n,M) = in (n,K) · Wt (K,M) + bias (M or NULL).  Used for the per-atom
  * first-layer projections of M3GNetConv (nn/conv.py:92-97 concat split: [x_i,x_j,e]·W = x_i·W_i + x_j·W_j + e·W_e)

@@ -116,7 +116,17 @@ def _threebody_reference_grads(g, gd):
     return out, red, gx, ge, gv
 
 
-def test_threebody_operator(device):
+@pytest.fixture(params=["fast", "generic"])
+def tb_path(request):
+    from torch_m3gnet_b200.nn import interaction
+
+    old = interaction.TB_PATH
+    interaction.TB_PATH = request.param
+    yield request.param
+    interaction.TB_PATH = old
+
+
+def test_threebody_operator(device, tb_path):
     """Operator-level parity with an O(1) factor table and non-unit upstream gradients (quirks Q1, Q3)."""
     from torch_m3gnet_b200.nn.interaction import ThreeBodyInteration
 
@@ -161,7 +171,7 @@ def test_threebody_operator(device):
     report("tb.g_pos", gp, gp_o, 5e-5, 5e-5)
 
 
-def test_threebody_asymmetric_triplet_list(device):
+def test_threebody_asymmetric_triplet_list(device, tb_path):
     """A hand-made triplet list that is not symmetric exercises the transposed CSR path."""
     from torch_m3gnet_b200.nn.interaction import ThreeBodyInteration
 

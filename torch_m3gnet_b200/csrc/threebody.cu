@@ -430,6 +430,240 @@ __global__ void tb_sigma_bwd_kernel(const float* __restrict__ g_sig_e, const int
   }
 }
 
+// ================================================================================================
+// Specialised kernels for the default model shape (l_max = n_max = 3, F = 64): compile-time loops, gated-MLP
+// weights in shared memory, every lane owns F/G contiguous features (vector loads / stores of the edge rows),
+// persistent blocks (grid-stride over bond groups) so that the weight staging is amortised.
+// ================================================================================================
+constexpr int FD = 9;   // D = 3 x 3
+constexpr int FF = 64;  // feature width
+
+__device__ __forceinline__ float silu_f(float z) { return __fdividef(z, 1.0f + __expf(-z)); }
+__device__ __forceinline__ float sigmoid_f(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
+
+__device__ __forceinline__ void legendre3(float x, float& y0, float& y1, float& y2) {
+  y0 = kYpref[0];
+  y1 = kYpref[1] * x;
+  y2 = kYpref[2] * ((3.0f * x * x - 1.0f) * 0.5f);
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) tb_reduce_fwd_fast_kernel(
+    const float4* __restrict__ vec4, const float* __restrict__ bas, const int32_t* __restrict__ tri_ptr,
+    const int32_t* __restrict__ tri_e2, float r3, const float* __restrict__ WdT, const float* __restrict__ WgT,
+    const float* __restrict__ e_in, int64_t E, float* __restrict__ red, float* __restrict__ e_out) {
+  constexpr int FPL = FF / G;
+  __shared__ __align__(16) float wd_s[FD * FF];
+  __shared__ __align__(16) float wg_s[FD * FF];
+  for (int i = threadIdx.x; i < FD * FF; i += blockDim.x) {
+    wd_s[i] = WdT[i];
+    wg_s[i] = WgT[i];
+  }
+  __syncthreads();
+  const int gpb = 256 / G;
+  const int gl = threadIdx.x % G;
+  const int f0 = gl * FPL;
+  for (int64_t base = (int64_t)blockIdx.x * gpb; base < E; base += (int64_t)gridDim.x * gpb) {
+    int64_t e1 = base + threadIdx.x / G;
+    bool valid = e1 < E;
+    float acc[FD];
+#pragma unroll
+    for (int d = 0; d < FD; ++d) acc[d] = 0.0f;
+    float4 v1 = make_float4(0.f, 0.f, 0.f, 1.f);
+    int beg = 0, end = 0;
+    if (valid) {
+      v1 = vec4[e1];
+      beg = tri_ptr[e1];
+      end = tri_ptr[e1 + 1];
+    }
+    for (int p = beg + gl; p < end; p += G) {
+      int e2 = tri_e2[p];
+      float4 v2 = vec4[e2];
+      float dot = __fadd_rn(__fadd_rn(__fmul_rn(v1.x, v2.x), __fmul_rn(v1.y, v2.y)), __fmul_rn(v1.z, v2.z));
+      float cs = fminf(fmaxf(__fdiv_rn(dot, __fmul_rn(v1.w, v2.w)), -1.0f), 1.0f);
+      float y0, y1, y2;
+      legendre3(cs, y0, y1, y2);
+      const float* b2 = bas + (int64_t)e2 * FD;
+      acc[0] += y0 * b2[0]; acc[1] += y0 * b2[1]; acc[2] += y0 * b2[2];
+      acc[3] += y1 * b2[3]; acc[4] += y1 * b2[4]; acc[5] += y1 * b2[5];
+      acc[6] += y2 * b2[6]; acc[7] += y2 * b2[7]; acc[8] += y2 * b2[8];
+    }
+    float c1 = valid ? cutoff_poly(v1.w, r3) : 0.0f;
+#pragma unroll
+    for (int d = 0; d < FD; ++d) acc[d] = c1 * group_sum<G>(acc[d]);
+    if (!valid) continue;
+    if (gl == 0) {
+#pragma unroll
+      for (int d = 0; d < FD; ++d) red[e1 * FD + d] = acc[d];
+    }
+    float row[FPL];
+#pragma unroll
+    for (int j = 0; j < FPL; j += 2) {
+      float2 t = *reinterpret_cast<const float2*>(e_in + e1 * FF + f0 + j);
+      row[j] = t.x;
+      row[j + 1] = t.y;
+    }
+    if (end > beg) {
+      float u[FPL], g[FPL];
+#pragma unroll
+      for (int j = 0; j < FPL; ++j) { u[j] = 0.0f; g[j] = 0.0f; }
+#pragma unroll
+      for (int d = 0; d < FD; ++d) {
+#pragma unroll
+        for (int j = 0; j < FPL; ++j) {
+          u[j] += acc[d] * wd_s[d * FF + f0 + j];
+          g[j] += acc[d] * wg_s[d * FF + f0 + j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < FPL; ++j) row[j] += silu_f(u[j]) * sigmoid_f(g[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < FPL; j += 2)
+      *reinterpret_cast<float2*>(e_out + e1 * FF + f0 + j) = make_float2(row[j], row[j + 1]);
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) tb_gate_bwd_fast_kernel(
+    const float* __restrict__ red, const float* __restrict__ g_e, const float* __restrict__ WdT,
+    const float* __restrict__ WgT, const int32_t* __restrict__ tri_ptr, int64_t E, float* __restrict__ g_red) {
+  constexpr int FPL = FF / G;
+  __shared__ __align__(16) float wd_s[FD * FF];
+  __shared__ __align__(16) float wg_s[FD * FF];
+  for (int i = threadIdx.x; i < FD * FF; i += blockDim.x) {
+    wd_s[i] = WdT[i];
+    wg_s[i] = WgT[i];
+  }
+  __syncthreads();
+  const int gpb = 256 / G;
+  const int gl = threadIdx.x % G;
+  const int f0 = gl * FPL;
+  for (int64_t base = (int64_t)blockIdx.x * gpb; base < E; base += (int64_t)gridDim.x * gpb) {
+    int64_t e = base + threadIdx.x / G;
+    bool valid = e < E;
+    bool work = valid && (tri_ptr[e + 1] > tri_ptr[e]);
+    float acc[FD];
+#pragma unroll
+    for (int d = 0; d < FD; ++d) acc[d] = 0.0f;
+    if (work) {
+      float rd[FD];
+#pragma unroll
+      for (int d = 0; d < FD; ++d) rd[d] = red[e * FD + d];
+      float u[FPL], g[FPL];
+#pragma unroll
+      for (int j = 0; j < FPL; ++j) { u[j] = 0.0f; g[j] = 0.0f; }
+#pragma unroll
+      for (int d = 0; d < FD; ++d)
+#pragma unroll
+        for (int j = 0; j < FPL; ++j) {
+          u[j] += rd[d] * wd_s[d * FF + f0 + j];
+          g[j] += rd[d] * wg_s[d * FF + f0 + j];
+        }
+#pragma unroll
+      for (int j = 0; j < FPL; j += 2) {
+        float2 ge2 = *reinterpret_cast<const float2*>(g_e + e * FF + f0 + j);
+        float gev[2] = {ge2.x, ge2.y};
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          float sg = sigmoid_f(g[j + t]);
+          float su = sigmoid_f(u[j + t]);
+          float du = gev[t] * sg * su * (1.0f + u[j + t] * (1.0f - su));
+          float dg = gev[t] * (u[j + t] * su) * sg * (1.0f - sg);
+#pragma unroll
+          for (int d = 0; d < FD; ++d)
+            acc[d] += du * wd_s[d * FF + f0 + j + t] + dg * wg_s[d * FF + f0 + j + t];
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < FD; ++d) acc[d] = group_sum<G>(acc[d]);
+    if (valid && gl == 0) {
+#pragma unroll
+      for (int d = 0; d < FD; ++d) g_red[e * FD + d] = acc[d];
+    }
+  }
+}
+
+// symmetric triplet lists ((e,p) present <=> (p,e) present): one sweep over the partners serves both roles of e
+template <int G>
+__global__ void __launch_bounds__(256) tb_reduce_bwd_sym_kernel(
+    const float4* __restrict__ vec4, const float* __restrict__ bas, const float* __restrict__ g_red,
+    const int32_t* __restrict__ tri_ptr, const int32_t* __restrict__ tri_e2, float r3, int64_t E,
+    float4* __restrict__ g_vec4, float* __restrict__ g_bas) {
+  const int gpb = 256 / G;
+  const int gl = threadIdx.x % G;
+  for (int64_t base = (int64_t)blockIdx.x * gpb; base < E; base += (int64_t)gridDim.x * gpb) {
+    int64_t e = base + threadIdx.x / G;
+    bool valid = e < E;
+    float4 ve = make_float4(0.f, 0.f, 0.f, 1.f);
+    float d1[FD], be[FD], gB[FD];
+#pragma unroll
+    for (int d = 0; d < FD; ++d) { d1[d] = 0.f; be[d] = 0.f; gB[d] = 0.f; }
+    int beg = 0, end = 0;
+    if (valid) {
+      ve = vec4[e];
+      beg = tri_ptr[e];
+      end = tri_ptr[e + 1];
+      if (end > beg) {
+#pragma unroll
+        for (int d = 0; d < FD; ++d) {
+          d1[d] = g_red[e * FD + d];
+          be[d] = bas[e * FD + d];
+        }
+      }
+    }
+    const float ce = cutoff_poly(ve.w, r3);
+    float gx = 0.f, gy = 0.f, gz = 0.f, gr = 0.f, gc = 0.f;
+    for (int p = beg + gl; p < end; p += G) {
+      int ep = tri_e2[p];
+      float4 vp = vec4[ep];
+      float cp = cutoff_poly(vp.w, r3);
+      float inv = 1.0f / (ve.w * vp.w);
+      float craw = (ve.x * vp.x + ve.y * vp.y + ve.z * vp.z) * inv;
+      bool inside = (craw >= -1.0f) && (craw <= 1.0f);
+      float cs = fminf(fmaxf(craw, -1.0f), 1.0f);
+      float y0, y1, y2;
+      legendre3(cs, y0, y1, y2);
+      const float* bp = bas + (int64_t)ep * FD;
+      const float* dq = g_red + (int64_t)ep * FD;
+      float b[FD], q[FD];
+#pragma unroll
+      for (int d = 0; d < FD; ++d) { b[d] = bp[d]; q[d] = dq[d]; }
+      // e as first bond of (e, p)
+      float s0 = b[0] * d1[0] + b[1] * d1[1] + b[2] * d1[2];
+      float s1 = b[3] * d1[3] + b[4] * d1[4] + b[5] * d1[5];
+      float s2 = b[6] * d1[6] + b[7] * d1[7] + b[8] * d1[8];
+      gc += y0 * s0 + y1 * s1 + y2 * s2;
+      // e as second bond of (p, e)
+      float w0 = y0 * cp, w1 = y1 * cp, w2 = y2 * cp;
+      gB[0] += w0 * q[0]; gB[1] += w0 * q[1]; gB[2] += w0 * q[2];
+      gB[3] += w1 * q[3]; gB[4] += w1 * q[4]; gB[5] += w1 * q[5];
+      gB[6] += w2 * q[6]; gB[7] += w2 * q[7]; gB[8] += w2 * q[8];
+      float t1 = be[3] * q[3] + be[4] * q[4] + be[5] * q[5];
+      float t2 = be[6] * q[6] + be[7] * q[7] + be[8] * q[8];
+      // Legendre backward with the reference's per-level grad_output (quirk Q3): l=1: go; l=2: go*(2x + x*go)
+      float goA1 = kYpref[1] * ce * s1, goA2 = kYpref[2] * ce * s2;
+      float goB1 = kYpref[1] * cp * t1, goB2 = kYpref[2] * cp * t2;
+      float gcos = goA1 + goA2 * (2.0f * cs + cs * goA2) + goB1 + goB2 * (2.0f * cs + cs * goB2);
+      if (inside) {
+        float w = gcos * inv;
+        gx += w * vp.x; gy += w * vp.y; gz += w * vp.z;
+        gr -= gcos * craw / ve.w;
+      }
+    }
+    gx = group_sum<G>(gx); gy = group_sum<G>(gy); gz = group_sum<G>(gz);
+    gr = group_sum<G>(gr); gc = group_sum<G>(gc);
+#pragma unroll
+    for (int d = 0; d < FD; ++d) gB[d] = group_sum<G>(gB[d]);
+    if (!valid || gl != 0) continue;
+    gr += gc * cutoff_poly_grad(ve.w, r3);
+    g_vec4[e] = make_float4(gx, gy, gz, gr);
+#pragma unroll
+    for (int d = 0; d < FD; ++d) g_bas[e * FD + d] = gB[d];
+  }
+}
+
 }  // namespace m3g
 
 using namespace m3g;
@@ -543,6 +777,54 @@ int m3g_tb_sigma_bwd(const float* g_sig_e, const int32_t* in_ptr, const int32_t*
   tb_sigma_bwd_kernel<<<blocks_for(N * 32, 256), 256, 0, as_stream(stream)>>>(g_sig_e, in_ptr, in_perm, sig, Ws, N,
                                                                               F, D, g_x);
   M3G_LAUNCH_CHECK("m3g_tb_sigma_bwd");
+  return M3G_OK;
+}
+
+#define M3G_GROUP_SWITCH(KERNEL, GRID_EXPR, ...)                                                      \
+  do {                                                                                               \
+    if (group == 8) KERNEL<8><<<GRID_EXPR(8), 256, 0, as_stream(stream)>>>(__VA_ARGS__);              \
+    else if (group == 16) KERNEL<16><<<GRID_EXPR(16), 256, 0, as_stream(stream)>>>(__VA_ARGS__);      \
+    else KERNEL<32><<<GRID_EXPR(32), 256, 0, as_stream(stream)>>>(__VA_ARGS__);                       \
+  } while (0)
+
+static inline unsigned persistent_grid(int64_t E, int group, int n_sm) {
+  int64_t need = (E * group + 255) / 256;
+  int64_t cap = (int64_t)n_sm * 8;
+  return (unsigned)((need < cap) ? (need < 1 ? 1 : need) : cap);
+}
+#define M3G_PGRID(G_) persistent_grid(E, G_, n_sm)
+
+int m3g_tb_reduce_fwd_fast(const float* vec4, const float* bas, const int32_t* tri_ptr, const int32_t* tri_e2,
+                           float r3, const float* WdT, const float* WgT, const float* e_in, int64_t E, int group,
+                           int n_sm, float* red, float* e_out, void* stream) {
+  if (E == 0) return M3G_OK;
+  M3G_REQUIRE(vec4 && bas && tri_ptr && WdT && WgT && e_in && red && e_out, "m3g_tb_reduce_fwd_fast: null pointer");
+  M3G_REQUIRE(group == 8 || group == 16 || group == 32, "m3g_tb_reduce_fwd_fast: group must be 8, 16 or 32");
+  M3G_GROUP_SWITCH(tb_reduce_fwd_fast_kernel, M3G_PGRID, (const float4*)vec4, bas, tri_ptr, tri_e2, r3, WdT, WgT, e_in,
+                   E, red, e_out);
+  M3G_LAUNCH_CHECK("m3g_tb_reduce_fwd_fast");
+  return M3G_OK;
+}
+
+int m3g_tb_gate_bwd_fast(const float* red, const float* g_e, const float* WdT, const float* WgT,
+                         const int32_t* tri_ptr, int64_t E, int n_sm, float* g_red, void* stream) {
+  if (E == 0) return M3G_OK;
+  M3G_REQUIRE(red && g_e && WdT && WgT && tri_ptr && g_red, "m3g_tb_gate_bwd_fast: null pointer");
+  tb_gate_bwd_fast_kernel<8><<<persistent_grid(E, 8, n_sm), 256, 0, as_stream(stream)>>>(red, g_e, WdT, WgT, tri_ptr,
+                                                                                         E, g_red);
+  M3G_LAUNCH_CHECK("m3g_tb_gate_bwd_fast");
+  return M3G_OK;
+}
+
+int m3g_tb_reduce_bwd_sym(const float* vec4, const float* bas, const float* g_red, const int32_t* tri_ptr,
+                          const int32_t* tri_e2, float r3, int64_t E, int group, int n_sm, float* g_vec4, float* g_bas,
+                          void* stream) {
+  if (E == 0) return M3G_OK;
+  M3G_REQUIRE(vec4 && bas && g_red && tri_ptr && g_vec4 && g_bas, "m3g_tb_reduce_bwd_sym: null pointer");
+  M3G_REQUIRE(group == 8 || group == 16 || group == 32, "m3g_tb_reduce_bwd_sym: group must be 8, 16 or 32");
+  M3G_GROUP_SWITCH(tb_reduce_bwd_sym_kernel, M3G_PGRID, (const float4*)vec4, bas, g_red, tri_ptr, tri_e2, r3, E,
+                   (float4*)g_vec4, g_bas);
+  M3G_LAUNCH_CHECK("m3g_tb_reduce_bwd_sym");
   return M3G_OK;
 }
 

@@ -22,6 +22,12 @@ def sm_count(device) -> int:
     return _SM_COUNT[idx]
 
 
+def tb_path() -> str:
+    from torch_m3gnet_b200.nn import interaction
+
+    return interaction.TB_PATH
+
+
 def conv_path() -> str:
     from torch_m3gnet_b200.nn import conv
 
@@ -145,9 +151,14 @@ class ThreeBodyFn(Function):
         call("tb_edge_basis_fwd", vec4, plan.dst, sig, w["consts"], E, L, R, bas)
         red = _empty((E, D), x)
         e_out = torch.empty_like(e)
-        call("tb_reduce_fwd", vec4, bas, plan.tri_ptr, plan.tri_e2, w["consts"], w["WdT"], w["WgT"], e, E, L, R, F,
-             plan.tri_group, red, e_out)
-        ctx.plan, ctx.w, ctx.L, ctx.R, ctx.F = plan, w, L, R, F
+        fast = (L, R, F) == (3, 3, 64) and tb_path() == "fast"
+        if fast:
+            call("tb_reduce_fwd_fast", vec4, bas, plan.tri_ptr, plan.tri_e2, w["r3"], w["WdT"], w["WgT"], e, E,
+                 plan.tri_group, sm_count(x.device), red, e_out)
+        else:
+            call("tb_reduce_fwd", vec4, bas, plan.tri_ptr, plan.tri_e2, w["consts"], w["WdT"], w["WgT"], e, E, L, R, F,
+                 plan.tri_group, red, e_out)
+        ctx.plan, ctx.w, ctx.L, ctx.R, ctx.F, ctx.fast = plan, w, L, R, F, fast
         ctx.save_for_backward(vec4, sig, bas, red)
         return e_out
 
@@ -158,11 +169,19 @@ class ThreeBodyFn(Function):
         E, N, D = plan.E, plan.N, L * R
         g_e = g_e.contiguous()
         g_red = torch.empty_like(red)
-        call("tb_gate_bwd", red, g_e, w["WdT"], w["WgT"], plan.tri_ptr, E, D, F, g_red)
         g_vec4 = torch.empty_like(vec4)
         g_bas = torch.empty_like(bas)
-        call("tb_reduce_bwd", vec4, bas, g_red, plan.tri_ptr, plan.tri_e2, plan.trt_ptr, plan.trt_e1, w["consts"], E,
-             L, R, plan.tri_group, g_vec4, g_bas)
+        if ctx.fast:
+            n_sm = sm_count(vec4.device)
+            call("tb_gate_bwd_fast", red, g_e, w["WdT"], w["WgT"], plan.tri_ptr, E, n_sm, g_red)
+        else:
+            call("tb_gate_bwd", red, g_e, w["WdT"], w["WgT"], plan.tri_ptr, E, D, F, g_red)
+        if ctx.fast and plan.tri_symmetric:
+            call("tb_reduce_bwd_sym", vec4, bas, g_red, plan.tri_ptr, plan.tri_e2, w["r3"], E, plan.tri_group, n_sm,
+                 g_vec4, g_bas)
+        else:
+            call("tb_reduce_bwd", vec4, bas, g_red, plan.tri_ptr, plan.tri_e2, plan.trt_ptr, plan.trt_e1, w["consts"],
+                 E, L, R, plan.tri_group, g_vec4, g_bas)
         g_sig_e = g_red  # reuse the buffer: g_red is dead after tb_reduce_bwd
         call("tb_edge_basis_bwd", vec4, plan.dst, sig, g_bas, w["consts"], E, L, R, g_vec4, g_sig_e)
         g_x = _empty((N, F), vec4)

@@ -1,6 +1,7 @@
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -11,6 +12,9 @@ from torch_m3gnet_b200.nn._functions import CutoffFn, LegendreCosFn, SphericalBe
 from torch_m3gnet_b200.nn._packing import PackedWeights, c_, t_
 from torch_m3gnet_b200.nn.core import GatedMLP
 from torch_m3gnet_b200.nn.invariant import PAIR_VEC4
+
+# "fast": specialised kernels for (l_max, n_max, F) = (3, 3, 64); "generic": the width-agnostic kernels everywhere
+TB_PATH = os.environ.get("M3G_TB_PATH", "fast")
 
 __all__ = ["ThreeBodyInteration", "NormalizedSphericalBessel", "SPHERICAL_BESSEL_ZEROS", "spherical_bessel",
            "legendre_cos", "cutoff_function"]
@@ -100,7 +104,7 @@ class ThreeBodyInteration(torch.nn.Module):
         return {
             "Ws": c_(self.linear_sigmoid1.weight), "bs": c_(self.linear_sigmoid1.bias),
             "WdT": t_(self.gated_mlp.dense[0].weight), "WgT": t_(self.gated_mlp.gate[0].weight),
-            "consts": torch.cat([zeros, fac, tail]).contiguous(),
+            "consts": torch.cat([zeros, fac, tail]).contiguous(), "r3": float(self.threebody_cutoff),
         }
 
     def forward(self, graph):
