@@ -229,15 +229,17 @@ int m3g_linear_bwd_input(const float* g, const float* W, const float* base, int6
  * m3g_tc_pack_b writes the hi / lo SWIZZLE_128B operand images of a (rows x cols) row-major weight matrix
  * (rows % 8 == 0, cols % 32 == 0; each image rows*cols floats).  wimg = [W1e hi | W1e lo | W2d hi | W2d lo |
  * W2g hi | W2g lo] with W1e (128 x 64) = rows [dense | gate] of the e-part of layer 1, W2d/W2g (64 x 64), all in
- * the reference's (out,in) orientation.  n_sm = number of SMs (persistent grid).
+ * the reference's (out,in) orientation.  n_sm = number of SMs (persistent grid).  variant 1 = one tile per CTA at
+ * a time (8 warps); variant 2 = two warp groups per CTA ping-pong two tiles over the shared operand buffer.
  * ------------------------------------------------------------------------------------------- */
 int m3g_tc_pack_b(const float* W, int rows, int cols, float* img_hi, float* img_lo, void* stream);
-/* UMMA plumbing self test on one 128-row tile: out (128 x rows) = A (128 x cols) · W^T, W given as its image */
+/* UMMA plumbing self test on one 128-row tile: out (128 x rows) = A (128 x cols) · W^T, W given as its image;
+ * a_tmem = 1 feeds A from tensor memory (tcgen05.st + the [a_tmem] operand form) instead of shared memory */
 int m3g_tc_selftest(const float* A, const float* img_hi, const float* img_lo, int rows, int cols, int passes,
-                    float* out, void* stream);
+                    int a_tmem, float* out, void* stream);
 int m3g_conv_tc_fwd(const float* P, int ldp, int po, const int32_t* src, const int32_t* dst, const float* e,
                     const float* h, const float* wimg, const float* b2d, const float* b2g, const float* WhT, int64_t E,
-                    int R, int mode, int passes, int n_sm, float* y, void* stream);
+                    int R, int mode, int passes, int variant, int n_sm, float* y, void* stream);
 
 /* adjoint of m3g_conv_tc_fwd (same outputs as m3g_conv_mlp_bwd; forward recomputed on the tensor cores).
  * wimgT = [W2d^T hi|lo, W2g^T hi|lo, W1e_dense^T hi|lo, W1e_gate^T hi|lo]: four 64x64 image pairs from

@@ -20,11 +20,12 @@ def test_umma_selftest(device, rows, cols):
     lo = torch.empty(rows * cols, device=device)
     _lib.call("tc_pack_b", W, rows, cols, hi, lo)
     want = (A.double() @ W.double().t()).float()
-    for passes, tol in ((3, 1e-5), (1, 3e-3)):
-        out = torch.full((128, rows), float("nan"), device=device)
-        _lib.call("tc_selftest", A, hi, lo, rows, cols, passes, out)
-        torch.cuda.synchronize()
-        report(f"umma rows={rows} cols={cols} passes={passes}", out, want, 0, tol)
+    for a_tmem in (0, 1):
+        for passes, tol in ((3, 1e-5), (1, 3e-3)):
+            out = torch.full((128, rows), float("nan"), device=device)
+            _lib.call("tc_selftest", A, hi, lo, rows, cols, passes, a_tmem, out)
+            torch.cuda.synchronize()
+            report(f"umma rows={rows} cols={cols} passes={passes} a_tmem={a_tmem}", out, want, 0, tol)
 
 
 @pytest.mark.parametrize("path", ["tc3", "tc1"])

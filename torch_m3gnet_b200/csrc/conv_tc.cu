@@ -57,6 +57,21 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_hi, uint3
   }
 }
 
+// Same product with the A operand in tensor memory: A_hi at columns [ta_hi, ta_hi+K), A_lo at [ta_lo, ta_lo+K)
+// (row m in lane m, written with tcgen05.st by the epilogue threads).
+__device__ __forceinline__ void issue_gemm_ts(uint32_t tmem_d, uint32_t ta_hi, uint32_t ta_lo, uint32_t b_hi,
+                                              uint32_t b_lo, int N, int K, bool accumulate, int passes) {
+  const uint32_t idesc = make_idesc_tf32(TILE_M, N, 0);
+  for (int pass = 0; pass < passes; ++pass) {
+    uint32_t a = (pass == 1) ? ta_lo : ta_hi;
+    uint32_t b = (pass == 2) ? b_lo : b_hi;
+    for (int kk = 0; kk < K / 8; ++kk) {
+      uint64_t db = make_desc(b + (kk >> 2) * (N * 128) + (kk & 3) * 32, 16, 1024);
+      mma_tf32_ts(tmem_d, a + 8 * kk, db, idesc, (accumulate || pass > 0 || kk > 0) ? 1u : 0u);
+    }
+  }
+}
+
 // --------------------------------------------------------------------------------------------------------
 // weight image packing: W (rows x cols) row-major -> hi / lo SWIZZLE_128B images
 __global__ void tc_pack_kernel(const float* __restrict__ W, int rows, int cols, float* __restrict__ img_hi,
@@ -76,7 +91,7 @@ __global__ void tc_pack_kernel(const float* __restrict__ W, int rows, int cols, 
 //   out[128 x rows] = A[128 x cols] · W^T   (W given as its packed K-major image, rows x cols)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ img_hi, const float* __restrict__ img_lo,
-                   int rows, int cols, int passes, float* __restrict__ out) {
+                   int rows, int cols, int passes, int a_tmem, float* __restrict__ out) {
   extern __shared__ __align__(1024) char smem_raw[];
   char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   char* b_hi = smem;
@@ -101,7 +116,7 @@ tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ img_hi
     *reinterpret_cast<float4*>(x_hi + off) = hi;
     *reinterpret_cast<float4*>(x_lo + off) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
   }
-  if (warp == 0) tmem_alloc<128>(&tmem_slot);
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
   if (tid == 0) {
     mbar_init(&bar, 1);
     mbar_fence_init();
@@ -111,14 +126,35 @@ tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ img_hi
   __syncthreads();
   fence_after_sync();
   uint32_t tmem = tmem_slot;
+  int q = warp & 3, hsel = warp >> 2;
+  int r = 32 * q + lane;
+  if (a_tmem) {
+    // A (hi | lo) into tensor memory columns [128, 128+K) | [256, 256+K): row r in lane r
+    for (int k0 = 32 * hsel; k0 < K; k0 += 64) {
+      float hi[32], lo[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        float v = A[r * K + k0 + c];
+        hi[c] = tf32_hi(v);
+        lo[c] = v - hi[c];
+      }
+      tmem_st32(tmem + ((uint32_t)(32 * q) << 16) + 128 + k0, hi);
+      tmem_st32(tmem + ((uint32_t)(32 * q) << 16) + 256 + k0, lo);
+    }
+    tmem_st_wait();
+    fence_before_sync();
+    __syncthreads();
+  }
   if (tid == 0) {
-    issue_gemm(tmem, smem_u32(x_hi), smem_u32(x_lo), smem_u32(b_hi), smem_u32(b_lo), N, K, false, passes);
+    fence_after_sync();
+    if (a_tmem)
+      issue_gemm_ts(tmem, tmem + 128, tmem + 256, smem_u32(b_hi), smem_u32(b_lo), N, K, false, passes);
+    else
+      issue_gemm(tmem, smem_u32(x_hi), smem_u32(x_lo), smem_u32(b_hi), smem_u32(b_lo), N, K, false, passes);
     commit(&bar);
   }
   mbar_wait(&bar, 0);
   fence_after_sync();
-  int q = warp & 3, hsel = warp >> 2;
-  int r = 32 * q + lane;
   for (int c0 = 32 * hsel; c0 < N; c0 += 64) {
     float v[32];
     tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + c0, v);
@@ -128,7 +164,7 @@ tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ img_hi
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<128>(tmem);
+  if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -309,6 +345,719 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(ConvTcParams
     __syncthreads();  // TMEM and X are free for the next tile
   }
   if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+// --------------------------------------------------------------------------------------------------------
+// Forward, two-group pipeline: 512 threads = 2 groups x 8 warps.  Each group owns a tile of 128 edges and half
+// of TMEM (256 columns); the operand buffer X and the tensor core are shared and handed back and forth in
+// strict alternation  A1 B1 A2 B2 A3 B3 A1' ...  (A1 = group A's GEMM1 window, A2 = GEMM2d, A3 = GEMM2g).
+// While one group's MMAs run, the other group does its epilogue math (TMEM loads, P gathers, SiLU, stores), so
+// global-load latency and ALU work overlap with tensor work.  Hand-off uses one mbarrier per group that
+// receives that group's tcgen05.commit arrivals: a group may write X when the other group's previous window has
+// completed; it reads its own accumulators when its own commit has completed.
+constexpr int TC2_THREADS = 512;
+constexpr int GRP_THREADS = 256;
+
+__global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_fwd_kernel(ConvTcParams p) {
+  extern __shared__ __align__(1024) char smem_raw[];
+  char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  char* w1_hi = smem;
+  char* w1_lo = w1_hi + IMG_W1 * 4;
+  char* w2d_hi = w1_lo + IMG_W1 * 4;
+  char* w2d_lo = w2d_hi + IMG_W2 * 4;
+  char* w2g_hi = w2d_lo + IMG_W2 * 4;
+  char* w2g_lo = w2g_hi + IMG_W2 * 4;
+  char* x_hi = smem + SMEM_W_BYTES;
+  char* x_lo = x_hi + TILE_M * TC_F * 4;
+  float* b2d_s = reinterpret_cast<float*>(smem + SMEM_W_BYTES + SMEM_X_BYTES);
+  float* b2g_s = b2d_s + 64;
+  float* wh_s = b2g_s + 64;
+  __shared__ uint64_t bars[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = warp >> 3, wg = warp & 7;
+  const int q = wg & 3, hsel = wg >> 2;
+  const int gtid = tid & (GRP_THREADS - 1);
+  const int row = 32 * q + lane;
+  const int c0 = 32 * hsel;
+
+  for (int i = tid; i < WIMG_FLOATS / 4; i += TC2_THREADS)
+    reinterpret_cast<float4*>(smem)[i] = reinterpret_cast<const float4*>(p.wimg)[i];
+  if (tid < 64) { b2d_s[tid] = p.b2d[tid]; b2g_s[tid] = p.b2g[tid]; }
+  for (int i = tid; i < p.R * 64; i += TC2_THREADS) wh_s[i] = p.WhT[i];
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot + grp * 256;
+  const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+  const uint32_t D1 = 0, D2D = 128, D2G = 192;
+  uint64_t* own = &bars[grp];
+  uint64_t* other = &bars[grp ^ 1];
+  uint32_t own_phase = 0, other_phase = 0;
+  bool skip_wait = (grp == 0);  // the very first window of group 0 has no predecessor
+  const uint32_t xh = smem_u32(x_hi), xl = smem_u32(x_lo);
+  const int bar_id = 1 + grp;
+
+  const int64_t n_tiles = (p.E + TILE_M - 1) / TILE_M;
+  const int64_t per_iter = 2 * (int64_t)gridDim.x;
+  const int64_t n_iter = (n_tiles + per_iter - 1) / per_iter;
+  for (int64_t it = 0; it < n_iter; ++it) {
+    const int64_t tile = (it * gridDim.x + blockIdx.x) * 2 + grp;
+    const bool has_tile = tile < n_tiles;
+    const int64_t e0 = tile * TILE_M;
+    if (!has_tile) {
+      // keep the hand-off protocol going: three empty windows
+      for (int w = 0; w < 3; ++w) {
+        if (skip_wait) skip_wait = false; else { mbar_wait(other, other_phase); other_phase ^= 1; }
+        named_bar_sync(bar_id, GRP_THREADS);
+        if (gtid == 0) commit(own);
+        mbar_wait(own, own_phase); own_phase ^= 1;
+      }
+      continue;
+    }
+    // ---- prefetch the e rows of this tile into registers (coalesced) ----
+    float4 ev[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int idx = gtid + GRP_THREADS * i;
+      int64_t eg_ = min(e0 + (idx >> 4), p.E - 1);
+      ev[i] = __ldg(reinterpret_cast<const float4*>(p.e + eg_ * TC_F) + (idx & 15));
+    }
+    const int64_t eg = min(e0 + row, p.E - 1);
+    const bool live = (e0 + row) < p.E;
+    const float* Pi = p.P + (int64_t)p.src[eg] * p.ldp + p.po;
+    const float* Pj = p.P + (int64_t)p.dst[eg] * p.ldp + p.po + 128;
+    // ---- window 1: X <- e ; GEMM1 ----
+    if (skip_wait) skip_wait = false; else { mbar_wait(other, other_phase); other_phase ^= 1; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int idx = gtid + GRP_THREADS * i;
+      store_split4(x_hi, x_lo, idx >> 4, 4 * (idx & 15), ev[i]);
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    named_bar_sync(bar_id, GRP_THREADS);
+    if (gtid == 0) {
+      fence_after_sync();
+      issue_gemm(tmem + D1, xh, xl, smem_u32(w1_hi), smem_u32(w1_lo), 128, 64, false, p.passes);
+      commit(own);
+    }
+    // ---- a1 dense -> registers (needs own GEMM1) ----
+    float act[32];
+    mbar_wait(own, own_phase); own_phase ^= 1;
+    fence_after_sync();
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      float v[16];
+      tmem_ld16(t_lane + D1 + c0 + 16 * h2, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 16; c += 4) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(Pi + c0 + 16 * h2 + c));
+        float4 b = __ldg(reinterpret_cast<const float4*>(Pj + c0 + 16 * h2 + c));
+        act[16 * h2 + c] = silu_fast(v[c] + a.x + b.x);
+        act[16 * h2 + c + 1] = silu_fast(v[c + 1] + a.y + b.y);
+        act[16 * h2 + c + 2] = silu_fast(v[c + 2] + a.z + b.z);
+        act[16 * h2 + c + 3] = silu_fast(v[c + 3] + a.w + b.w);
+      }
+    }
+    // ---- window 2: X <- a1 dense ; GEMM2d ----
+    mbar_wait(other, other_phase); other_phase ^= 1;
+#pragma unroll
+    for (int c = 0; c < 32; c += 4)
+      store_split4(x_hi, x_lo, row, c0 + c, make_float4(act[c], act[c + 1], act[c + 2], act[c + 3]));
+    fence_proxy_async();
+    fence_before_sync();
+    named_bar_sync(bar_id, GRP_THREADS);
+    if (gtid == 0) {
+      fence_after_sync();
+      issue_gemm(tmem + D2D, xh, xl, smem_u32(w2d_hi), smem_u32(w2d_lo), 64, 64, false, p.passes);
+      commit(own);
+    }
+    // ---- a1 gate -> registers (D1 gate half is already complete) ----
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      float v[16];
+      tmem_ld16(t_lane + D1 + 64 + c0 + 16 * h2, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 16; c += 4) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(Pi + 64 + c0 + 16 * h2 + c));
+        float4 b = __ldg(reinterpret_cast<const float4*>(Pj + 64 + c0 + 16 * h2 + c));
+        act[16 * h2 + c] = silu_fast(v[c] + a.x + b.x);
+        act[16 * h2 + c + 1] = silu_fast(v[c + 1] + a.y + b.y);
+        act[16 * h2 + c + 2] = silu_fast(v[c + 2] + a.z + b.z);
+        act[16 * h2 + c + 3] = silu_fast(v[c + 3] + a.w + b.w);
+      }
+    }
+    // ---- window 3: X <- a1 gate ; GEMM2g ----
+    mbar_wait(other, other_phase); other_phase ^= 1;
+    // own GEMM2d precedes the other group's window 2 in the tensor queue, so it has completed too; consume its
+    // phase HERE (before the next commit) — a parity wait that falls two phases behind would never return
+    mbar_wait(own, own_phase); own_phase ^= 1;
+#pragma unroll
+    for (int c = 0; c < 32; c += 4)
+      store_split4(x_hi, x_lo, row, c0 + c, make_float4(act[c], act[c + 1], act[c + 2], act[c + 3]));
+    fence_proxy_async();
+    fence_before_sync();
+    named_bar_sync(bar_id, GRP_THREADS);
+    if (gtid == 0) {
+      fence_after_sync();
+      issue_gemm(tmem + D2G, xh, xl, smem_u32(w2g_hi), smem_u32(w2g_lo), 64, 64, false, p.passes);
+      commit(own);
+    }
+    // ---- output stage ----
+    float hm[M3G_MAX_RADIAL];
+#pragma unroll
+    for (int m = 0; m < M3G_MAX_RADIAL; ++m) hm[m] = (m < p.R) ? p.h[eg * p.R + m] : 0.0f;
+    fence_after_sync();  // GEMM2d: phase consumed in window 3
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      float v[16];
+      tmem_ld16(t_lane + D2D + c0 + 16 * h2, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 16; ++c) act[16 * h2 + c] = silu_fast(v[c] + b2d_s[c0 + 16 * h2 + c]);
+    }
+    mbar_wait(own, own_phase); own_phase ^= 1;  // GEMM2g
+    fence_after_sync();
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      float v[16];
+      tmem_ld16(t_lane + D2G + c0 + 16 * h2, v);
+      tmem_ld_wait();
+      if (live) {
+#pragma unroll
+        for (int c = 0; c < 16; c += 4) {
+          float o[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            int col = c0 + 16 * h2 + c + u;
+            float sacc = 0.0f;
+#pragma unroll
+            for (int m = 0; m < M3G_MAX_RADIAL; ++m)
+              if (m < p.R) sacc += hm[m] * wh_s[m * 64 + col];
+            o[u] = act[16 * h2 + c + u] * sigmoid_fast(v[c + u] + b2g_s[col]) * sacc;
+          }
+          float4 res = make_float4(o[0], o[1], o[2], o[3]);
+          if (p.mode == 0) {
+            float4 e4 = __ldg(reinterpret_cast<const float4*>(p.e + eg * TC_F + c0 + 16 * h2 + c));
+            res.x += e4.x; res.y += e4.y; res.z += e4.z; res.w += e4.w;
+          }
+          *reinterpret_cast<float4*>(p.y + eg * TC_F + c0 + 16 * h2 + c) = res;
+        }
+      }
+    }
+    fence_before_sync();
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem_slot);
+}
+
+// --------------------------------------------------------------------------------------------------------
+// Forward, two-group pipeline with COALESCED global traffic (variant 3).
+// The accumulator layout is row-per-lane (tcgen05.ld 32x32b), so a naive epilogue gathers P[dst] and writes y
+// with 32 different cache lines per warp instruction (ncu: the L1 wavefront queue, not the tensor pipe, paced
+// variants 1 and 2).  Here every gather/scatter goes through a private 2 KB per-warp staging buffer:
+//   P[dst] rows:  coalesced LDG.128 (8 rows x 64 B per instruction, dst indices broadcast by shuffle)
+//                 -> staging (XOR-swizzled 16 B slots, conflict-free both ways) -> row-per-lane LDS.128
+//   y rows:       row-per-lane -> staging -> coalesced STG.128 (+ the residual e rows, read coalesced)
+// P[src] stays a direct row-per-lane load: edges are grouped by source atom, so the 32 rows of a warp share one or
+// two source atoms and the load is (nearly) a broadcast.
+constexpr int STG_WARP_BYTES = 32 * 16 * 4;  // 32 rows x 16 floats
+constexpr int TC3_MAX_R = 4;
+constexpr int SMEM_MISC3_BYTES = (64 + 64 + TC3_MAX_R * 64) * 4 + 32;  // biases, Wh^T, 2 mbarriers + TMEM slot
+constexpr int SMEM_FWD3_BYTES = SMEM_W_BYTES + SMEM_X_BYTES + SMEM_MISC3_BYTES + 16 * STG_WARP_BYTES + 1024;
+static_assert(SMEM_FWD3_BYTES <= 232448, "variant-3 forward exceeds the 227 KB shared-memory limit");
+
+// 16-byte slot of (row r, 4-column group c4) in a 32 x 16 float staging tile
+__device__ __forceinline__ uint32_t stg_off(int r, int c4) { return (uint32_t)((r * 4 + (c4 ^ ((r >> 1) & 3))) << 4); }
+
+__global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc3_fwd_kernel(ConvTcParams p) {
+  extern __shared__ __align__(1024) char smem_raw[];
+  char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  char* w1_hi = smem;
+  char* w1_lo = w1_hi + IMG_W1 * 4;
+  char* w2d_hi = w1_lo + IMG_W1 * 4;
+  char* w2d_lo = w2d_hi + IMG_W2 * 4;
+  char* w2g_hi = w2d_lo + IMG_W2 * 4;
+  char* w2g_lo = w2g_hi + IMG_W2 * 4;
+  char* x_hi = smem + SMEM_W_BYTES;
+  char* x_lo = x_hi + TILE_M * TC_F * 4;
+  float* b2d_s = reinterpret_cast<float*>(smem + SMEM_W_BYTES + SMEM_X_BYTES);
+  float* b2g_s = b2d_s + 64;
+  float* wh_s = b2g_s + 64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wh_s + TC3_MAX_R * 64);
+  uint32_t* tmem_slot_p = reinterpret_cast<uint32_t*>(bars + 2);
+  char* stg_base = smem + SMEM_W_BYTES + SMEM_X_BYTES + SMEM_MISC3_BYTES;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = warp >> 3, wg = warp & 7;
+  const int q = wg & 3, hsel = wg >> 2;
+  const int gtid = tid & (GRP_THREADS - 1);
+  const int row = 32 * q + lane;
+  const int c0 = 32 * hsel;
+  char* stg = stg_base + warp * STG_WARP_BYTES;
+  const int cr = lane >> 2, cc4 = lane & 3;  // coalesced layout: row 8*i + cr, 4-column group cc4
+
+  for (int i = tid; i < WIMG_FLOATS / 4; i += TC2_THREADS)
+    reinterpret_cast<float4*>(smem)[i] = reinterpret_cast<const float4*>(p.wimg)[i];
+  if (tid < 64) { b2d_s[tid] = p.b2d[tid]; b2g_s[tid] = p.b2g[tid]; }
+  for (int i = tid; i < TC3_MAX_R * 64; i += TC2_THREADS) wh_s[i] = (i < p.R * 64) ? p.WhT[i] : 0.0f;
+  if (warp == 0) tmem_alloc<512>(tmem_slot_p);
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot_p;
+  const uint32_t tmem = tmem_base + grp * 256;
+  const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+  const uint32_t D1 = 0, D2D = 128, D2G = 192;
+  uint64_t* own = &bars[grp];
+  uint64_t* other = &bars[grp ^ 1];
+  uint32_t own_phase = 0, other_phase = 0;
+  bool skip_wait = (grp == 0);  // the very first window of group 0 has no predecessor
+  const uint32_t xh = smem_u32(x_hi), xl = smem_u32(x_lo);
+  const int bar_id = 1 + grp;
+
+  const int64_t n_tiles = (p.E + TILE_M - 1) / TILE_M;
+  const int64_t per_iter = 2 * (int64_t)gridDim.x;
+  const int64_t n_iter = (n_tiles + per_iter - 1) / per_iter;
+  for (int64_t it = 0; it < n_iter; ++it) {
+    const int64_t tile = (it * gridDim.x + blockIdx.x) * 2 + grp;
+    const bool has_tile = tile < n_tiles;
+    const int64_t e0 = tile * TILE_M;
+    if (!has_tile) {
+      // keep the hand-off protocol going: three empty windows
+      for (int w = 0; w < 3; ++w) {
+        if (skip_wait) skip_wait = false; else { mbar_wait(other, other_phase); other_phase ^= 1; }
+        named_bar_sync(bar_id, GRP_THREADS);
+        if (gtid == 0) commit(own);
+        mbar_wait(own, own_phase); own_phase ^= 1;
+      }
+      continue;
+    }
+    // ---- prefetch the e rows of this tile into registers (coalesced: 2 rows x 256 B per warp instruction) ----
+    float4 ev[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int idx = gtid + GRP_THREADS * i;
+      int64_t eg_ = min(e0 + (idx >> 4), p.E - 1);
+      ev[i] = __ldg(reinterpret_cast<const float4*>(p.e + eg_ * TC_F) + (idx & 15));
+    }
+    const int64_t eg = min(e0 + row, p.E - 1);
+    const int d_row = __ldg(p.dst + eg);
+    const float* Pi = p.P + (int64_t)__ldg(p.src + eg) * p.ldp + p.po;
+    // P[dst] row pointers of the four rows this lane serves in the coalesced layout
+    const float* Pj[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      Pj[i] = p.P + (int64_t)__shfl_sync(FULL, d_row, 8 * i + cr) * p.ldp + p.po + 128 + 4 * cc4;
+    float4 pj[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pj[i] = __ldg(reinterpret_cast<const float4*>(Pj[i] + c0));
+    // ---- window 1: X <- e ; GEMM1 ----
+    if (skip_wait) skip_wait = false; else { mbar_wait(other, other_phase); other_phase ^= 1; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int idx = gtid + GRP_THREADS * i;
+      store_split4(x_hi, x_lo, idx >> 4, 4 * (idx & 15), ev[i]);
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    named_bar_sync(bar_id, GRP_THREADS);
+    if (gtid == 0) {
+      fence_after_sync();
+      issue_gemm(tmem + D1, xh, xl, smem_u32(w1_hi), smem_u32(w1_lo), 128, 64, false, p.passes);
+      commit(own);
+    }
+    float act[32];
+    // ---- layer-1 activations: four 16-column sub-chunks (dense c0, c0+16 ; gate c0, c0+16) ----
+#pragma unroll
+    for (int sc = 0; sc < 4; ++sc) {
+      const int col = ((sc >> 1) << 6) + c0 + ((sc & 1) << 4);  // column inside the 128-wide z1 row
+      // staging <- P[dst] sub-chunk (coalesced layout), then prefetch the next one
+#pragma unroll
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(stg + stg_off(8 * i + cr, cc4)) = pj[i];
+      if (sc < 3) {
+        const int ncol = (((sc + 1) >> 1) << 6) + c0 + (((sc + 1) & 1) << 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pj[i] = __ldg(reinterpret_cast<const float4*>(Pj[i] + ncol));
+      }
+      float4 pi4[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) pi4[c] = __ldg(reinterpret_cast<const float4*>(Pi + col + 4 * c));
+      __syncwarp();
+      if (sc == 0) {  // own GEMM1
+        mbar_wait(own, own_phase); own_phase ^= 1;
+        fence_after_sync();
+      }
+      float v[16];
+      tmem_ld16(t_lane + D1 + col, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float4 b = *reinterpret_cast<const float4*>(stg + stg_off(lane, c));
+        act[16 * (sc & 1) + 4 * c] = silu_fast(v[4 * c] + pi4[c].x + b.x);
+        act[16 * (sc & 1) + 4 * c + 1] = silu_fast(v[4 * c + 1] + pi4[c].y + b.y);
+        act[16 * (sc & 1) + 4 * c + 2] = silu_fast(v[4 * c + 2] + pi4[c].z + b.z);
+        act[16 * (sc & 1) + 4 * c + 3] = silu_fast(v[4 * c + 3] + pi4[c].w + b.w);
+      }
+      __syncwarp();
+      if (sc & 1) {
+        // ---- window 2 (dense) / window 3 (gate): X <- a1 ; GEMM2 ----
+        mbar_wait(other, other_phase); other_phase ^= 1;
+        if (sc == 3) {
+          // own GEMM2d precedes the other group's window 2 in the tensor queue: complete; consume its phase HERE
+          // (a parity wait that falls two phases behind never returns)
+          mbar_wait(own, own_phase); own_phase ^= 1;
+        }
+#pragma unroll
+        for (int c = 0; c < 32; c += 4)
+          store_split4(x_hi, x_lo, row, c0 + c, make_float4(act[c], act[c + 1], act[c + 2], act[c + 3]));
+        fence_proxy_async();
+        fence_before_sync();
+        named_bar_sync(bar_id, GRP_THREADS);
+        if (gtid == 0) {
+          fence_after_sync();
+          if (sc == 1)
+            issue_gemm(tmem + D2D, xh, xl, smem_u32(w2d_hi), smem_u32(w2d_lo), 64, 64, false, p.passes);
+          else
+            issue_gemm(tmem + D2G, xh, xl, smem_u32(w2g_hi), smem_u32(w2g_lo), 64, 64, false, p.passes);
+          commit(own);
+        }
+      }
+    }
+    // ---- output stage ----
+    float hm[TC3_MAX_R];
+#pragma unroll
+    for (int m = 0; m < TC3_MAX_R; ++m) hm[m] = (m < p.R) ? __ldg(p.h + eg * p.R + m) : 0.0f;
+    fence_after_sync();  // GEMM2d: phase consumed in window 3
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      float v[16];
+      tmem_ld16(t_lane + D2D + c0 + 16 * h2, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 16; c += 4) {
+        float4 b = *reinterpret_cast<const float4*>(b2d_s + c0 + 16 * h2 + c);
+        act[16 * h2 + c] = silu_fast(v[c] + b.x);
+        act[16 * h2 + c + 1] = silu_fast(v[c + 1] + b.y);
+        act[16 * h2 + c + 2] = silu_fast(v[c + 2] + b.z);
+        act[16 * h2 + c + 3] = silu_fast(v[c + 3] + b.w);
+      }
+    }
+    mbar_wait(own, own_phase); own_phase ^= 1;  // GEMM2g
+    fence_after_sync();
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int col = c0 + 16 * h2;
+      // residual rows (mode 0), coalesced layout; issued before the TMEM read so that they overlap it
+      float4 er[4];
+      if (p.mode == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int64_t er_ = min(e0 + 32 * q + 8 * i + cr, p.E - 1);
+          er[i] = __ldg(reinterpret_cast<const float4*>(p.e + er_ * TC_F + col + 4 * cc4));
+        }
+      }
+      float v[16];
+      tmem_ld16(t_lane + D2G + col, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 16; c += 4) {
+        float4 bg = *reinterpret_cast<const float4*>(b2g_s + col + c);
+        float bgv[4] = {bg.x, bg.y, bg.z, bg.w};
+        float o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) o[u] = 0.0f;
+#pragma unroll
+        for (int m = 0; m < TC3_MAX_R; ++m) {
+          float4 w4 = *reinterpret_cast<const float4*>(wh_s + m * 64 + col + c);
+          o[0] += hm[m] * w4.x; o[1] += hm[m] * w4.y; o[2] += hm[m] * w4.z; o[3] += hm[m] * w4.w;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) o[u] *= act[16 * h2 + c + u] * sigmoid_fast(v[c + u] + bgv[u]);
+        *reinterpret_cast<float4*>(stg + stg_off(lane, c >> 2)) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 r4 = *reinterpret_cast<const float4*>(stg + stg_off(8 * i + cr, cc4));
+        if (p.mode == 0) { r4.x += er[i].x; r4.y += er[i].y; r4.z += er[i].z; r4.w += er[i].w; }
+        int64_t er_ = e0 + 32 * q + 8 * i + cr;
+        if (er_ < p.E) *reinterpret_cast<float4*>(p.y + er_ * TC_F + col + 4 * cc4) = r4;
+      }
+      __syncwarp();
+    }
+    fence_before_sync();
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+// --------------------------------------------------------------------------------------------------------
+// Forward, variant 4 = variant 3 + layer-2 A operands in TENSOR MEMORY.
+// ncu on variant 3: the shared-memory data pipe is ~95 % busy (LSU wavefronts 69 % + tensor-core operand fetch
+// 26 %), so the layer-1 activations no longer round-trip through shared memory: the epilogue threads write their
+// hi / lo split with tcgen05.st into TMEM columns they own (the consumed D1 columns, and the idle D2g columns) and
+// GEMM2d / GEMM2g read A from TMEM ([a_tmem] operand form).  Only the e tile still uses the shared operand buffer X,
+// so the two groups hand X over once per tile (mbarrier of the other group's GEMM1) and each GEMM has its own
+// mbarrier (one completion per tile -> parity = tile counter, no multi-phase bookkeeping).
+// TMEM columns per group: [0,128) D1, then A_hi at [0,64); A_lo at [192,256) for the dense branch and [64,128) for
+// the gate branch; [128,192) D2d; [192,256) D2g.  Every thread only ever overwrites columns it has already read.
+constexpr int SMEM_MISC4_BYTES = (64 + 64 + TC3_MAX_R * 64) * 4 + 64;  // biases, Wh^T, 6 mbarriers + TMEM slot
+constexpr int SMEM_FWD4_BYTES = SMEM_W_BYTES + SMEM_X_BYTES + SMEM_MISC4_BYTES + 16 * STG_WARP_BYTES + 1024;
+static_assert(SMEM_FWD4_BYTES <= 232448, "variant-4 forward exceeds the 227 KB shared-memory limit");
+
+__device__ __forceinline__ void store_split4_s(uint32_t x_hi, uint32_t x_lo, int r, int k, float4 v) {
+  uint32_t off = sw128_offset(r, k, TILE_M);
+  float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+  sts128(x_hi + off, hi);
+  sts128(x_lo + off, make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w));
+}
+
+// hi / lo split of 32 activations into two 32-column TMEM slices of this thread's lane
+__device__ __forceinline__ void tmem_put_split32(uint32_t t_hi, uint32_t t_lo, const float* a) {
+#pragma unroll
+  for (int h2 = 0; h2 < 2; ++h2) {
+    float t[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) t[c] = tf32_hi(a[16 * h2 + c]);
+    tmem_st16(t_hi + 16 * h2, t);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) t[c] = a[16 * h2 + c] - t[c];
+    tmem_st16(t_lo + 16 * h2, t);
+  }
+  tmem_st_wait();
+}
+
+__global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc4_fwd_kernel(ConvTcParams p) {
+  extern __shared__ __align__(1024) char smem_raw[];
+  char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t w1_hi = sbase, w1_lo = w1_hi + IMG_W1 * 4;
+  const uint32_t w2d_hi = w1_lo + IMG_W1 * 4, w2d_lo = w2d_hi + IMG_W2 * 4;
+  const uint32_t w2g_hi = w2d_lo + IMG_W2 * 4, w2g_lo = w2g_hi + IMG_W2 * 4;
+  const uint32_t xh = sbase + SMEM_W_BYTES, xl = xh + TILE_M * TC_F * 4;
+  float* misc = reinterpret_cast<float*>(smem + SMEM_W_BYTES + SMEM_X_BYTES);
+  const uint32_t b2d_a = sbase + SMEM_W_BYTES + SMEM_X_BYTES, b2g_a = b2d_a + 256, wh_a = b2g_a + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc + 128 + TC3_MAX_R * 64);  // [g1 A,B | g2d A,B | g2g A,B]
+  uint32_t* tmem_slot_p = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = warp >> 3, wg = warp & 7;
+  const int q = wg & 3, hsel = wg >> 2;
+  const int gtid = tid & (GRP_THREADS - 1);
+  const int row = 32 * q + lane;
+  const int c0 = 32 * hsel;
+  const uint32_t stg = sbase + SMEM_W_BYTES + SMEM_X_BYTES + SMEM_MISC4_BYTES + warp * STG_WARP_BYTES;
+  const int cr = lane >> 2, cc4 = lane & 3;  // coalesced layout: row 8*i + cr, 4-column group cc4
+
+  for (int i = tid; i < WIMG_FLOATS / 4; i += TC2_THREADS)
+    reinterpret_cast<float4*>(smem)[i] = reinterpret_cast<const float4*>(p.wimg)[i];
+  if (tid < 64) { misc[tid] = p.b2d[tid]; misc[64 + tid] = p.b2g[tid]; }
+  for (int i = tid; i < TC3_MAX_R * 64; i += TC2_THREADS) misc[128 + i] = (i < p.R * 64) ? p.WhT[i] : 0.0f;
+  if (warp == 0) tmem_alloc<512>(tmem_slot_p);
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot_p;
+  const uint32_t tmem = tmem_base + grp * 256;
+  const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+  const uint32_t D1 = 0, D2D = 128, D2G = 192;
+  uint64_t* g1_own = &bars[grp];
+  uint64_t* g1_other = &bars[grp ^ 1];
+  uint64_t* g2d_own = &bars[2 + grp];
+  uint64_t* g2g_own = &bars[4 + grp];
+  const int bar_id = 1 + grp;
+
+  const int64_t n_tiles = (p.E + TILE_M - 1) / TILE_M;
+  const int64_t per_iter = 2 * (int64_t)gridDim.x;
+  const int64_t n_iter = (n_tiles + per_iter - 1) / per_iter;
+  for (int64_t it = 0; it < n_iter; ++it) {
+    const int64_t tile = (it * gridDim.x + blockIdx.x) * 2 + grp;
+    if (tile >= n_tiles) break;  // tiles are dealt A,B,A,B,...: the other group never waits on a tile that is absent
+    const uint32_t par = (uint32_t)(it & 1);
+    const int64_t e0 = tile * TILE_M;
+    // ---- prefetch the e rows of this tile into registers (coalesced: 2 rows x 256 B per warp instruction) ----
+    float4 ev[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int idx = gtid + GRP_THREADS * i;
+      int64_t eg_ = min(e0 + (idx >> 4), p.E - 1);
+      ev[i] = __ldg(reinterpret_cast<const float4*>(p.e + eg_ * TC_F) + (idx & 15));
+    }
+    const int64_t eg = min(e0 + row, p.E - 1);
+    const int d_row = __ldg(p.dst + eg);
+    const float* Pi = p.P + (int64_t)__ldg(p.src + eg) * p.ldp + p.po;
+    // P[dst] row pointers of the four rows this lane serves in the coalesced layout
+    const float* Pj[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      Pj[i] = p.P + (int64_t)__shfl_sync(FULL, d_row, 8 * i + cr) * p.ldp + p.po + 128 + 4 * cc4;
+    float4 pj[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pj[i] = __ldg(reinterpret_cast<const float4*>(Pj[i] + c0));
+    // ---- X hand-off: the other group's latest GEMM1 must have consumed X ----
+    if (grp == 1) mbar_wait_warp(g1_other, par);
+    else if (it > 0) mbar_wait_warp(g1_other, par ^ 1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int idx = gtid + GRP_THREADS * i;
+      store_split4_s(xh, xl, idx >> 4, 4 * (idx & 15), ev[i]);
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    named_bar_sync(bar_id, GRP_THREADS);
+    if (gtid == 0) {
+      fence_after_sync();
+      issue_gemm(tmem + D1, xh, xl, w1_hi, w1_lo, 128, 64, false, p.passes);
+      commit(g1_own);
+    }
+    float act[32];
+    // ---- layer-1 activations: four 16-column sub-chunks (dense c0, c0+16 ; gate c0, c0+16) ----
+#pragma unroll
+    for (int sc = 0; sc < 4; ++sc) {
+      const int col = ((sc >> 1) << 6) + c0 + ((sc & 1) << 4);  // column inside the 128-wide z1 row
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sts128(stg + stg_off(8 * i + cr, cc4), pj[i]);
+      if (sc < 3) {
+        const int ncol = (((sc + 1) >> 1) << 6) + c0 + (((sc + 1) & 1) << 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pj[i] = __ldg(reinterpret_cast<const float4*>(Pj[i] + ncol));
+      }
+      float4 pi4[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) pi4[c] = __ldg(reinterpret_cast<const float4*>(Pi + col + 4 * c));
+      __syncwarp();
+      if (sc == 0) {  // own GEMM1
+        mbar_wait_warp(g1_own, par);
+        fence_after_sync();
+      }
+      float v[16];
+      tmem_ld16(t_lane + D1 + col, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float4 b = lds128(stg + stg_off(lane, c));
+        act[16 * (sc & 1) + 4 * c] = silu_fast(v[4 * c] + pi4[c].x + b.x);
+        act[16 * (sc & 1) + 4 * c + 1] = silu_fast(v[4 * c + 1] + pi4[c].y + b.y);
+        act[16 * (sc & 1) + 4 * c + 2] = silu_fast(v[4 * c + 2] + pi4[c].z + b.z);
+        act[16 * (sc & 1) + 4 * c + 3] = silu_fast(v[4 * c + 3] + pi4[c].w + b.w);
+      }
+      __syncwarp();
+      if (sc == 1) {
+        // dense branch: A_hi -> own D1 dense columns, A_lo -> own (idle) D2g columns ; GEMM2d
+        tmem_put_split32(t_lane + D1 + c0, t_lane + D2G + c0, act);
+        fence_before_sync();
+        named_bar_sync(bar_id, GRP_THREADS);
+        if (gtid == 0) {
+          fence_after_sync();
+          issue_gemm_ts(tmem + D2D, tmem + D1, tmem + D2G, w2d_hi, w2d_lo, 64, 64, false, p.passes);
+          commit(g2d_own);
+        }
+      } else if (sc == 3) {
+        // gate branch: GEMM2d must have consumed A ; A_hi -> D1 dense columns, A_lo -> own D1 gate columns ; GEMM2g
+        mbar_wait_warp(g2d_own, par);
+        fence_after_sync();
+        tmem_put_split32(t_lane + D1 + c0, t_lane + D1 + 64 + c0, act);
+        fence_before_sync();
+        named_bar_sync(bar_id, GRP_THREADS);
+        if (gtid == 0) {
+          fence_after_sync();
+          issue_gemm_ts(tmem + D2G, tmem + D1, tmem + D1 + 64, w2g_hi, w2g_lo, 64, 64, false, p.passes);
+          commit(g2g_own);
+        }
+      }
+    }
+    // ---- output stage ----
+    float hm[TC3_MAX_R];
+#pragma unroll
+    for (int m = 0; m < TC3_MAX_R; ++m) hm[m] = (m < p.R) ? __ldg(p.h + eg * p.R + m) : 0.0f;
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      float v[16];
+      tmem_ld16(t_lane + D2D + c0 + 16 * h2, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 16; c += 4) {
+        float4 b = lds128(b2d_a + 4 * (c0 + 16 * h2 + c));
+        act[16 * h2 + c] = silu_fast(v[c] + b.x);
+        act[16 * h2 + c + 1] = silu_fast(v[c + 1] + b.y);
+        act[16 * h2 + c + 2] = silu_fast(v[c + 2] + b.z);
+        act[16 * h2 + c + 3] = silu_fast(v[c + 3] + b.w);
+      }
+    }
+    mbar_wait_warp(g2g_own, par);
+    fence_after_sync();
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int col = c0 + 16 * h2;
+      // residual rows (mode 0), coalesced layout; issued before the TMEM read so that they overlap it
+      float4 er[4];
+      if (p.mode == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int64_t er_ = min(e0 + 32 * q + 8 * i + cr, p.E - 1);
+          er[i] = __ldg(reinterpret_cast<const float4*>(p.e + er_ * TC_F + col + 4 * cc4));
+        }
+      }
+      float v[16];
+      tmem_ld16(t_lane + D2G + col, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 16; c += 4) {
+        float4 bg = lds128(b2g_a + 4 * (col + c));
+        float bgv[4] = {bg.x, bg.y, bg.z, bg.w};
+        float o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) o[u] = 0.0f;
+#pragma unroll
+        for (int m = 0; m < TC3_MAX_R; ++m) {
+          float4 w4 = lds128(wh_a + 4 * (m * 64 + col + c));
+          o[0] += hm[m] * w4.x; o[1] += hm[m] * w4.y; o[2] += hm[m] * w4.z; o[3] += hm[m] * w4.w;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) o[u] *= act[16 * h2 + c + u] * sigmoid_fast(v[c + u] + bgv[u]);
+        sts128(stg + stg_off(lane, c >> 2), make_float4(o[0], o[1], o[2], o[3]));
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 r4 = lds128(stg + stg_off(8 * i + cr, cc4));
+        if (p.mode == 0) { r4.x += er[i].x; r4.y += er[i].y; r4.z += er[i].z; r4.w += er[i].w; }
+        int64_t er_ = e0 + 32 * q + 8 * i + cr;
+        if (er_ < p.E) *reinterpret_cast<float4*>(p.y + er_ * TC_F + col + 4 * cc4) = r4;
+      }
+      __syncwarp();
+    }
+    fence_before_sync();
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -652,7 +1401,7 @@ int m3g_tc_pack_b(const float* W, int rows, int cols, float* img_hi, float* img_
 }
 
 int m3g_tc_selftest(const float* A, const float* img_hi, const float* img_lo, int rows, int cols, int passes,
-                    float* out, void* stream) {
+                    int a_tmem, float* out, void* stream) {
   M3G_REQUIRE(A && img_hi && img_lo && out, "m3g_tc_selftest: null pointer");
   M3G_REQUIRE((rows == 64 || rows == 128) && (cols == 64 || cols == 128), "m3g_tc_selftest: rows/cols in {64,128}");
   M3G_REQUIRE(passes == 1 || passes == 3, "m3g_tc_selftest: passes must be 1 or 3");
@@ -662,14 +1411,14 @@ int m3g_tc_selftest(const float* A, const float* img_hi, const float* img_lo, in
     set_error("m3g_tc_selftest: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     return M3G_ERR_CUDA;
   }
-  tc_selftest_kernel<<<1, TC_THREADS, smem, as_stream(stream)>>>(A, img_hi, img_lo, rows, cols, passes, out);
+  tc_selftest_kernel<<<1, TC_THREADS, smem, as_stream(stream)>>>(A, img_hi, img_lo, rows, cols, passes, a_tmem, out);
   M3G_LAUNCH_CHECK("m3g_tc_selftest");
   return M3G_OK;
 }
 
 int m3g_conv_tc_fwd(const float* P, int ldp, int po, const int32_t* src, const int32_t* dst, const float* e,
                     const float* h, const float* wimg, const float* b2d, const float* b2g, const float* WhT, int64_t E,
-                    int R, int mode, int passes, int n_sm, float* y, void* stream) {
+                    int R, int mode, int passes, int variant, int n_sm, float* y, void* stream) {
   if (E == 0) return M3G_OK;
   M3G_REQUIRE(P && src && dst && e && h && wimg && b2d && b2g && WhT && y, "m3g_conv_tc_fwd: null pointer");
   M3G_REQUIRE(R >= 1 && R <= M3G_MAX_RADIAL, "m3g_conv_tc_fwd: R=%d unsupported", R);
@@ -683,6 +1432,42 @@ int m3g_conv_tc_fwd(const float* P, int ldp, int po, const int32_t* src, const i
   }
   ConvTcParams p{P, ldp, po, src, dst, e, h, wimg, b2d, b2g, WhT, E, R, mode, passes, y};
   int64_t n_tiles = (E + TILE_M - 1) / TILE_M;
+  if (variant == 4 && R <= TC3_MAX_R) {
+    err = cudaFuncSetAttribute(conv_tc4_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD4_BYTES);
+    if (err != cudaSuccess) {
+      set_error("m3g_conv_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+      return M3G_ERR_CUDA;
+    }
+    int64_t pairs = (n_tiles + 1) / 2;
+    unsigned grid4 = (unsigned)((pairs < n_sm) ? pairs : n_sm);
+    conv_tc4_fwd_kernel<<<grid4, TC2_THREADS, SMEM_FWD4_BYTES, as_stream(stream)>>>(p);
+    M3G_LAUNCH_CHECK("m3g_conv_tc_fwd");
+    return M3G_OK;
+  }
+  if (variant == 3 && R <= TC3_MAX_R) {
+    err = cudaFuncSetAttribute(conv_tc3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD3_BYTES);
+    if (err != cudaSuccess) {
+      set_error("m3g_conv_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+      return M3G_ERR_CUDA;
+    }
+    int64_t pairs = (n_tiles + 1) / 2;
+    unsigned grid3 = (unsigned)((pairs < n_sm) ? pairs : n_sm);
+    conv_tc3_fwd_kernel<<<grid3, TC2_THREADS, SMEM_FWD3_BYTES, as_stream(stream)>>>(p);
+    M3G_LAUNCH_CHECK("m3g_conv_tc_fwd");
+    return M3G_OK;
+  }
+  if (variant == 2) {
+    err = cudaFuncSetAttribute(conv_tc2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD_BYTES);
+    if (err != cudaSuccess) {
+      set_error("m3g_conv_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+      return M3G_ERR_CUDA;
+    }
+    int64_t pairs = (n_tiles + 1) / 2;
+    unsigned grid2 = (unsigned)((pairs < n_sm) ? pairs : n_sm);
+    conv_tc2_fwd_kernel<<<grid2, TC2_THREADS, SMEM_FWD_BYTES, as_stream(stream)>>>(p);
+    M3G_LAUNCH_CHECK("m3g_conv_tc_fwd");
+    return M3G_OK;
+  }
   unsigned grid = (unsigned)((n_tiles < n_sm) ? n_tiles : n_sm);
   conv_tc_fwd_kernel<<<grid, TC_THREADS, SMEM_FWD_BYTES, as_stream(stream)>>>(p);
   M3G_LAUNCH_CHECK("m3g_conv_tc_fwd");

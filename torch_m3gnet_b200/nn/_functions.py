@@ -28,6 +28,12 @@ def tb_path() -> str:
     return interaction.TB_PATH
 
 
+def tc_variant() -> int:
+    from torch_m3gnet_b200.nn import conv
+
+    return conv.TC_VARIANT
+
+
 def conv_path() -> str:
     from torch_m3gnet_b200.nn import conv
 
@@ -208,9 +214,9 @@ class ConvFn(Function):
             passes = 3 if path == "tc3" else 1
             n_sm = sm_count(x.device)
             call("conv_tc_fwd", P, 8 * F, 0, plan.src, plan.dst, e, h, ed["wimg"], ed["b2d"], ed["b2g"], ed["WhT"], E, R,
-                 0, passes, n_sm, e2)
+                 0, passes, tc_variant(), n_sm, e2)
             call("conv_tc_fwd", P, 8 * F, 4 * F, plan.src, plan.dst, e2, h, nd["wimg"], nd["b2d"], nd["b2g"], nd["WhT"],
-                 E, R, 1, passes, n_sm, msg)
+                 E, R, 1, passes, tc_variant(), n_sm, msg)
         else:
             call("conv_mlp_fwd", P, 8 * F, 0, plan.src, plan.dst, e, h, ed["W1eT"], ed["W2dT"], ed["b2d"], ed["W2gT"],
                  ed["b2g"], ed["WhT"], E, F, R, 0, e2)

@@ -14,6 +14,9 @@ from torch_m3gnet_b200.nn.core import GatedMLP
 
 # "tc3": tcgen05 3xTF32 (fp32-faithful, default for F = 64 on CUDA), "tc1": plain TF32, "fma": generic fp32 kernels
 CONV_PATH = os.environ.get("M3G_CONV_PATH", "tc3")
+# 1: one 128-edge tile per CTA at a time; 2: two warp groups ping-pong two tiles; 3: 2 + coalesced gathers through
+# per-warp staging (csrc/conv_tc.cu)
+TC_VARIANT = int(os.environ.get("M3G_TC_VARIANT", "4"))
 
 
 def _tc_images(w1e: torch.Tensor, w2d: torch.Tensor, w2g: torch.Tensor) -> torch.Tensor:
