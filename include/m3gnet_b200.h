@@ -247,7 +247,7 @@ int m3g_conv_tc_fwd(const float* P, int ldp, int po, const int32_t* src, const i
 int m3g_conv_tc_bwd(const float* P, int ldp, int po, const int32_t* src, const int32_t* dst, const float* e,
                     const float* h, const float* wimg, const float* wimgT, const float* b2d, const float* b2g,
                     const float* WhT, const float* g_up, const float* g_e_base, int64_t E, int R, int mode, int passes,
-                    int n_sm, float* g_e, float* g_z1, float* g_h, void* stream);
+                    int variant, int n_sm, float* g_e, float* g_z1, float* g_h, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * AtomWiseReadout (nn/readout.py:39-58) + virial (nn/gradient.py:39-62)

@@ -1386,6 +1386,359 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_bwd_kernel(ConvTcBwdPar
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+// --------------------------------------------------------------------------------------------------------
+// Backward, variant 2.  One persistent CTA per SM, 16 warps (4 threads per edge row, 16-column slices), one
+// 128-edge tile in flight; what changed against conv_tc_bwd_kernel (ncu: L1 wavefront queue + exposed latency):
+//  * EVERY A operand lives in tensor memory: the epilogue threads write hi / lo splits with tcgen05.st into columns
+//    they own, so no activation / adjoint tile round-trips through shared memory and the tensor core only fetches B
+//    from shared memory.  The layer-1 SiLU derivative is stashed in the D1 columns for the later dz1 stage.
+//  * every global gather / scatter (e, P[dst], g_up, g_e, g_z1) is coalesced through a private 2 KB per-warp staging
+//    tile (see the forward kernel); outputs are written at the end of the tile, re-read from the TMEM operand copies.
+//  * the four transposed 64x64 weight image pairs are streamed by cp.async.bulk (TMA 1-D, mbarrier byte counts)
+//    through two 32 KB buffers instead of LDG+STS by all threads; forward images stay resident.
+//  * four MMA sync points per tile (GEMM1 | GEMM2d+2g | GEMM3d+3g | GEMM4a+4b) instead of seven.
+// TMEM columns: [0,128) D1 -> SiLU'(z1) stash -> D4 in [0,64) ; [128,192) D2d, [192,256) D2g -> operand A2 (hi|lo) ;
+//               [256,320) | [320,384) operand A (hi|lo) ; [384,448) D3d, [448,512) D3g (before that: operand A' = a1g).
+constexpr int TCB2_THREADS = 512;
+constexpr int SMEM_B2_MISC = (64 + 64 + TC_BWD_MAX_R * 64) * 4 + 64;  // biases, Wh^T, 6 mbarriers, TMEM slot
+constexpr int SMEM_BWD2_BYTES = SMEM_W_BYTES + 2 * SMEM_S_BYTES + 16 * STG_WARP_BYTES + SMEM_B2_MISC + 1024;
+static_assert(SMEM_BWD2_BYTES <= 232448, "backward variant 2 exceeds the 227 KB shared-memory limit");
+
+__device__ __forceinline__ void tmem_put_split16(uint32_t t_hi, uint32_t t_lo, const float* a) {
+  float t[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) t[c] = tf32_hi(a[c]);
+  tmem_st16(t_hi, t);
+#pragma unroll
+  for (int c = 0; c < 16; ++c) t[c] = a[c] - t[c];
+  tmem_st16(t_lo, t);
+}
+
+__global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwd2_kernel(ConvTcBwdParams p) {
+  extern __shared__ __align__(1024) char smem_raw[];
+  char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t w1_hi = sbase, w1_lo = w1_hi + IMG_W1 * 4;
+  const uint32_t w2d_hi = w1_lo + IMG_W1 * 4, w2d_lo = w2d_hi + IMG_W2 * 4;
+  const uint32_t w2g_hi = w2d_lo + IMG_W2 * 4, w2g_lo = w2g_hi + IMG_W2 * 4;
+  const uint32_t s0 = sbase + SMEM_W_BYTES, s1 = s0 + SMEM_S_BYTES;  // streamed image pairs (hi | lo)
+  const uint32_t stg_all = s1 + SMEM_S_BYTES;
+  char* misc_c = smem + SMEM_W_BYTES + 2 * SMEM_S_BYTES + 16 * STG_WARP_BYTES;
+  float* misc = reinterpret_cast<float*>(misc_c);
+  const uint32_t b2d_a = stg_all + 16 * STG_WARP_BYTES, b2g_a = b2d_a + 256, wh_a = b2g_a + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc + 128 + TC_BWD_MAX_R * 64);  // bar1..bar4, tb0, tb1
+  uint32_t* tmem_slot_p = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, cs = warp >> 2;
+  const int row = 32 * q + lane;
+  const int k0 = 16 * cs;  // this thread's 16-column slice of every 64-column block
+  const uint32_t stg = stg_all + warp * STG_WARP_BYTES;
+  const int cr = lane >> 2, cc4 = lane & 3;  // coalesced layout: row 8*i + cr, 4-column group cc4
+  const int R = p.R;
+  constexpr uint32_t PAIR_BYTES = 2 * IMG_W2 * 4;
+
+  for (int i = tid; i < WIMG_FLOATS / 4; i += TCB2_THREADS)
+    reinterpret_cast<float4*>(smem)[i] = reinterpret_cast<const float4*>(p.wimg)[i];
+  if (tid < 64) { misc[tid] = p.b2d[tid]; misc[64 + tid] = p.b2g[tid]; }
+  for (int i = tid; i < TC_BWD_MAX_R * 64; i += TCB2_THREADS) misc[128 + i] = (i < R * 64) ? p.WhT[i] : 0.0f;
+  if (warp == 0) tmem_alloc<512>(tmem_slot_p);
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot_p;
+  const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+  constexpr uint32_t Z1 = 0, D2D = 128, D2G = 192, AH = 256, AL = 320, D3D = 384, D3G = 448;
+  uint64_t *bar1 = &bars[0], *bar2 = &bars[1], *bar3 = &bars[2], *bar4 = &bars[3], *tb0 = &bars[4], *tb1 = &bars[5];
+
+  const int64_t n_tiles = (p.E + TILE_M - 1) / TILE_M;
+  if (tid == 0 && (int64_t)blockIdx.x < n_tiles) {
+    mbar_arrive_expect_tx(tb0, PAIR_BYTES);
+    bulk_g2s(s0, p.wimgT + 0 * 2 * IMG_W2, PAIR_BYTES, tb0);  // W2d^T
+    mbar_arrive_expect_tx(tb1, PAIR_BYTES);
+    bulk_g2s(s1, p.wimgT + 1 * 2 * IMG_W2, PAIR_BYTES, tb1);  // W2g^T
+  }
+  uint32_t par = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, par ^= 1) {
+    const int64_t e0 = tile * TILE_M;
+    const int64_t eg = min(e0 + row, p.E - 1);
+    const bool live = (e0 + row) < p.E;
+    const int s_atom = __ldg(p.src + eg);
+    const int d_atom = __ldg(p.dst + eg);
+    // rows this lane serves in the coalesced layout
+    int64_t erow[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) erow[i] = e0 + 32 * q + 8 * i + cr;
+    float4 c4v[4];
+    // ---- T1: e slice -> staging -> row-per-lane -> hi|lo -> operand A in TMEM ; GEMM1 ----
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      c4v[i] = __ldg(reinterpret_cast<const float4*>(p.e + min(erow[i], p.E - 1) * TC_F + k0 + 4 * cc4));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sts128(stg + stg_off(8 * i + cr, cc4), c4v[i]);
+    __syncwarp();
+    {
+      float t[16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float4 b = lds128(stg + stg_off(lane, c));
+        t[4 * c] = b.x; t[4 * c + 1] = b.y; t[4 * c + 2] = b.z; t[4 * c + 3] = b.w;
+      }
+      tmem_put_split16(t_lane + AH + k0, t_lane + AL + k0, t);
+    }
+    __syncwarp();
+    tmem_st_wait();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_gemm_ts(tmem + Z1, tmem + AH, tmem + AL, w1_hi, w1_lo, 128, 64, false, p.passes);
+      commit(bar1);
+    }
+    // ---- T2 (overlaps GEMM1): P[src] + P[dst] for the dense and gate slices ----
+    float pz[32];
+    {
+      const float* Pi = p.P + (int64_t)s_atom * p.ldp + p.po;
+      const float* Pj[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        Pj[i] = p.P + (int64_t)__shfl_sync(FULL, d_atom, 8 * i + cr) * p.ldp + p.po + 128 + k0 + 4 * cc4;
+#pragma unroll
+      for (int hb = 0; hb < 2; ++hb) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c4v[i] = __ldg(reinterpret_cast<const float4*>(Pj[i] + 64 * hb));
+        float4 pi4[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) pi4[c] = __ldg(reinterpret_cast<const float4*>(Pi + 64 * hb + k0 + 4 * c));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sts128(stg + stg_off(8 * i + cr, cc4), c4v[i]);
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float4 b = lds128(stg + stg_off(lane, c));
+          pz[16 * hb + 4 * c] = pi4[c].x + b.x;
+          pz[16 * hb + 4 * c + 1] = pi4[c].y + b.y;
+          pz[16 * hb + 4 * c + 2] = pi4[c].z + b.z;
+          pz[16 * hb + 4 * c + 3] = pi4[c].w + b.w;
+        }
+        __syncwarp();
+      }
+    }
+    // ---- T3: z1 -> a1 (operands A, A') and SiLU'(z1) (stash) ; GEMM2d + GEMM2g ----
+    mbar_wait_warp(bar1, par);
+    fence_after_sync();
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+      float v[16], g[16];
+      tmem_ld16(t_lane + Z1 + 64 * hb + k0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        float z = v[c] + pz[16 * hb + c];
+        float sg = sigmoid_fast(z);
+        v[c] = z * sg;
+        g[c] = sg * (1.0f + z * (1.0f - sg));
+      }
+      tmem_st16(t_lane + Z1 + 64 * hb + k0, g);
+      if (hb == 0) tmem_put_split16(t_lane + AH + k0, t_lane + AL + k0, v);
+      else tmem_put_split16(t_lane + D3D + k0, t_lane + D3G + k0, v);
+    }
+    tmem_st_wait();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_gemm_ts(tmem + D2D, tmem + AH, tmem + AL, w2d_hi, w2d_lo, 64, 64, false, p.passes);
+      issue_gemm_ts(tmem + D2G, tmem + D3D, tmem + D3G, w2g_hi, w2g_lo, 64, 64, false, p.passes);
+      commit(bar2);
+    }
+    // ---- T4 (overlaps GEMM2): upstream gradient slice, h ----
+    float gu[16];
+    if (p.mode == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        c4v[i] = __ldg(reinterpret_cast<const float4*>(p.g_up + min(erow[i], p.E - 1) * TC_F + k0 + 4 * cc4));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sts128(stg + stg_off(8 * i + cr, cc4), c4v[i]);
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float4 b = lds128(stg + stg_off(lane, c));
+        gu[4 * c] = b.x; gu[4 * c + 1] = b.y; gu[4 * c + 2] = b.z; gu[4 * c + 3] = b.w;
+      }
+      __syncwarp();
+    } else {
+      const float* gr = p.g_up + (int64_t)s_atom * TC_F + k0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float4 b = __ldg(reinterpret_cast<const float4*>(gr + 4 * c));
+        gu[4 * c] = b.x; gu[4 * c + 1] = b.y; gu[4 * c + 2] = b.z; gu[4 * c + 3] = b.w;
+      }
+    }
+    float hm[TC_BWD_MAX_R], ghp[TC_BWD_MAX_R];
+#pragma unroll
+    for (int m = 0; m < TC_BWD_MAX_R; ++m) {
+      hm[m] = (m < R) ? __ldg(p.h + eg * R + m) : 0.0f;
+      ghp[m] = 0.0f;
+    }
+    // ---- T5: output-stage adjoint -> dz2d (operand A), dz2g (operand A2) ; GEMM3d + GEMM3g ----
+    mbar_wait_warp(bar2, par);
+    fence_after_sync();
+    {
+      float vd[16], vg[16];
+      tmem_ld16(t_lane + D2D + k0, vd);
+      tmem_ld16(t_lane + D2G + k0, vg);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 16; c += 4) {
+        float4 bd = lds128(b2d_a + 4 * (k0 + c));
+        float4 bg = lds128(b2g_a + 4 * (k0 + c));
+        float bdv[4] = {bd.x, bd.y, bd.z, bd.w}, bgv[4] = {bg.x, bg.y, bg.z, bg.w};
+        float whv[TC_BWD_MAX_R][4];
+#pragma unroll
+        for (int m = 0; m < TC_BWD_MAX_R; ++m) {
+          float4 w4 = lds128(wh_a + 4 * (m * 64 + k0 + c));
+          whv[m][0] = w4.x; whv[m][1] = w4.y; whv[m][2] = w4.z; whv[m][3] = w4.w;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float zd = vd[c + u] + bdv[u];
+          float sgm = sigmoid_fast(zd);
+          float sd = zd * sgm;
+          float sgr = sgm * (1.0f + zd * (1.0f - sgm));
+          float sg = sigmoid_fast(vg[c + u] + bgv[u]);
+          float s = 0.0f;
+#pragma unroll
+          for (int m = 0; m < TC_BWD_MAX_R; ++m) s += hm[m] * whv[m][u];
+          float gs = gu[c + u] * sd * sg;
+#pragma unroll
+          for (int m = 0; m < TC_BWD_MAX_R; ++m) ghp[m] += gs * whv[m][u];
+          float gphi = gu[c + u] * s;
+          vd[c + u] = gphi * sg * sgr;               // dz2d
+          vg[c + u] = gphi * sd * sg * (1.0f - sg);  // dz2g
+        }
+      }
+      tmem_put_split16(t_lane + AH + k0, t_lane + AL + k0, vd);
+      tmem_put_split16(t_lane + D2D + k0, t_lane + D2G + k0, vg);
+    }
+    // g_h partial sums of the three other column slices of this row travel through their warps' own (idle)
+    // staging tiles: slot `lane` of warp q + 4*cs
+    if (cs != 0) sts128(stg + lane * 16, make_float4(ghp[0], ghp[1], ghp[2], 0.0f));
+    tmem_st_wait();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      mbar_wait(tb0, 0);
+      issue_gemm_ts(tmem + D3D, tmem + AH, tmem + AL, s0, s0 + IMG_W2 * 4, 64, 64, false, p.passes);
+      mbar_wait(tb1, 0);
+      issue_gemm_ts(tmem + D3G, tmem + D2D, tmem + D2G, s1, s1 + IMG_W2 * 4, 64, 64, false, p.passes);
+      commit(bar3);
+    }
+    if (cs == 0) {
+      float4 g1 = lds128(stg + 4 * STG_WARP_BYTES + lane * 16);
+      float4 g2 = lds128(stg + 8 * STG_WARP_BYTES + lane * 16);
+      float4 g3 = lds128(stg + 12 * STG_WARP_BYTES + lane * 16);
+      if (live) {
+        float tot[3] = {((ghp[0] + g1.x) + g2.x) + g3.x, ((ghp[1] + g1.y) + g2.y) + g3.y,
+                        ((ghp[2] + g1.z) + g2.z) + g3.z};
+#pragma unroll
+        for (int m = 0; m < TC_BWD_MAX_R; ++m)
+          if (m < R) p.g_h[eg * R + m] += tot[m];
+      }
+    }
+    // residual gradient rows for the final g_e store (coalesced layout), prefetched while GEMM3 runs
+    float4 gb[4];
+    if (p.g_e_base) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        gb[i] = __ldg(reinterpret_cast<const float4*>(p.g_e_base + min(erow[i], p.E - 1) * TC_F + k0 + 4 * cc4));
+    }
+    // ---- T6: dz1 = D3 * SiLU'(z1) -> operands A (dense), A2 (gate) ; GEMM4a + GEMM4b ----
+    mbar_wait_warp(bar3, par);
+    fence_after_sync();
+    if (tid == 0) {
+      mbar_arrive_expect_tx(tb0, PAIR_BYTES);
+      bulk_g2s(s0, p.wimgT + 2 * 2 * IMG_W2, PAIR_BYTES, tb0);  // W1e(dense rows)^T
+      mbar_arrive_expect_tx(tb1, PAIR_BYTES);
+      bulk_g2s(s1, p.wimgT + 3 * 2 * IMG_W2, PAIR_BYTES, tb1);  // W1e(gate rows)^T
+    }
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+      float v[16], g[16];
+      tmem_ld16(t_lane + (hb ? D3G : D3D) + k0, v);
+      tmem_ld16(t_lane + Z1 + 64 * hb + k0, g);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 16; ++c) v[c] *= g[c];
+      if (hb == 0) tmem_put_split16(t_lane + AH + k0, t_lane + AL + k0, v);
+      else tmem_put_split16(t_lane + D2D + k0, t_lane + D2G + k0, v);
+    }
+    tmem_st_wait();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      mbar_wait(tb0, 1);
+      issue_gemm_ts(tmem + Z1, tmem + AH, tmem + AL, s0, s0 + IMG_W2 * 4, 64, 64, false, p.passes);
+      mbar_wait(tb1, 1);
+      issue_gemm_ts(tmem + Z1, tmem + D2D, tmem + D2G, s1, s1 + IMG_W2 * 4, 64, 64, true, p.passes);
+      commit(bar4);
+    }
+    // ---- T7: outputs (g_e, g_z1), coalesced through the staging tile ----
+    mbar_wait_warp(bar4, par);
+    fence_after_sync();
+    if (tid == 0 && tile + gridDim.x < n_tiles) {
+      mbar_arrive_expect_tx(tb0, PAIR_BYTES);
+      bulk_g2s(s0, p.wimgT + 0 * 2 * IMG_W2, PAIR_BYTES, tb0);
+      mbar_arrive_expect_tx(tb1, PAIR_BYTES);
+      bulk_g2s(s1, p.wimgT + 1 * 2 * IMG_W2, PAIR_BYTES, tb1);
+    }
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      float v[16];
+      if (o == 0) {
+        tmem_ld16(t_lane + Z1 + k0, v);
+        tmem_ld_wait();
+      } else {
+        float w[16];
+        tmem_ld16(t_lane + (o == 1 ? AH : D2D) + k0, v);
+        tmem_ld16(t_lane + (o == 1 ? AL : D2G) + k0, w);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] += w[c];
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        sts128(stg + stg_off(lane, c), make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 r4 = lds128(stg + stg_off(8 * i + cr, cc4));
+        if (erow[i] < p.E) {
+          if (o == 0) {
+            if (p.g_e_base) { r4.x += gb[i].x; r4.y += gb[i].y; r4.z += gb[i].z; r4.w += gb[i].w; }
+            *reinterpret_cast<float4*>(p.g_e + erow[i] * TC_F + k0 + 4 * cc4) = r4;
+          } else {
+            *reinterpret_cast<float4*>(p.g_z1 + erow[i] * 128 + 64 * (o - 1) + k0 + 4 * cc4) = r4;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    fence_before_sync();
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 }  // namespace m3g
 
 using namespace m3g;
@@ -1477,7 +1830,7 @@ int m3g_conv_tc_fwd(const float* P, int ldp, int po, const int32_t* src, const i
 int m3g_conv_tc_bwd(const float* P, int ldp, int po, const int32_t* src, const int32_t* dst, const float* e,
                     const float* h, const float* wimg, const float* wimgT, const float* b2d, const float* b2g,
                     const float* WhT, const float* g_up, const float* g_e_base, int64_t E, int R, int mode, int passes,
-                    int n_sm, float* g_e, float* g_z1, float* g_h, void* stream) {
+                    int variant, int n_sm, float* g_e, float* g_z1, float* g_h, void* stream) {
   if (E == 0) return M3G_OK;
   M3G_REQUIRE(P && src && dst && e && h && wimg && wimgT && b2d && b2g && WhT && g_up && g_e && g_z1 && g_h,
               "m3g_conv_tc_bwd: null pointer");
@@ -1494,6 +1847,16 @@ int m3g_conv_tc_bwd(const float* P, int ldp, int po, const int32_t* src, const i
                     g_e, g_z1, g_h};
   int64_t n_tiles = (E + TILE_M - 1) / TILE_M;
   unsigned grid = (unsigned)((n_tiles < n_sm) ? n_tiles : n_sm);
+  if (variant == 2) {
+    err = cudaFuncSetAttribute(conv_tc_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD2_BYTES);
+    if (err != cudaSuccess) {
+      set_error("m3g_conv_tc_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+      return M3G_ERR_CUDA;
+    }
+    conv_tc_bwd2_kernel<<<grid, TCB2_THREADS, SMEM_BWD2_BYTES, as_stream(stream)>>>(p);
+    M3G_LAUNCH_CHECK("m3g_conv_tc_bwd");
+    return M3G_OK;
+  }
   conv_tc_bwd_kernel<<<grid, TC_THREADS, SMEM_BWD_BYTES, as_stream(stream)>>>(p);
   M3G_LAUNCH_CHECK("m3g_conv_tc_bwd");
   return M3G_OK;

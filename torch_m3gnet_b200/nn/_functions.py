@@ -34,6 +34,12 @@ def tc_variant() -> int:
     return conv.TC_VARIANT
 
 
+def tc_bwd_variant() -> int:
+    from torch_m3gnet_b200.nn import conv
+
+    return conv.TC_BWD_VARIANT
+
+
 def conv_path() -> str:
     from torch_m3gnet_b200.nn import conv
 
@@ -248,9 +254,9 @@ class ConvFn(Function):
             passes = 3 if path == "tc3" else 1
             n_sm = sm_count(x.device)
             call("conv_tc_bwd", P, 8 * F, 4 * F, plan.src, plan.dst, e2, h, nd["wimg"], nd["wimgT"], nd["b2d"], nd["b2g"],
-                 nd["WhT"], g_x2, g_e2, E, R, 1, passes, n_sm, ge2, gz_node, g_h)
+                 nd["WhT"], g_x2, g_e2, E, R, 1, passes, tc_bwd_variant(), n_sm, ge2, gz_node, g_h)
             call("conv_tc_bwd", P, 8 * F, 0, plan.src, plan.dst, e, h, ed["wimg"], ed["wimgT"], ed["b2d"], ed["b2g"],
-                 ed["WhT"], ge2, ge2, E, R, 0, passes, n_sm, g_e, gz_edge, g_h)
+                 ed["WhT"], ge2, ge2, E, R, 0, passes, tc_bwd_variant(), n_sm, g_e, gz_edge, g_h)
         else:
             call("conv_mlp_bwd", P, 8 * F, 4 * F, plan.src, plan.dst, e2, h, nd["W1eT"], nd["W2dT"], nd["b2d"],
                  nd["W2gT"], nd["b2g"], nd["WhT"], nd["W1e"], nd["W2d"], nd["W2g"], nd["Wh"], g_x2, g_e2, E, F, R, 1,

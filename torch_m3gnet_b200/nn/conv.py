@@ -17,6 +17,9 @@ CONV_PATH = os.environ.get("M3G_CONV_PATH", "tc3")
 # 1: one 128-edge tile per CTA at a time; 2: two warp groups ping-pong two tiles; 3: 2 + coalesced gathers through
 # per-warp staging (csrc/conv_tc.cu)
 TC_VARIANT = int(os.environ.get("M3G_TC_VARIANT", "4"))
+# backward: 1 = one tile per CTA through shared operand buffers; 2 = all A operands in tensor memory, coalesced
+# traffic, bulk-copied transposed weight images (csrc/conv_tc.cu)
+TC_BWD_VARIANT = int(os.environ.get("M3G_TC_BWD_VARIANT", "2"))
 
 
 def _tc_images(w1e: torch.Tensor, w2d: torch.Tensor, w2g: torch.Tensor) -> torch.Tensor:
