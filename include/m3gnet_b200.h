@@ -233,6 +233,12 @@ int m3g_linear_bwd_input(const float* g, const float* W, const float* base, int6
  * a time (8 warps); variant 2 = two warp groups per CTA ping-pong two tiles over the shared operand buffer.
  * ------------------------------------------------------------------------------------------- */
 int m3g_tc_pack_b(const float* W, int rows, int cols, float* img_hi, float* img_lo, void* stream);
+/* debug: per-phase cycle sums of the backward kernel (HOST buffer of 16 int64; all zero unless the library was built
+ * with -DM3G_TC_TIMING); synchronises the stream */
+int m3g_debug_tc_timing(int64_t* out16, int reset, void* stream);
+/* debug: cycles to issue / to complete n_mma back-to-back tcgen05.mma kind::tf32 (M = 128, K = 8) of width N with A
+ * from shared (a_tmem = 0) or tensor memory (1); cycles2 = DEVICE buffer of two int64 */
+int m3g_debug_mma_rate(int N, int a_tmem, int n_mma, int64_t* cycles2, void* stream);
 /* UMMA plumbing self test on one 128-row tile: out (128 x rows) = A (128 x cols) · W^T, W given as its image;
  * a_tmem = 1 feeds A from tensor memory (tcgen05.st + the [a_tmem] operand form) instead of shared memory */
 int m3g_tc_selftest(const float* A, const float* img_hi, const float* img_lo, int rows, int cols, int passes,

@@ -16,6 +16,7 @@ OBJ_DIR = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", HERE]
+FLAGS += os.environ.get("M3G_EXTRA_NVCC_FLAGS", "").split()  # e.g. -DM3G_TC_TIMING (debug phase timing)
 
 
 def sources():

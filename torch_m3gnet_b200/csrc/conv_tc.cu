@@ -43,32 +43,72 @@ __device__ __forceinline__ void store_split4(char* x_hi, char* x_lo, int r, int 
 
 // D[128 x N] (+)= A[128 x K] · Bimg^T with A a K-major image (128 rows) and B a K-major image with N rows:
 //   D[m][n] += sum_k A[m][k] * Bimg[n][k]        (3 passes: hi·hi, lo·hi, hi·lo).  Issued by ONE thread.
-__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
-                                           uint32_t b_lo, int N, int K, bool accumulate, int passes) {
-  const uint32_t idesc = make_idesc_tf32(TILE_M, N, 0);
-  for (int pass = 0; pass < passes; ++pass) {
-    uint32_t a = (pass == 1) ? a_lo : a_hi;
-    uint32_t b = (pass == 2) ? b_lo : b_hi;
+// Descriptors only differ in their start-address field (bits 0-13, in 16-byte units), so the loops advance the
+// low word instead of rebuilding them; PASSES / N / K are compile-time so the issue stream is straight-line code.
+template <int PASSES, int N, int K>
+__device__ __forceinline__ void issue_gemm_t(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                             uint32_t b_lo, bool accumulate) {
+  constexpr uint32_t idesc = make_idesc_tf32(TILE_M, N, 0);
+  const uint64_t dah = make_desc(a_hi, 16, 1024), dal = make_desc(a_lo, 16, 1024);
+  const uint64_t dbh = make_desc(b_hi, 16, 1024), dbl = make_desc(b_lo, 16, 1024);
+#pragma unroll
+  for (int pass = 0; pass < PASSES; ++pass) {
+    const uint64_t da0 = (pass == 1) ? dal : dah;
+    const uint64_t db0 = (pass == 2) ? dbl : dbh;
+#pragma unroll
     for (int kk = 0; kk < K / 8; ++kk) {
-      uint64_t da = make_desc(a + (kk >> 2) * (TILE_M * 128) + (kk & 3) * 32, 16, 1024);
-      uint64_t db = make_desc(b + (kk >> 2) * (N * 128) + (kk & 3) * 32, 16, 1024);
+      const uint64_t da = da0 + (uint64_t)(((kk >> 2) * (TILE_M * 128) + (kk & 3) * 32) >> 4);
+      const uint64_t db = db0 + (uint64_t)(((kk >> 2) * (N * 128) + (kk & 3) * 32) >> 4);
       mma_tf32(tmem_d, da, db, idesc, (accumulate || pass > 0 || kk > 0) ? 1u : 0u);
     }
+  }
+}
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                           uint32_t b_lo, int N, int K, bool accumulate, int passes) {
+  // (N, K) is (128, 64), (64, 64), (64, 128) or (128, 128) on every call site
+  if (passes == 3) {
+    if (N == 128 && K == 64) issue_gemm_t<3, 128, 64>(tmem_d, a_hi, a_lo, b_hi, b_lo, accumulate);
+    else if (N == 64 && K == 64) issue_gemm_t<3, 64, 64>(tmem_d, a_hi, a_lo, b_hi, b_lo, accumulate);
+    else if (N == 64) issue_gemm_t<3, 64, 128>(tmem_d, a_hi, a_lo, b_hi, b_lo, accumulate);
+    else issue_gemm_t<3, 128, 128>(tmem_d, a_hi, a_lo, b_hi, b_lo, accumulate);
+  } else {
+    if (N == 128 && K == 64) issue_gemm_t<1, 128, 64>(tmem_d, a_hi, a_lo, b_hi, b_lo, accumulate);
+    else if (N == 64 && K == 64) issue_gemm_t<1, 64, 64>(tmem_d, a_hi, a_lo, b_hi, b_lo, accumulate);
+    else if (N == 64) issue_gemm_t<1, 64, 128>(tmem_d, a_hi, a_lo, b_hi, b_lo, accumulate);
+    else issue_gemm_t<1, 128, 128>(tmem_d, a_hi, a_lo, b_hi, b_lo, accumulate);
   }
 }
 
 // Same product with the A operand in tensor memory: A_hi at columns [ta_hi, ta_hi+K), A_lo at [ta_lo, ta_lo+K)
 // (row m in lane m, written with tcgen05.st by the epilogue threads).
-__device__ __forceinline__ void issue_gemm_ts(uint32_t tmem_d, uint32_t ta_hi, uint32_t ta_lo, uint32_t b_hi,
-                                              uint32_t b_lo, int N, int K, bool accumulate, int passes) {
-  const uint32_t idesc = make_idesc_tf32(TILE_M, N, 0);
-  for (int pass = 0; pass < passes; ++pass) {
-    uint32_t a = (pass == 1) ? ta_lo : ta_hi;
-    uint32_t b = (pass == 2) ? b_lo : b_hi;
+template <int PASSES, int N, int K>
+__device__ __forceinline__ void issue_gemm_ts_t(uint32_t tmem_d, uint32_t ta_hi, uint32_t ta_lo, uint32_t b_hi,
+                                                uint32_t b_lo, bool accumulate) {
+  constexpr uint32_t idesc = make_idesc_tf32(TILE_M, N, 0);
+  const uint64_t dbh = make_desc(b_hi, 16, 1024), dbl = make_desc(b_lo, 16, 1024);
+#pragma unroll
+  for (int pass = 0; pass < PASSES; ++pass) {
+    const uint32_t a = (pass == 1) ? ta_lo : ta_hi;
+    const uint64_t db0 = (pass == 2) ? dbl : dbh;
+#pragma unroll
     for (int kk = 0; kk < K / 8; ++kk) {
-      uint64_t db = make_desc(b + (kk >> 2) * (N * 128) + (kk & 3) * 32, 16, 1024);
+      const uint64_t db = db0 + (uint64_t)(((kk >> 2) * (N * 128) + (kk & 3) * 32) >> 4);
       mma_tf32_ts(tmem_d, a + 8 * kk, db, idesc, (accumulate || pass > 0 || kk > 0) ? 1u : 0u);
     }
+  }
+}
+__device__ __forceinline__ void issue_gemm_ts(uint32_t tmem_d, uint32_t ta_hi, uint32_t ta_lo, uint32_t b_hi,
+                                              uint32_t b_lo, int N, int K, bool accumulate, int passes) {
+  if (passes == 3) {
+    if (N == 128 && K == 64) issue_gemm_ts_t<3, 128, 64>(tmem_d, ta_hi, ta_lo, b_hi, b_lo, accumulate);
+    else if (N == 64 && K == 64) issue_gemm_ts_t<3, 64, 64>(tmem_d, ta_hi, ta_lo, b_hi, b_lo, accumulate);
+    else if (N == 64) issue_gemm_ts_t<3, 64, 128>(tmem_d, ta_hi, ta_lo, b_hi, b_lo, accumulate);
+    else issue_gemm_ts_t<3, 128, 128>(tmem_d, ta_hi, ta_lo, b_hi, b_lo, accumulate);
+  } else {
+    if (N == 128 && K == 64) issue_gemm_ts_t<1, 128, 64>(tmem_d, ta_hi, ta_lo, b_hi, b_lo, accumulate);
+    else if (N == 64 && K == 64) issue_gemm_ts_t<1, 64, 64>(tmem_d, ta_hi, ta_lo, b_hi, b_lo, accumulate);
+    else if (N == 64) issue_gemm_ts_t<1, 64, 128>(tmem_d, ta_hi, ta_lo, b_hi, b_lo, accumulate);
+    else issue_gemm_ts_t<1, 128, 128>(tmem_d, ta_hi, ta_lo, b_hi, b_lo, accumulate);
   }
 }
 
@@ -912,6 +952,16 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc4_fwd_kernel(ConvTcPara
     const int64_t eg = min(e0 + row, p.E - 1);
     const int d_row = __ldg(p.dst + eg);
     const float* Pi = p.P + (int64_t)__ldg(p.src + eg) * p.ldp + p.po;
+    {
+      // pull this group's next tile (e rows, indices, h) into L2 while this tile computes
+      const int64_t en = (tile + 2 * (int64_t)gridDim.x) * TILE_M;
+      if (en < p.E) {
+        prefetch_l2(p.e + min(en + gtid / 2, p.E - 1) * TC_F + (gtid & 1) * 32);
+        if (gtid < 16) prefetch_l2(p.h + min(en * p.R + gtid * 32, p.E * p.R - 1));
+        else if (gtid < 20) prefetch_l2(p.src + min(en + (gtid - 16) * 32, p.E - 1));
+        else if (gtid < 24) prefetch_l2(p.dst + min(en + (gtid - 20) * 32, p.E - 1));
+      }
+    }
     // P[dst] row pointers of the four rows this lane serves in the coalesced layout
     const float* Pj[4];
 #pragma unroll
@@ -1400,7 +1450,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_bwd_kernel(ConvTcBwdPar
 // TMEM columns: [0,128) D1 -> SiLU'(z1) stash -> D4 in [0,64) ; [128,192) D2d, [192,256) D2g -> operand A2 (hi|lo) ;
 //               [256,320) | [320,384) operand A (hi|lo) ; [384,448) D3d, [448,512) D3g (before that: operand A' = a1g).
 constexpr int TCB2_THREADS = 512;
-constexpr int SMEM_B2_MISC = (64 + 64 + TC_BWD_MAX_R * 64) * 4 + 64;  // biases, Wh^T, 6 mbarriers, TMEM slot
+constexpr int SMEM_B2_MISC = (64 + 64 + TC_BWD_MAX_R * 64) * 4 + 80;  // biases, Wh^T, 8 mbarriers, TMEM slot
 constexpr int SMEM_BWD2_BYTES = SMEM_W_BYTES + 2 * SMEM_S_BYTES + 16 * STG_WARP_BYTES + SMEM_B2_MISC + 1024;
 static_assert(SMEM_BWD2_BYTES <= 232448, "backward variant 2 exceeds the 227 KB shared-memory limit");
 
@@ -1413,6 +1463,22 @@ __device__ __forceinline__ void tmem_put_split16(uint32_t t_hi, uint32_t t_lo, c
   for (int c = 0; c < 16; ++c) t[c] = a[c] - t[c];
   tmem_st16(t_lo, t);
 }
+
+// optional phase timing (build with M3G_EXTRA_NVCC_FLAGS=-DM3G_TC_TIMING): thread 0 of every CTA accumulates the
+// cycles between consecutive phase marks of the backward kernel; read back with m3g_debug_tc_timing
+__device__ unsigned long long g_tc_timing[16];
+#ifdef M3G_TC_TIMING
+#define TCT(k)                                                          \
+  do {                                                                  \
+    if (tid == 0) {                                                     \
+      long long now__ = clock64();                                      \
+      atomicAdd(&g_tc_timing[k], (unsigned long long)(now__ - tct_prev)); \
+      tct_prev = now__;                                                 \
+    }                                                                   \
+  } while (0)
+#else
+#define TCT(k) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwd2_kernel(ConvTcBwdParams p) {
   extern __shared__ __align__(1024) char smem_raw[];
@@ -1427,7 +1493,7 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwd2_kernel(ConvTcBwd
   float* misc = reinterpret_cast<float*>(misc_c);
   const uint32_t b2d_a = stg_all + 16 * STG_WARP_BYTES, b2g_a = b2d_a + 256, wh_a = b2g_a + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc + 128 + TC_BWD_MAX_R * 64);  // bar1..bar4, tb0, tb1
-  uint32_t* tmem_slot_p = reinterpret_cast<uint32_t*>(bars + 6);
+  uint32_t* tmem_slot_p = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, cs = warp >> 2;
@@ -1445,17 +1511,22 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwd2_kernel(ConvTcBwd
   if (warp == 0) tmem_alloc<512>(tmem_slot_p);
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
   }
   fence_proxy_async();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem = *tmem_slot_p;
-  const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+  // One CTA per SM owns all 512 columns, so the allocation starts at lane 0 / column 0; using the literal keeps every
+  // MMA operand address a compile-time uniform value (otherwise each tcgen05.mma costs two R2UR round trips and the
+  // single issuing thread, not the tensor core, paces the 64-wide GEMMs).
+  if (*tmem_slot_p != 0u) __trap();
+  constexpr uint32_t tmem = 0u;
+  const uint32_t t_lane = ((uint32_t)(32 * q) << 16);
   constexpr uint32_t Z1 = 0, D2D = 128, D2G = 192, AH = 256, AL = 320, D3D = 384, D3G = 448;
   uint64_t *bar1 = &bars[0], *bar2 = &bars[1], *bar3 = &bars[2], *bar4 = &bars[3], *tb0 = &bars[4], *tb1 = &bars[5];
+  uint64_t *bar3a = &bars[6], *bar4a = &bars[7];  // GEMM3d / GEMM4a alone: their weight buffer can be refilled early
 
   const int64_t n_tiles = (p.E + TILE_M - 1) / TILE_M;
   if (tid == 0 && (int64_t)blockIdx.x < n_tiles) {
@@ -1465,12 +1536,33 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwd2_kernel(ConvTcBwd
     bulk_g2s(s1, p.wimgT + 1 * 2 * IMG_W2, PAIR_BYTES, tb1);  // W2g^T
   }
   uint32_t par = 0;
+#ifdef M3G_TC_TIMING
+  long long tct_prev = clock64();
+#endif
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, par ^= 1) {
+    TCT(0);
     const int64_t e0 = tile * TILE_M;
     const int64_t eg = min(e0 + row, p.E - 1);
     const bool live = (e0 + row) < p.E;
     const int s_atom = __ldg(p.src + eg);
     const int d_atom = __ldg(p.dst + eg);
+    {
+      // pull the next tile's streamed rows (e, g_up / g_e_base, indices, h) into L2 while this tile computes
+      const int64_t en = (tile + gridDim.x) * TILE_M;
+      if (en < p.E) {
+        const int64_t rn = min(en + (tid & 255) / 2, p.E - 1);  // 2 x 128-byte lines per 64-float row
+        const int half = (tid & 1) * 32;
+        if (tid < 256) {
+          prefetch_l2(p.e + rn * TC_F + half);
+          if (p.g_e_base) prefetch_l2(p.g_e_base + rn * TC_F + half);
+        } else {
+          if (p.mode == 0) prefetch_l2(p.g_up + rn * TC_F + half);
+          if (tid < 256 + 16) prefetch_l2(p.h + min(en * R + (tid - 256) * 32, p.E * R - 1));
+          else if (tid < 256 + 20) prefetch_l2(p.src + min(en + (tid - 272) * 32, p.E - 1));
+          else if (tid < 256 + 24) prefetch_l2(p.dst + min(en + (tid - 276) * 32, p.E - 1));
+        }
+      }
+    }
     // rows this lane serves in the coalesced layout
     int64_t erow[4];
 #pragma unroll
@@ -1496,11 +1588,13 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwd2_kernel(ConvTcBwd
     tmem_st_wait();
     fence_before_sync();
     __syncthreads();
+    TCT(1);
     if (tid == 0) {
       fence_after_sync();
       issue_gemm_ts(tmem + Z1, tmem + AH, tmem + AL, w1_hi, w1_lo, 128, 64, false, p.passes);
       commit(bar1);
     }
+    TCT(2);
     // ---- T2 (overlaps GEMM1): P[src] + P[dst] for the dense and gate slices ----
     float pz[32];
     {
@@ -1531,7 +1625,9 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwd2_kernel(ConvTcBwd
       }
     }
     // ---- T3: z1 -> a1 (operands A, A') and SiLU'(z1) (stash) ; GEMM2d + GEMM2g ----
+    TCT(14);
     mbar_wait_warp(bar1, par);
+    TCT(3);
     fence_after_sync();
 #pragma unroll
     for (int hb = 0; hb < 2; ++hb) {
@@ -1552,12 +1648,14 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwd2_kernel(ConvTcBwd
     tmem_st_wait();
     fence_before_sync();
     __syncthreads();
+    TCT(4);
     if (tid == 0) {
       fence_after_sync();
       issue_gemm_ts(tmem + D2D, tmem + AH, tmem + AL, w2d_hi, w2d_lo, 64, 64, false, p.passes);
       issue_gemm_ts(tmem + D2G, tmem + D3D, tmem + D3G, w2g_hi, w2g_lo, 64, 64, false, p.passes);
       commit(bar2);
     }
+    TCT(5);
     // ---- T4 (overlaps GEMM2): upstream gradient slice, h ----
     float gu[16];
     if (p.mode == 0) {
@@ -1588,7 +1686,9 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwd2_kernel(ConvTcBwd
       ghp[m] = 0.0f;
     }
     // ---- T5: output-stage adjoint -> dz2d (operand A), dz2g (operand A2) ; GEMM3d + GEMM3g ----
+    TCT(14);
     mbar_wait_warp(bar2, par);
+    TCT(6);
     fence_after_sync();
     {
       float vd[16], vg[16];
@@ -1633,14 +1733,21 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwd2_kernel(ConvTcBwd
     tmem_st_wait();
     fence_before_sync();
     __syncthreads();
+    TCT(7);
     if (tid == 0) {
       fence_after_sync();
       mbar_wait(tb0, 0);
       issue_gemm_ts(tmem + D3D, tmem + AH, tmem + AL, s0, s0 + IMG_W2 * 4, 64, 64, false, p.passes);
+      commit(bar3a);
       mbar_wait(tb1, 0);
       issue_gemm_ts(tmem + D3G, tmem + D2D, tmem + D2G, s1, s1 + IMG_W2 * 4, 64, 64, false, p.passes);
       commit(bar3);
+      // GEMM3d finished while GEMM3g was being issued: its buffer takes W1e(dense rows)^T now
+      mbar_wait(bar3a, par);
+      mbar_arrive_expect_tx(tb0, PAIR_BYTES);
+      bulk_g2s(s0, p.wimgT + 2 * 2 * IMG_W2, PAIR_BYTES, tb0);
     }
+    TCT(8);
     if (cs == 0) {
       float4 g1 = lds128(stg + 4 * STG_WARP_BYTES + lane * 16);
       float4 g2 = lds128(stg + 8 * STG_WARP_BYTES + lane * 16);
@@ -1653,67 +1760,81 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwd2_kernel(ConvTcBwd
           if (m < R) p.g_h[eg * R + m] += tot[m];
       }
     }
-    // residual gradient rows for the final g_e store (coalesced layout), prefetched while GEMM3 runs
+    // ---- T6: dz1 = D3 * SiLU'(z1) -> operands A (dense), A2 (gate) ; GEMM4a + GEMM4b ----
+    TCT(15);
+    mbar_wait_warp(bar3, par);
+    TCT(9);
+    fence_after_sync();
+    if (tid == 0) {
+      mbar_arrive_expect_tx(tb1, PAIR_BYTES);
+      bulk_g2s(s1, p.wimgT + 3 * 2 * IMG_W2, PAIR_BYTES, tb1);  // W1e(gate rows)^T
+    }
+    float dz1[32];
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+      float g[16];
+      tmem_ld16(t_lane + (hb ? D3G : D3D) + k0, dz1 + 16 * hb);
+      tmem_ld16(t_lane + Z1 + 64 * hb + k0, g);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 16; ++c) dz1[16 * hb + c] *= g[c];
+      if (hb == 0) tmem_put_split16(t_lane + AH + k0, t_lane + AL + k0, dz1);
+      else tmem_put_split16(t_lane + D2D + k0, t_lane + D2G + k0, dz1 + 16);
+    }
+    tmem_st_wait();
+    fence_before_sync();
+    __syncthreads();
+    TCT(10);
+    if (tid == 0) {
+      fence_after_sync();
+      mbar_wait(tb0, 1);
+      issue_gemm_ts(tmem + Z1, tmem + AH, tmem + AL, s0, s0 + IMG_W2 * 4, 64, 64, false, p.passes);
+      commit(bar4a);
+      mbar_wait(tb1, 1);
+      issue_gemm_ts(tmem + Z1, tmem + D2D, tmem + D2G, s1, s1 + IMG_W2 * 4, 64, 64, true, p.passes);
+      commit(bar4);
+      if (tile + gridDim.x < n_tiles) {  // the next tile's W2d^T
+        mbar_wait(bar4a, par);
+        mbar_arrive_expect_tx(tb0, PAIR_BYTES);
+        bulk_g2s(s0, p.wimgT + 0 * 2 * IMG_W2, PAIR_BYTES, tb0);
+      }
+    }
+    // residual gradient rows for the final g_e store (coalesced layout; L2-resident thanks to the tile prefetch)
     float4 gb[4];
     if (p.g_e_base) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         gb[i] = __ldg(reinterpret_cast<const float4*>(p.g_e_base + min(erow[i], p.E - 1) * TC_F + k0 + 4 * cc4));
     }
-    // ---- T6: dz1 = D3 * SiLU'(z1) -> operands A (dense), A2 (gate) ; GEMM4a + GEMM4b ----
-    mbar_wait_warp(bar3, par);
-    fence_after_sync();
-    if (tid == 0) {
-      mbar_arrive_expect_tx(tb0, PAIR_BYTES);
-      bulk_g2s(s0, p.wimgT + 2 * 2 * IMG_W2, PAIR_BYTES, tb0);  // W1e(dense rows)^T
-      mbar_arrive_expect_tx(tb1, PAIR_BYTES);
-      bulk_g2s(s1, p.wimgT + 3 * 2 * IMG_W2, PAIR_BYTES, tb1);  // W1e(gate rows)^T
-    }
+    // g_z1 rows straight from registers (overlaps GEMM4), coalesced through the staging tile
 #pragma unroll
     for (int hb = 0; hb < 2; ++hb) {
-      float v[16], g[16];
-      tmem_ld16(t_lane + (hb ? D3G : D3D) + k0, v);
-      tmem_ld16(t_lane + Z1 + 64 * hb + k0, g);
-      tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 16; ++c) v[c] *= g[c];
-      if (hb == 0) tmem_put_split16(t_lane + AH + k0, t_lane + AL + k0, v);
-      else tmem_put_split16(t_lane + D2D + k0, t_lane + D2G + k0, v);
+      for (int c = 0; c < 4; ++c)
+        sts128(stg + stg_off(lane, c), make_float4(dz1[16 * hb + 4 * c], dz1[16 * hb + 4 * c + 1],
+                                                   dz1[16 * hb + 4 * c + 2], dz1[16 * hb + 4 * c + 3]));
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 r4 = lds128(stg + stg_off(8 * i + cr, cc4));
+        if (erow[i] < p.E) *reinterpret_cast<float4*>(p.g_z1 + erow[i] * 128 + 64 * hb + k0 + 4 * cc4) = r4;
+      }
+      __syncwarp();
     }
-    tmem_st_wait();
-    fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      fence_after_sync();
-      mbar_wait(tb0, 1);
-      issue_gemm_ts(tmem + Z1, tmem + AH, tmem + AL, s0, s0 + IMG_W2 * 4, 64, 64, false, p.passes);
-      mbar_wait(tb1, 1);
-      issue_gemm_ts(tmem + Z1, tmem + D2D, tmem + D2G, s1, s1 + IMG_W2 * 4, 64, 64, true, p.passes);
-      commit(bar4);
-    }
+    TCT(11);
     // ---- T7: outputs (g_e, g_z1), coalesced through the staging tile ----
+    TCT(15);
     mbar_wait_warp(bar4, par);
+    TCT(12);
     fence_after_sync();
     if (tid == 0 && tile + gridDim.x < n_tiles) {
-      mbar_arrive_expect_tx(tb0, PAIR_BYTES);
-      bulk_g2s(s0, p.wimgT + 0 * 2 * IMG_W2, PAIR_BYTES, tb0);
       mbar_arrive_expect_tx(tb1, PAIR_BYTES);
       bulk_g2s(s1, p.wimgT + 1 * 2 * IMG_W2, PAIR_BYTES, tb1);
     }
-#pragma unroll
-    for (int o = 0; o < 3; ++o) {
+    {
       float v[16];
-      if (o == 0) {
-        tmem_ld16(t_lane + Z1 + k0, v);
-        tmem_ld_wait();
-      } else {
-        float w[16];
-        tmem_ld16(t_lane + (o == 1 ? AH : D2D) + k0, v);
-        tmem_ld16(t_lane + (o == 1 ? AL : D2G) + k0, w);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] += w[c];
-      }
+      tmem_ld16(t_lane + Z1 + k0, v);
+      tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         sts128(stg + stg_off(lane, c), make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
@@ -1722,21 +1843,63 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwd2_kernel(ConvTcBwd
       for (int i = 0; i < 4; ++i) {
         float4 r4 = lds128(stg + stg_off(8 * i + cr, cc4));
         if (erow[i] < p.E) {
-          if (o == 0) {
-            if (p.g_e_base) { r4.x += gb[i].x; r4.y += gb[i].y; r4.z += gb[i].z; r4.w += gb[i].w; }
-            *reinterpret_cast<float4*>(p.g_e + erow[i] * TC_F + k0 + 4 * cc4) = r4;
-          } else {
-            *reinterpret_cast<float4*>(p.g_z1 + erow[i] * 128 + 64 * (o - 1) + k0 + 4 * cc4) = r4;
-          }
+          if (p.g_e_base) { r4.x += gb[i].x; r4.y += gb[i].y; r4.z += gb[i].z; r4.w += gb[i].w; }
+          *reinterpret_cast<float4*>(p.g_e + erow[i] * TC_F + k0 + 4 * cc4) = r4;
         }
       }
       __syncwarp();
     }
     fence_before_sync();
+    TCT(13);
   }
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// --------------------------------------------------------------------------------------------------------
+// debug: issue rate of tcgen05.mma kind::tf32 M=128 for a given N, A from shared (0) or tensor memory (1)
+template <int N, int ATMEM>
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n_rep, long long* out) {
+  extern __shared__ __align__(1024) char smem_raw[];
+  char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  for (int i = threadIdx.x; i < (64 + 128) * 1024 / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 1.0f;
+  if (threadIdx.x < 32) tmem_alloc<512>(&tmem_slot);
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  if (tmem_slot != 0u) __trap();
+  if (threadIdx.x == 0) {
+    constexpr uint32_t idesc = make_idesc_tf32(TILE_M, N, 0);
+    const uint32_t a = smem_u32(smem), b = a + 64 * 1024;
+    const uint64_t da0 = make_desc(a, 16, 1024), db0 = make_desc(b, 16, 1024);
+    long long t0 = clock64();
+    for (int r = 0; r < n_rep; ++r) {
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const uint64_t db = db0 + (uint64_t)(((kk >> 2) * (N * 128) + (kk & 3) * 32) >> 4);
+        if (ATMEM) {
+          mma_tf32_ts(0u, 256u + 8 * kk, db, idesc, 1u);
+        } else {
+          const uint64_t da = da0 + (uint64_t)(((kk >> 2) * (TILE_M * 128) + (kk & 3) * 32) >> 4);
+          mma_tf32(0u, da, db, idesc, 1u);
+        }
+      }
+    }
+    long long t1 = clock64();
+    commit(&bar);
+    mbar_wait(&bar, 0);
+    long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc<512>(0u);
 }
 
 }  // namespace m3g
@@ -1744,6 +1907,41 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwd2_kernel(ConvTcBwd
 using namespace m3g;
 
 extern "C" {
+
+int m3g_debug_mma_rate(int N, int a_tmem, int n_mma, int64_t* cycles2, void* stream) {
+  M3G_REQUIRE(cycles2 && (N == 64 || N == 128 || N == 256) && n_mma >= 8, "m3g_debug_mma_rate: bad arguments");
+  int smem = (64 + 128) * 1024 + 1024;
+  long long* out = (long long*)cycles2;
+#define RATE_(N_, A_)                                                                                         \
+  do {                                                                                                        \
+    cudaFuncSetAttribute(mma_rate_kernel<N_, A_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);         \
+    mma_rate_kernel<N_, A_><<<1, 128, smem, as_stream(stream)>>>(n_mma / 8, out);                             \
+  } while (0)
+  if (N == 64 && !a_tmem) RATE_(64, 0);
+  else if (N == 64) RATE_(64, 1);
+  else if (N == 128 && !a_tmem) RATE_(128, 0);
+  else if (N == 128) RATE_(128, 1);
+  else if (!a_tmem) RATE_(256, 0);
+  else RATE_(256, 1);
+#undef RATE_
+  M3G_LAUNCH_CHECK("m3g_debug_mma_rate");
+  return M3G_OK;
+}
+
+int m3g_debug_tc_timing(int64_t* out16, int reset, void* stream) {
+  M3G_REQUIRE(out16, "m3g_debug_tc_timing: null pointer");
+  cudaError_t err = cudaStreamSynchronize(as_stream(stream));
+  if (err == cudaSuccess) err = cudaMemcpyFromSymbol(out16, g_tc_timing, 16 * sizeof(unsigned long long));
+  if (err == cudaSuccess && reset) {
+    unsigned long long z[16] = {0};
+    err = cudaMemcpyToSymbol(g_tc_timing, z, sizeof(z));
+  }
+  if (err != cudaSuccess) {
+    set_error("m3g_debug_tc_timing: %s", cudaGetErrorString(err));
+    return M3G_ERR_CUDA;
+  }
+  return M3G_OK;
+}
 
 int m3g_tc_pack_b(const float* W, int rows, int cols, float* img_hi, float* img_lo, void* stream) {
   M3G_REQUIRE(W && img_hi && img_lo, "m3g_tc_pack_b: null pointer");
