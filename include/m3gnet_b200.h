@@ -172,6 +172,23 @@ int m3g_tb_edge_basis_bwd(const float* vec4, const int32_t* dst, const float* si
 int m3g_tb_sigma_bwd(const float* g_sig_e, const int32_t* in_ptr, const int32_t* in_perm, const float* sig,
                      const float* Ws, int64_t N, int F, int D, float* g_x, void* stream);
 
+/* Canonical triplet layout (what compute_threebody, data/material_graph.py:239-248, emits): for every atom the
+ * rows of its member bonds (bonds with a non-empty triplet row) list exactly all other member bonds of that atom,
+ * ascending.  m3g_tri_dense_check: flags[0] = 1 if the CSR has that layout, flags[1] = max members per atom.
+ * m3g_tb_atom_fwd / _bwd (csrc/threebody_atom.cu; l_max = n_max = 3, F = 64, members per atom <=
+ * m3g_tb_atom_capacity()) evaluate the three-body op with one warp per centre atom out of shared memory: no
+ * triplet index list is read.  fwd writes red for member bonds only and e_out for all bonds; bwd writes g_vec4 /
+ * g_bas for all bonds (zeros for non-members).  The gradient w.r.t. e_in is g_e itself. */
+int m3g_tri_dense_check(const int32_t* edge_ptr, const int32_t* tri_ptr, const int32_t* tri_e2, int64_t N,
+                        int32_t* flags, void* stream);
+int m3g_tb_atom_capacity(void);
+int m3g_tb_atom_fwd(const float* vec4, const float* bas, const int32_t* edge_ptr, const int32_t* tri_ptr, float r3,
+                    const float* WdT, const float* WgT, const float* e_in, int64_t N, int n_sm, float* red,
+                    float* e_out, void* stream);
+int m3g_tb_atom_bwd(const float* vec4, const float* bas, const float* red, const float* g_e, const int32_t* edge_ptr,
+                    const int32_t* tri_ptr, float r3, const float* WdT, const float* WgT, int64_t N, int n_sm,
+                    float* g_vec4, float* g_bas, void* stream);
+
 /* Specialised variants for the default model shape l_max = n_max = 3, F = 64 (compile-time loops, gated-MLP
  * weights in shared memory, vector row I/O, persistent grid of 8 x n_sm blocks).  Same results and buffers as
  * the generic entry points above; r3 = three-body cutoff.  m3g_tb_reduce_bwd_sym requires a symmetric triplet

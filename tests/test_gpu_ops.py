@@ -116,7 +116,7 @@ def _threebody_reference_grads(g, gd):
     return out, red, gx, ge, gv
 
 
-@pytest.fixture(params=["fast", "generic"])
+@pytest.fixture(params=["atom", "fast", "generic"])
 def tb_path(request):
     from torch_m3gnet_b200.nn import interaction
 
@@ -134,6 +134,7 @@ def test_threebody_operator(device, tb_path):
     gd = graph_dict(g)
     b, plan, pos, vec4, dist, cos = _plan_and_geometry(gd, device)
     report("tb.geom.dist", dist, g["dist"], 1e-6, 1e-6)
+    assert plan.tri_dense, "compute_threebody layout must be certified dense (per-atom kernels would be skipped)"
     tb = ThreeBodyInteration(5.0, 4.0, 3, 3, 64, 64, device=device)
     tb.load_state_dict(state_dict_of(g))
     tb.nsb.factors = torch.from_numpy(g["factors"]).to(device)
@@ -182,7 +183,7 @@ def test_threebody_asymmetric_triplet_list(device, tb_path):
     keep = torch.rand(T) < 0.6
     gd["triplet_edge_index"] = gd["triplet_edge_index"][:, keep][:, torch.randperm(int(keep.sum()))]
     b, plan, pos, vec4, dist, cos = _plan_and_geometry(gd, device)
-    assert not plan.tri_symmetric
+    assert not plan.tri_symmetric and not plan.tri_dense
     tb = ThreeBodyInteration(5.0, 4.0, 3, 3, 64, 64, device=device)
     tb.load_state_dict(state_dict_of(g))
     tb.nsb.factors = torch.from_numpy(g["factors"]).to(device)

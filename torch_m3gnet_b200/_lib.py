@@ -130,3 +130,7 @@ def call(name: str, *args):
 
 def scan_work_elems(n: int) -> int:
     return int(LIB.load().m3g_scan_work_elems(n))
+
+
+def tb_atom_capacity() -> int:
+    return int(LIB.load().m3g_tb_atom_capacity())

@@ -1,0 +1,347 @@
+// ThreeBodyInteration (nn/interaction.py:187-223) for the canonical triplet layout, one warp per CENTRE ATOM.
+//
+// compute_threebody (data/material_graph.py:239-248) emits, for every atom, the full off-diagonal of the pair matrix
+// of its bonds inside the three-body cutoff ("member" bonds).  When the plan certifies that layout (tri_dense, see
+// m3g_tri_dense_check) the triplet list itself carries no information: a warp stages the per-bond data of its atom's
+// member bonds in shared memory ONCE (O(n3) HBM/L2 reads) and evaluates the n3 x n3 pair matrix out of shared memory
+// (O(n3^2) work, broadcast reads, no atomics, no index list).  HBM traffic per block:
+//   forward   e rows 256 B read + 256 B write per bond; member bonds: geometry 16 B + basis 36 B in, red 36 B out
+//   backward  member bonds: upstream rows 256 B, geometry/basis/red in, g_vec4 16 B + g_bas 36 B out (zeros elsewhere)
+// i.e. the algorithmic bytes of SURVEY.md §8(d) minus the 4 B / triplet index term.
+// Accumulation order (stated): bond j sums its partners k in ascending member order = ascending second-bond id, one
+// lane, sequentially — the order of the reference's CPU scatter_add_ over its triplet list.
+#include "common.cuh"
+
+namespace m3g {
+
+namespace {
+
+constexpr int AD = 9;     // D = 3 x 3
+constexpr int AF = 64;    // feature width
+constexpr int ACAP = 96;  // member bonds per atom held in shared memory
+constexpr int AWARPS = 4;
+constexpr int ENT = 6;    // float4 per entry: [v.xyz, r] [c, b0..b2] [b3..b6] [b7, b8, eidx, -] [q0..q3] [q4..q7] + q8 in slot 3.w
+
+__device__ __constant__ float kY[3] = {0.28209479177387814f, 0.4886025119029199f, 0.6307831305050401f};
+
+__device__ __forceinline__ float silu_a(float z) { return __fdividef(z, 1.0f + __expf(-z)); }
+__device__ __forceinline__ float sigmoid_a(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
+
+// member bonds of one atom -> shared memory entries (geometry, cutoff, basis, optional per-bond 9-vector q)
+template <bool WITH_Q>
+__device__ __forceinline__ int stage_members(float4 (*ent)[ENT], int beg, int end, const float4* __restrict__ vec4,
+                                             const float* __restrict__ bas, const float* __restrict__ qsrc,
+                                             const int32_t* __restrict__ tri_ptr, float r3, int lane) {
+  int n3 = 0;
+  for (int base = beg; base < end; base += 32) {
+    const int e = base + lane;
+    bool m = false;
+    if (e < end) m = __ldg(tri_ptr + e + 1) > __ldg(tri_ptr + e);
+    const unsigned bal = __ballot_sync(FULL, m);
+    const int pos = n3 + __popc(bal & ((1u << lane) - 1u));
+    if (m && pos < ACAP) {
+      const float4 v = __ldg(vec4 + e);
+      const float* b = bas + (int64_t)e * AD;
+      float bb[AD];
+#pragma unroll
+      for (int d = 0; d < AD; ++d) bb[d] = __ldg(b + d);
+      ent[pos][0] = v;
+      ent[pos][1] = make_float4(cutoff_poly(v.w, r3), bb[0], bb[1], bb[2]);
+      ent[pos][2] = make_float4(bb[3], bb[4], bb[5], bb[6]);
+      float q8 = 0.0f;
+      if (WITH_Q) {
+        const float* q = qsrc + (int64_t)e * AD;
+        float qq[AD];
+#pragma unroll
+        for (int d = 0; d < AD; ++d) qq[d] = __ldg(q + d);
+        ent[pos][4] = make_float4(qq[0], qq[1], qq[2], qq[3]);
+        ent[pos][5] = make_float4(qq[4], qq[5], qq[6], qq[7]);
+        q8 = qq[8];
+      }
+      ent[pos][3] = make_float4(bb[7], bb[8], __int_as_float(e), q8);
+    }
+    n3 += __popc(bal);
+  }
+  __syncwarp();
+  return n3;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// forward: red (member bonds) and e_out = e_in + SiLU(red WdT) * sigmoid(red WgT) (all bonds)
+__global__ void __launch_bounds__(32 * AWARPS) tb_atom_fwd_kernel(
+    const float4* __restrict__ vec4, const float* __restrict__ bas, const int32_t* __restrict__ edge_ptr,
+    const int32_t* __restrict__ tri_ptr, float r3, const float* __restrict__ WdT, const float* __restrict__ WgT,
+    const float* __restrict__ e_in, int64_t N, float* __restrict__ red, float* __restrict__ e_out) {
+  __shared__ float4 ent_s[AWARPS][ACAP][ENT];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4(*ent)[ENT] = ent_s[warp];
+  // this lane's two feature columns of the 9 -> 64 gated MLP
+  float wd[AD][2], wg[AD][2];
+#pragma unroll
+  for (int d = 0; d < AD; ++d) {
+    wd[d][0] = __ldg(WdT + d * AF + 2 * lane); wd[d][1] = __ldg(WdT + d * AF + 2 * lane + 1);
+    wg[d][0] = __ldg(WgT + d * AF + 2 * lane); wg[d][1] = __ldg(WgT + d * AF + 2 * lane + 1);
+  }
+  for (int64_t atom = (int64_t)blockIdx.x * AWARPS + warp; atom < N; atom += (int64_t)gridDim.x * AWARPS) {
+    const int beg = __ldg(edge_ptr + atom), end = __ldg(edge_ptr + atom + 1);
+    const int n3 = stage_members<false>(ent, beg, end, vec4, bas, nullptr, tri_ptr, r3, lane);
+    // ---- pair matrix: bond j (one lane) sums its partners k ----
+    for (int j = lane; j < n3; j += 32) {
+      const float4 v1 = ent[j][0];
+      const float c1 = ent[j][1].x;
+      float acc[AD];
+#pragma unroll
+      for (int d = 0; d < AD; ++d) acc[d] = 0.0f;
+      for (int k = 0; k < n3; ++k) {
+        if (k == j) continue;
+        const float4 v2 = ent[k][0], p1 = ent[k][1], p2 = ent[k][2], p3 = ent[k][3];
+        const float dot = __fadd_rn(__fadd_rn(__fmul_rn(v1.x, v2.x), __fmul_rn(v1.y, v2.y)), __fmul_rn(v1.z, v2.z));
+        const float cs = fminf(fmaxf(__fdiv_rn(dot, __fmul_rn(v1.w, v2.w)), -1.0f), 1.0f);
+        const float y0 = kY[0], y1 = kY[1] * cs, y2 = kY[2] * ((3.0f * cs * cs - 1.0f) * 0.5f);
+        acc[0] += y0 * p1.y; acc[1] += y0 * p1.z; acc[2] += y0 * p1.w;
+        acc[3] += y1 * p2.x; acc[4] += y1 * p2.y; acc[5] += y1 * p2.z;
+        acc[6] += y2 * p2.w; acc[7] += y2 * p3.x; acc[8] += y2 * p3.y;
+      }
+#pragma unroll
+      for (int d = 0; d < AD; ++d) acc[d] *= c1;
+      const int e1 = __float_as_int(ent[j][3].z);
+      float* ro = red + (int64_t)e1 * AD;
+#pragma unroll
+      for (int d = 0; d < AD; ++d) ro[d] = acc[d];
+      ent[j][4] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      ent[j][5] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      ent[j][3].w = acc[8];
+    }
+    __syncwarp();
+    // ---- edge rows: 4 rows per pass (loads first), lane owns features 2*lane, 2*lane+1 ----
+    int pos = 0;
+    for (int e0 = beg; e0 < end; e0 += 4) {
+      float2 row[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (e0 + i < end) row[i] = __ldg(reinterpret_cast<const float2*>(e_in + (int64_t)(e0 + i) * AF) + lane);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e = e0 + i;
+        if (e >= end) break;
+        if (pos < n3 && __float_as_int(ent[pos][3].z) == e) {
+          const float4 q0 = ent[pos][4], q1 = ent[pos][5];
+          const float rd[AD] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, ent[pos][3].w};
+          float u0 = 0.f, u1 = 0.f, g0 = 0.f, g1 = 0.f;
+#pragma unroll
+          for (int d = 0; d < AD; ++d) {
+            u0 += rd[d] * wd[d][0]; u1 += rd[d] * wd[d][1];
+            g0 += rd[d] * wg[d][0]; g1 += rd[d] * wg[d][1];
+          }
+          row[i].x += silu_a(u0) * sigmoid_a(g0);
+          row[i].y += silu_a(u1) * sigmoid_a(g1);
+          ++pos;
+        }
+        reinterpret_cast<float2*>(e_out + (int64_t)e * AF)[lane] = row[i];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: g_red (member bonds, internal), g_vec4 (E,4) = d/d(v, r), g_bas (E,9); zeros for non-member bonds
+__global__ void __launch_bounds__(32 * AWARPS) tb_atom_bwd_kernel(
+    const float4* __restrict__ vec4, const float* __restrict__ bas, const float* __restrict__ red,
+    const float* __restrict__ g_e, const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ tri_ptr, float r3,
+    const float* __restrict__ WdT, const float* __restrict__ WgT, int64_t N, float4* __restrict__ g_vec4,
+    float* __restrict__ g_bas) {
+  __shared__ float4 ent_s[AWARPS][ACAP][ENT];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4(*ent)[ENT] = ent_s[warp];
+  float wd[AD][2], wg[AD][2];
+#pragma unroll
+  for (int d = 0; d < AD; ++d) {
+    wd[d][0] = __ldg(WdT + d * AF + 2 * lane); wd[d][1] = __ldg(WdT + d * AF + 2 * lane + 1);
+    wg[d][0] = __ldg(WgT + d * AF + 2 * lane); wg[d][1] = __ldg(WgT + d * AF + 2 * lane + 1);
+  }
+  for (int64_t atom = (int64_t)blockIdx.x * AWARPS + warp; atom < N; atom += (int64_t)gridDim.x * AWARPS) {
+    const int beg = __ldg(edge_ptr + atom), end = __ldg(edge_ptr + atom + 1);
+    // non-member bonds carry no three-body term: zero gradients
+    for (int e = beg + lane; e < end; e += 32) {
+      if (!(__ldg(tri_ptr + e + 1) > __ldg(tri_ptr + e))) {
+        g_vec4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* gb = g_bas + (int64_t)e * AD;
+#pragma unroll
+        for (int d = 0; d < AD; ++d) gb[d] = 0.0f;
+      }
+    }
+    const int n3 = stage_members<true>(ent, beg, end, vec4, bas, red, tri_ptr, r3, lane);  // q = red
+    // ---- gated-MLP adjoint: q <- g_red ; lane owns features 2*lane, 2*lane+1 ; 2 bonds per pass ----
+    for (int p0 = 0; p0 < n3; p0 += 2) {
+      float2 ge[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        if (p0 + i < n3)
+          ge[i] = __ldg(reinterpret_cast<const float2*>(g_e + (int64_t)__float_as_int(ent[p0 + i][3].z) * AF) + lane);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int pos = p0 + i;
+        if (pos >= n3) break;
+        const float4 q0 = ent[pos][4], q1 = ent[pos][5];
+        const float rd[AD] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, ent[pos][3].w};
+        float u0 = 0.f, u1 = 0.f, g0 = 0.f, g1 = 0.f;
+#pragma unroll
+        for (int d = 0; d < AD; ++d) {
+          u0 += rd[d] * wd[d][0]; u1 += rd[d] * wd[d][1];
+          g0 += rd[d] * wg[d][0]; g1 += rd[d] * wg[d][1];
+        }
+        const float sg0 = sigmoid_a(g0), sg1 = sigmoid_a(g1), su0 = sigmoid_a(u0), su1 = sigmoid_a(u1);
+        const float du0 = ge[i].x * sg0 * su0 * (1.0f + u0 * (1.0f - su0));
+        const float du1 = ge[i].y * sg1 * su1 * (1.0f + u1 * (1.0f - su1));
+        const float dg0 = ge[i].x * (u0 * su0) * sg0 * (1.0f - sg0);
+        const float dg1 = ge[i].y * (u1 * su1) * sg1 * (1.0f - sg1);
+        float part[AD];
+#pragma unroll
+        for (int d = 0; d < AD; ++d)
+          part[d] = (du0 * wd[d][0] + du1 * wd[d][1]) + (dg0 * wg[d][0] + dg1 * wg[d][1]);
+#pragma unroll
+        for (int d = 0; d < AD; ++d) part[d] = warp_sum(part[d]);
+        __syncwarp();
+        if (lane == 0) {
+          ent[pos][4] = make_float4(part[0], part[1], part[2], part[3]);
+          ent[pos][5] = make_float4(part[4], part[5], part[6], part[7]);
+          ent[pos][3].w = part[8];
+        }
+      }
+    }
+    __syncwarp();
+    // ---- pair matrix, both roles of bond j in one sweep over its partners k ----
+    for (int j = lane; j < n3; j += 32) {
+      const float4 ve = ent[j][0];
+      const float4 e1 = ent[j][1], e2 = ent[j][2], e3 = ent[j][3], d0 = ent[j][4], d4 = ent[j][5];
+      const float ce = e1.x;
+      const float be[AD] = {e1.y, e1.z, e1.w, e2.x, e2.y, e2.z, e2.w, e3.x, e3.y};
+      const float d1[AD] = {d0.x, d0.y, d0.z, d0.w, d4.x, d4.y, d4.z, d4.w, e3.w};
+      float gB[AD];
+#pragma unroll
+      for (int d = 0; d < AD; ++d) gB[d] = 0.0f;
+      float gx = 0.f, gy = 0.f, gz = 0.f, gr = 0.f, gc = 0.f;
+      for (int k = 0; k < n3; ++k) {
+        if (k == j) continue;
+        const float4 vp = ent[k][0], p1 = ent[k][1], p2 = ent[k][2], p3 = ent[k][3], q0 = ent[k][4], q4 = ent[k][5];
+        const float cp = p1.x;
+        const float b[AD] = {p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w, p3.x, p3.y};
+        const float q[AD] = {q0.x, q0.y, q0.z, q0.w, q4.x, q4.y, q4.z, q4.w, p3.w};
+        const float inv = 1.0f / (ve.w * vp.w);
+        const float craw = (ve.x * vp.x + ve.y * vp.y + ve.z * vp.z) * inv;
+        const bool inside = (craw >= -1.0f) && (craw <= 1.0f);
+        const float cs = fminf(fmaxf(craw, -1.0f), 1.0f);
+        const float y0 = kY[0], y1 = kY[1] * cs, y2 = kY[2] * ((3.0f * cs * cs - 1.0f) * 0.5f);
+        // j as first bond of (j, k)
+        const float s0 = b[0] * d1[0] + b[1] * d1[1] + b[2] * d1[2];
+        const float s1 = b[3] * d1[3] + b[4] * d1[4] + b[5] * d1[5];
+        const float s2 = b[6] * d1[6] + b[7] * d1[7] + b[8] * d1[8];
+        gc += y0 * s0 + y1 * s1 + y2 * s2;
+        // j as second bond of (k, j)
+        const float w0 = y0 * cp, w1 = y1 * cp, w2 = y2 * cp;
+        gB[0] += w0 * q[0]; gB[1] += w0 * q[1]; gB[2] += w0 * q[2];
+        gB[3] += w1 * q[3]; gB[4] += w1 * q[4]; gB[5] += w1 * q[5];
+        gB[6] += w2 * q[6]; gB[7] += w2 * q[7]; gB[8] += w2 * q[8];
+        const float t1 = be[3] * q[3] + be[4] * q[4] + be[5] * q[5];
+        const float t2 = be[6] * q[6] + be[7] * q[7] + be[8] * q[8];
+        // Legendre backward with the reference's per-level grad_output (quirk Q3): l=1: go; l=2: go*(2x + x*go)
+        const float goA1 = kY[1] * ce * s1, goA2 = kY[2] * ce * s2;
+        const float goB1 = kY[1] * cp * t1, goB2 = kY[2] * cp * t2;
+        const float gcos = goA1 + goA2 * (2.0f * cs + cs * goA2) + goB1 + goB2 * (2.0f * cs + cs * goB2);
+        if (inside) {
+          const float w = gcos * inv;
+          gx += w * vp.x; gy += w * vp.y; gz += w * vp.z;
+          gr -= gcos * craw / ve.w;
+        }
+      }
+      gr += gc * cutoff_poly_grad(ve.w, r3);
+      const int e = __float_as_int(e3.z);
+      g_vec4[e] = make_float4(gx, gy, gz, gr);
+      float* gb = g_bas + (int64_t)e * AD;
+#pragma unroll
+      for (int d = 0; d < AD; ++d) gb[d] = gB[d];
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout certificate: for every atom, the rows of its member bonds (non-empty triplet rows) are exactly "all other
+// member bonds of the same atom, ascending".  flags[0] = 1 if so, flags[1] = max member count of an atom.
+__global__ void tri_dense_check_kernel(const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ tri_ptr,
+                                       const int32_t* __restrict__ tri_e2, int64_t N, int32_t* __restrict__ flags) {
+  const int64_t atom = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (atom >= N) return;
+  const int beg = edge_ptr[atom], end = edge_ptr[atom + 1];
+  int n3 = 0;
+  for (int e = beg; e < end; ++e) n3 += (tri_ptr[e + 1] > tri_ptr[e]);
+  bool ok = true;
+  for (int e1 = beg; e1 < end && ok; ++e1) {
+    const int rb = tri_ptr[e1], re = tri_ptr[e1 + 1];
+    if (re == rb) continue;
+    if (re - rb != n3 - 1) { ok = false; break; }
+    int p = rb;
+    for (int e2 = beg; e2 < end; ++e2) {
+      if (e2 == e1 || !(tri_ptr[e2 + 1] > tri_ptr[e2])) continue;
+      if (tri_e2[p] != e2) { ok = false; break; }
+      ++p;
+    }
+  }
+  if (!ok) atomicExch(&flags[0], 0);
+  atomicMax(&flags[1], n3);
+}
+
+__global__ void tri_dense_init_kernel(int32_t* flags) { flags[0] = 1; flags[1] = 0; }
+
+}  // namespace m3g
+
+using namespace m3g;
+
+extern "C" {
+
+int m3g_tri_dense_check(const int32_t* edge_ptr, const int32_t* tri_ptr, const int32_t* tri_e2, int64_t N,
+                        int32_t* flags, void* stream) {
+  M3G_REQUIRE(edge_ptr && tri_ptr && flags, "m3g_tri_dense_check: null pointer");
+  tri_dense_init_kernel<<<1, 1, 0, as_stream(stream)>>>(flags);
+  if (N > 0)
+    tri_dense_check_kernel<<<blocks_for(N, 128), 128, 0, as_stream(stream)>>>(edge_ptr, tri_ptr, tri_e2, N, flags);
+  M3G_LAUNCH_CHECK("m3g_tri_dense_check");
+  return M3G_OK;
+}
+
+int m3g_tb_atom_capacity(void) { return ACAP; }
+
+static inline unsigned atom_grid(int64_t N, int n_sm) {
+  int64_t need = (N + AWARPS - 1) / AWARPS;
+  int64_t cap = (int64_t)n_sm * 4;  // 36 KB of shared memory per block
+  return (unsigned)((need < cap) ? (need < 1 ? 1 : need) : cap);
+}
+
+int m3g_tb_atom_fwd(const float* vec4, const float* bas, const int32_t* edge_ptr, const int32_t* tri_ptr, float r3,
+                    const float* WdT, const float* WgT, const float* e_in, int64_t N, int n_sm, float* red,
+                    float* e_out, void* stream) {
+  if (N == 0) return M3G_OK;
+  M3G_REQUIRE(vec4 && bas && edge_ptr && tri_ptr && WdT && WgT && e_in && red && e_out,
+              "m3g_tb_atom_fwd: null pointer");
+  tb_atom_fwd_kernel<<<atom_grid(N, n_sm), 32 * AWARPS, 0, as_stream(stream)>>>(
+      (const float4*)vec4, bas, edge_ptr, tri_ptr, r3, WdT, WgT, e_in, N, red, e_out);
+  M3G_LAUNCH_CHECK("m3g_tb_atom_fwd");
+  return M3G_OK;
+}
+
+int m3g_tb_atom_bwd(const float* vec4, const float* bas, const float* red, const float* g_e, const int32_t* edge_ptr,
+                    const int32_t* tri_ptr, float r3, const float* WdT, const float* WgT, int64_t N, int n_sm,
+                    float* g_vec4, float* g_bas, void* stream) {
+  if (N == 0) return M3G_OK;
+  M3G_REQUIRE(vec4 && bas && red && g_e && edge_ptr && tri_ptr && WdT && WgT && g_vec4 && g_bas,
+              "m3g_tb_atom_bwd: null pointer");
+  tb_atom_bwd_kernel<<<atom_grid(N, n_sm), 32 * AWARPS, 0, as_stream(stream)>>>(
+      (const float4*)vec4, bas, red, g_e, edge_ptr, tri_ptr, r3, WdT, WgT, N, (float4*)g_vec4, g_bas);
+  M3G_LAUNCH_CHECK("m3g_tb_atom_bwd");
+  return M3G_OK;
+}
+
+}  // extern "C"

@@ -313,6 +313,11 @@ class GraphPlan:
     def _pick_group(self):
         avg = self.T / max(self.E, 1)
         self.tri_group = 8 if avg <= 12 else (16 if avg <= 28 else 32)
+        # canonical per-atom layout (full off-diagonal of the member-bond pair matrix)?  -> per-atom kernels
+        flags = torch.empty(2, dtype=torch.int32, device=self.device)
+        _lib.call("tri_dense_check", self.edge_ptr, self.tri_ptr, self.tri_e2, self.N, flags)
+        dense, self.max_members = flags.tolist()
+        self.tri_dense = bool(dense) and self.max_members <= _lib.tb_atom_capacity()
 
     @classmethod
     def build(cls, g: MaterialGraph) -> "GraphPlan":

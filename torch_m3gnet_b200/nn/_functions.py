@@ -163,14 +163,18 @@ class ThreeBodyFn(Function):
         call("tb_edge_basis_fwd", vec4, plan.dst, sig, w["consts"], E, L, R, bas)
         red = _empty((E, D), x)
         e_out = torch.empty_like(e)
-        fast = (L, R, F) == (3, 3, 64) and tb_path() == "fast"
-        if fast:
+        fast = (L, R, F) == (3, 3, 64) and tb_path() in ("fast", "atom")
+        atom = fast and tb_path() == "atom" and plan.tri_dense
+        if atom:
+            call("tb_atom_fwd", vec4, bas, plan.edge_ptr, plan.tri_ptr, w["r3"], w["WdT"], w["WgT"], e, plan.N,
+                 sm_count(x.device), red, e_out)
+        elif fast:
             call("tb_reduce_fwd_fast", vec4, bas, plan.tri_ptr, plan.tri_e2, w["r3"], w["WdT"], w["WgT"], e, E,
                  plan.tri_group, sm_count(x.device), red, e_out)
         else:
             call("tb_reduce_fwd", vec4, bas, plan.tri_ptr, plan.tri_e2, w["consts"], w["WdT"], w["WgT"], e, E, L, R, F,
                  plan.tri_group, red, e_out)
-        ctx.plan, ctx.w, ctx.L, ctx.R, ctx.F, ctx.fast = plan, w, L, R, F, fast
+        ctx.plan, ctx.w, ctx.L, ctx.R, ctx.F, ctx.fast, ctx.atom = plan, w, L, R, F, fast, atom
         ctx.save_for_backward(vec4, sig, bas, red)
         return e_out
 
@@ -183,12 +187,17 @@ class ThreeBodyFn(Function):
         g_red = torch.empty_like(red)
         g_vec4 = torch.empty_like(vec4)
         g_bas = torch.empty_like(bas)
-        if ctx.fast:
+        if ctx.atom:
+            call("tb_atom_bwd", vec4, bas, red, g_e, plan.edge_ptr, plan.tri_ptr, w["r3"], w["WdT"], w["WgT"], N,
+                 sm_count(vec4.device), g_vec4, g_bas)
+        elif ctx.fast:
             n_sm = sm_count(vec4.device)
             call("tb_gate_bwd_fast", red, g_e, w["WdT"], w["WgT"], plan.tri_ptr, E, n_sm, g_red)
         else:
             call("tb_gate_bwd", red, g_e, w["WdT"], w["WgT"], plan.tri_ptr, E, D, F, g_red)
-        if ctx.fast and plan.tri_symmetric:
+        if ctx.atom:
+            pass
+        elif ctx.fast and plan.tri_symmetric:
             call("tb_reduce_bwd_sym", vec4, bas, g_red, plan.tri_ptr, plan.tri_e2, w["r3"], E, plan.tri_group, n_sm,
                  g_vec4, g_bas)
         else:

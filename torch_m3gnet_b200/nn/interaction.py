@@ -14,7 +14,7 @@ from torch_m3gnet_b200.nn.core import GatedMLP
 from torch_m3gnet_b200.nn.invariant import PAIR_VEC4
 
 # "fast": specialised kernels for (l_max, n_max, F) = (3, 3, 64); "generic": the width-agnostic kernels everywhere
-TB_PATH = os.environ.get("M3G_TB_PATH", "fast")
+TB_PATH = os.environ.get("M3G_TB_PATH", "atom")
 
 __all__ = ["ThreeBodyInteration", "NormalizedSphericalBessel", "SPHERICAL_BESSEL_ZEROS", "spherical_bessel",
            "legendre_cos", "cutoff_function"]
