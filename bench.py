@@ -136,9 +136,9 @@ def kernel_model(E, T, N, F=64, R=3, D=9):
     single["conv_tc_fwd"] = single["conv_mlp_fwd"]
     single["conv_tc_bwd"] = single["conv_mlp_bwd"]
     groups = {
-        "threebody_fwd": (("tb_sigma_fwd", "tb_edge_basis_fwd", "tb_reduce_fwd", "tb_reduce_fwd_fast"),
+        "threebody_fwd": (("tb_sigma_fwd", "tb_edge_basis_fwd", "tb_reduce_fwd", "tb_reduce_fwd_fast", "tb_atom_fwd"),
                           "hbm", 4 * T + 536 * E + 36 * N),
-        "threebody_bwd": (("tb_gate_bwd", "tb_gate_bwd_fast", "tb_reduce_bwd", "tb_reduce_bwd_sym",
+        "threebody_bwd": (("tb_gate_bwd", "tb_gate_bwd_fast", "tb_reduce_bwd", "tb_reduce_bwd_sym", "tb_atom_bwd",
                            "tb_edge_basis_bwd", "tb_sigma_bwd"), "hbm", 4 * T + 332 * E + 72 * N),
     }
     return single, groups

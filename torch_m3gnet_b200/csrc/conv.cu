@@ -73,6 +73,90 @@ __global__ void linear_kernel(const float* __restrict__ in, const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Shared-memory tiled fp32 GEMM for the per-atom projections: out (n,M) = base + in (n,K) Wt (K,M) + bias, with
+// K % 32 == 0 and M % 64 == 0.  Block tile BM x 64, K chunks of 32 staged in shared memory (A transposed so that
+// both operands are read as float4), thread tile (BM/16) x 4, k ascending per output (deterministic order).
+template <int BM>
+__global__ void __launch_bounds__(256) linear_tiled_kernel(const float* __restrict__ in, const float* __restrict__ Wt,
+                                                           const float* __restrict__ bias,
+                                                           const float* __restrict__ base, int64_t n, int K, int M,
+                                                           float* __restrict__ out) {
+  constexpr int BN = 64, BK = 32, TM = BM / 16;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;  // 16 column groups x 16 row groups
+  const int64_t row0 = (int64_t)blockIdx.x * BM;
+  const int col0 = blockIdx.y * BN;
+  float acc[TM][4];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    // A chunk (BM x 32): each thread loads float4 along k and stores it transposed
+#pragma unroll
+    for (int i = 0; i < BM / 32; ++i) {
+      int idx = tid + 256 * i;
+      int r = idx >> 3, c4 = idx & 7;
+      int64_t row = min(row0 + r, n - 1);
+      float4 v = __ldg(reinterpret_cast<const float4*>(in + row * K + k0) + c4);
+      As[4 * c4 + 0][r] = v.x; As[4 * c4 + 1][r] = v.y; As[4 * c4 + 2][r] = v.z; As[4 * c4 + 3][r] = v.w;
+    }
+    // B chunk (32 x 64)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      int idx = tid + 256 * i;
+      int r = idx >> 4, c4 = idx & 15;
+      *reinterpret_cast<float4*>(&Bs[r][4 * c4]) =
+          __ldg(reinterpret_cast<const float4*>(Wt + (int64_t)(k0 + r) * M + col0) + c4);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[TM];
+#pragma unroll
+      for (int i = 0; i < TM; i += 4) {
+        float4 t = *reinterpret_cast<const float4*>(&As[k][TM * ty + i]);
+        a[i] = t.x; a[i + 1] = t.y; a[i + 2] = t.z; a[i + 3] = t.w;
+      }
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][4 * tx]);
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        acc[i][0] += a[i] * b.x; acc[i][1] += a[i] * b.y; acc[i][2] += a[i] * b.z; acc[i][3] += a[i] * b.w;
+      }
+    }
+    __syncthreads();
+  }
+  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + col0) + tx);
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int64_t row = row0 + TM * ty + i;
+    if (row >= n) continue;
+    float4 r4 = make_float4(acc[i][0] + bv.x, acc[i][1] + bv.y, acc[i][2] + bv.z, acc[i][3] + bv.w);
+    if (base) {
+      float4 b4 = __ldg(reinterpret_cast<const float4*>(base + row * M + col0) + tx);
+      r4.x += b4.x; r4.y += b4.y; r4.z += b4.z; r4.w += b4.w;
+    }
+    reinterpret_cast<float4*>(out + row * M + col0)[tx] = r4;
+  }
+}
+
+static inline bool launch_linear_tiled(const float* in, const float* Wt, const float* bias, const float* base,
+                                       int64_t n, int K, int M, float* out, cudaStream_t stream) {
+  if (K % 32 != 0 || M % 64 != 0) return false;
+  if (M >= 256) {
+    dim3 grid((unsigned)((n + 127) / 128), (unsigned)(M / 64));
+    linear_tiled_kernel<128><<<grid, 256, 0, stream>>>(in, Wt, bias, base, n, K, M, out);
+  } else {
+    dim3 grid((unsigned)((n + 63) / 64), (unsigned)(M / 64));
+    linear_tiled_kernel<64><<<grid, 256, 0, stream>>>(in, Wt, bias, base, n, K, M, out);
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // forward of one gated MLP on edges
 template <int NJ>
 __global__ void conv_mlp_fwd_kernel(const float* __restrict__ P, int ldp, int po, const int32_t* __restrict__ src,
@@ -356,8 +440,9 @@ int m3g_linear_fwd(const float* in, const float* Wt, const float* bias, int64_t 
                    void* stream) {
   if (n == 0) return M3G_OK;
   M3G_REQUIRE(in && Wt && out && K > 0 && M > 0, "m3g_linear_fwd: bad argument");
-  linear_kernel<<<blocks_for(n, WARPS_PER_BLOCK * EPW), WARPS_PER_BLOCK * 32, 0, as_stream(stream)>>>(
-      in, Wt, bias, nullptr, n, K, M, out);
+  if (!launch_linear_tiled(in, Wt, bias, nullptr, n, K, M, out, as_stream(stream)))
+    linear_kernel<<<blocks_for(n, WARPS_PER_BLOCK * EPW), WARPS_PER_BLOCK * 32, 0, as_stream(stream)>>>(
+        in, Wt, bias, nullptr, n, K, M, out);
   M3G_LAUNCH_CHECK("m3g_linear_fwd");
   return M3G_OK;
 }
@@ -367,8 +452,9 @@ int m3g_linear_bwd_input(const float* g, const float* W, const float* base, int6
   if (n == 0) return M3G_OK;
   M3G_REQUIRE(g && W && out && K > 0 && M > 0, "m3g_linear_bwd_input: bad argument");
   // out (n,K) = base + g (n,M) · W (M,K): the same kernel with the roles of K and M exchanged
-  linear_kernel<<<blocks_for(n, WARPS_PER_BLOCK * EPW), WARPS_PER_BLOCK * 32, 0, as_stream(stream)>>>(
-      g, W, nullptr, base, n, M, K, out);
+  if (!launch_linear_tiled(g, W, nullptr, base, n, M, K, out, as_stream(stream)))
+    linear_kernel<<<blocks_for(n, WARPS_PER_BLOCK * EPW), WARPS_PER_BLOCK * 32, 0, as_stream(stream)>>>(
+        g, W, nullptr, base, n, M, K, out);
   M3G_LAUNCH_CHECK("m3g_linear_bwd_input");
   return M3G_OK;
 }

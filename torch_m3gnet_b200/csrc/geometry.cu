@@ -187,6 +187,27 @@ __global__ void edge_adjust_fwd_kernel(const float* __restrict__ h, const float*
   e0[idx] = silu_acc(z);
 }
 
+// F % 4 == 0: one thread per 4 consecutive features (float4 stores, the h row is a broadcast inside the row's threads)
+template <int RC>
+__global__ void edge_adjust_fwd4_kernel(const float* __restrict__ h, const float* __restrict__ Wt, int64_t E, int R,
+                                        int F, float* __restrict__ e0) {
+  const int F4 = F >> 2;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= E * F4) return;
+  int64_t e = idx / F4;
+  int f = 4 * (int)(idx - e * F4);
+  float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int m = 0; m < RC; ++m) {
+    if (m < R) {
+      float hv = __ldg(h + e * R + m);
+      float4 w = __ldg(reinterpret_cast<const float4*>(Wt + m * F + f));
+      z.x += hv * w.x; z.y += hv * w.y; z.z += hv * w.z; z.w += hv * w.w;
+    }
+  }
+  reinterpret_cast<float4*>(e0 + e * F)[f >> 2] = make_float4(silu_acc(z.x), silu_acc(z.y), silu_acc(z.z), silu_acc(z.w));
+}
+
 // one warp per edge
 __global__ void edge_adjust_bwd_kernel(const float* __restrict__ h, const float* __restrict__ Wt,
                                        const float* __restrict__ g_e0, int64_t E, int R, int F,
@@ -211,6 +232,35 @@ __global__ void edge_adjust_bwd_kernel(const float* __restrict__ h, const float*
       float s = warp_sum(acc[m]);
       if (lane == 0) g_h[e * R + m] = s;
     }
+  }
+}
+
+// F == 64, R <= 4: 16 lanes per edge, one float4 of the upstream row per lane, butterfly over the 16 lanes
+template <int RC>
+__global__ void edge_adjust_bwd64_kernel(const float* __restrict__ h, const float* __restrict__ Wt,
+                                         const float* __restrict__ g_e0, int64_t E, int R, float* __restrict__ g_h) {
+  constexpr int F = 64;
+  int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const int gl = threadIdx.x & 15;
+  const bool valid = e < E;
+  const int64_t ec = valid ? e : (E - 1);
+  float hv[RC];
+  float4 w[RC];
+#pragma unroll
+  for (int m = 0; m < RC; ++m) {
+    hv[m] = (m < R) ? __ldg(h + ec * R + m) : 0.0f;
+    w[m] = (m < R) ? __ldg(reinterpret_cast<const float4*>(Wt + m * F) + gl) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float4 g = __ldg(reinterpret_cast<const float4*>(g_e0 + ec * F) + gl);
+  float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int m = 0; m < RC; ++m) { z.x += hv[m] * w[m].x; z.y += hv[m] * w[m].y; z.z += hv[m] * w[m].z; z.w += hv[m] * w[m].w; }
+  const float gx = g.x * silu_grad(z.x), gy = g.y * silu_grad(z.y), gz = g.z * silu_grad(z.z), gw = g.w * silu_grad(z.w);
+#pragma unroll
+  for (int m = 0; m < RC; ++m) {
+    float a = ((gx * w[m].x + gy * w[m].y) + gz * w[m].z) + gw * w[m].w;
+    a = group_sum<16>(a);
+    if (valid && gl == 0 && m < R) g_h[e * R + m] = a;
   }
 }
 
@@ -343,7 +393,10 @@ int m3g_embed_fwd(const float* weight, const int32_t* types, int64_t N, int F, i
 int m3g_edge_adjust_fwd(const float* h, const float* Wt, int64_t E, int R, int F, float* e0, void* stream) {
   if (E == 0) return M3G_OK;
   M3G_REQUIRE(h && Wt && e0, "m3g_edge_adjust_fwd: null pointer");
-  edge_adjust_fwd_kernel<<<blocks_for(E * F, 256), 256, 0, as_stream(stream)>>>(h, Wt, E, R, F, e0);
+  if (F % 4 == 0 && R <= 4)
+    edge_adjust_fwd4_kernel<4><<<blocks_for(E * (F / 4), 256), 256, 0, as_stream(stream)>>>(h, Wt, E, R, F, e0);
+  else
+    edge_adjust_fwd_kernel<<<blocks_for(E * F, 256), 256, 0, as_stream(stream)>>>(h, Wt, E, R, F, e0);
   M3G_LAUNCH_CHECK("m3g_edge_adjust_fwd");
   return M3G_OK;
 }
@@ -353,7 +406,10 @@ int m3g_edge_adjust_bwd(const float* h, const float* Wt, const float* g_e0, int6
   if (E == 0) return M3G_OK;
   M3G_REQUIRE(h && Wt && g_e0 && g_h, "m3g_edge_adjust_bwd: null pointer");
   M3G_REQUIRE(R >= 1 && R <= M3G_MAX_RADIAL, "m3g_edge_adjust_bwd: n_max=%d outside [1,%d]", R, M3G_MAX_RADIAL);
-  edge_adjust_bwd_kernel<<<blocks_for(E * 32, 256), 256, 0, as_stream(stream)>>>(h, Wt, g_e0, E, R, F, g_h);
+  if (F == 64 && R <= 4)
+    edge_adjust_bwd64_kernel<4><<<blocks_for(E * 16, 256), 256, 0, as_stream(stream)>>>(h, Wt, g_e0, E, R, g_h);
+  else
+    edge_adjust_bwd_kernel<<<blocks_for(E * 32, 256), 256, 0, as_stream(stream)>>>(h, Wt, g_e0, E, R, F, g_h);
   M3G_LAUNCH_CHECK("m3g_edge_adjust_bwd");
   return M3G_OK;
 }

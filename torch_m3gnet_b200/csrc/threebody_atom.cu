@@ -86,6 +86,15 @@ __global__ void __launch_bounds__(32 * AWARPS) tb_atom_fwd_kernel(
   }
   for (int64_t atom = (int64_t)blockIdx.x * AWARPS + warp; atom < N; atom += (int64_t)gridDim.x * AWARPS) {
     const int beg = __ldg(edge_ptr + atom), end = __ldg(edge_ptr + atom + 1);
+    constexpr int RB = 8;
+    float2 ra[RB], rb[RB];
+    auto load_rows = [&](float2* row, int e0) {
+#pragma unroll
+      for (int i = 0; i < RB; ++i)
+        if (e0 + i < end) row[i] = __ldg(reinterpret_cast<const float2*>(e_in + (int64_t)(e0 + i) * AF) + lane);
+    };
+    load_rows(ra, beg);
+    load_rows(rb, beg + RB);
     const int n3 = stage_members<false>(ent, beg, end, vec4, bas, nullptr, tri_ptr, r3, lane);
     // ---- pair matrix: bond j (one lane) sums its partners k ----
     for (int j = lane; j < n3; j += 32) {
@@ -115,15 +124,12 @@ __global__ void __launch_bounds__(32 * AWARPS) tb_atom_fwd_kernel(
       ent[j][3].w = acc[8];
     }
     __syncwarp();
-    // ---- edge rows: 4 rows per pass (loads first), lane owns features 2*lane, 2*lane+1 ----
+    // ---- edge rows, lane owns features 2*lane, 2*lane+1; two register buffers of RB rows: one is processed while
+    //      the other is in flight (the first two were requested before the pair phase) ----
     int pos = 0;
-    for (int e0 = beg; e0 < end; e0 += 4) {
-      float2 row[4];
+    auto process_rows = [&](float2* row, int e0) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (e0 + i < end) row[i] = __ldg(reinterpret_cast<const float2*>(e_in + (int64_t)(e0 + i) * AF) + lane);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < RB; ++i) {
         const int e = e0 + i;
         if (e >= end) break;
         if (pos < n3 && __float_as_int(ent[pos][3].z) == e) {
@@ -141,6 +147,12 @@ __global__ void __launch_bounds__(32 * AWARPS) tb_atom_fwd_kernel(
         }
         reinterpret_cast<float2*>(e_out + (int64_t)e * AF)[lane] = row[i];
       }
+    };
+    for (int e0 = beg; e0 < end; e0 += 2 * RB) {
+      process_rows(ra, e0);
+      load_rows(ra, e0 + 2 * RB);
+      process_rows(rb, e0 + RB);
+      load_rows(rb, e0 + 3 * RB);
     }
     __syncwarp();
   }
@@ -174,15 +186,19 @@ __global__ void __launch_bounds__(32 * AWARPS) tb_atom_bwd_kernel(
       }
     }
     const int n3 = stage_members<true>(ent, beg, end, vec4, bas, red, tri_ptr, r3, lane);  // q = red
-    // ---- gated-MLP adjoint: q <- g_red ; lane owns features 2*lane, 2*lane+1 ; 2 bonds per pass ----
-    for (int p0 = 0; p0 < n3; p0 += 2) {
-      float2 ge[2];
+    // ---- gated-MLP adjoint: q <- g_red ; lane owns features 2*lane, 2*lane+1 ; two register buffers of GB upstream
+    //      rows: one is processed while the other is in flight ----
+    constexpr int GB = 4;
+    float2 ga[GB], gb2[GB];
+    auto load_g = [&](float2* ge, int p0) {
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+      for (int i = 0; i < GB; ++i)
         if (p0 + i < n3)
           ge[i] = __ldg(reinterpret_cast<const float2*>(g_e + (int64_t)__float_as_int(ent[p0 + i][3].z) * AF) + lane);
+    };
+    auto process_g = [&](const float2* ge, int p0) {
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < GB; ++i) {
         const int pos = p0 + i;
         if (pos >= n3) break;
         const float4 q0 = ent[pos][4], q1 = ent[pos][5];
@@ -211,6 +227,14 @@ __global__ void __launch_bounds__(32 * AWARPS) tb_atom_bwd_kernel(
           ent[pos][3].w = part[8];
         }
       }
+    };
+    load_g(ga, 0);
+    load_g(gb2, GB);
+    for (int p0 = 0; p0 < n3; p0 += 2 * GB) {
+      process_g(ga, p0);
+      load_g(ga, p0 + 2 * GB);
+      process_g(gb2, p0 + GB);
+      load_g(gb2, p0 + 3 * GB);
     }
     __syncwarp();
     // ---- pair matrix, both roles of bond j in one sweep over its partners k ----
@@ -300,6 +324,17 @@ __global__ void tri_dense_init_kernel(int32_t* flags) { flags[0] = 1; flags[1] =
 
 using namespace m3g;
 
+// persistent grid = exactly the resident capacity (a partial second wave would leave most SMs idle in the tail)
+template <typename Kernel>
+static inline unsigned atom_grid(Kernel kernel, int64_t N, int n_sm) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * AWARPS, 0) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  int64_t need = (N + AWARPS - 1) / AWARPS;
+  int64_t cap = (int64_t)n_sm * per_sm;
+  return (unsigned)((need < cap) ? (need < 1 ? 1 : need) : cap);
+}
+
 extern "C" {
 
 int m3g_tri_dense_check(const int32_t* edge_ptr, const int32_t* tri_ptr, const int32_t* tri_e2, int64_t N,
@@ -314,19 +349,13 @@ int m3g_tri_dense_check(const int32_t* edge_ptr, const int32_t* tri_ptr, const i
 
 int m3g_tb_atom_capacity(void) { return ACAP; }
 
-static inline unsigned atom_grid(int64_t N, int n_sm) {
-  int64_t need = (N + AWARPS - 1) / AWARPS;
-  int64_t cap = (int64_t)n_sm * 4;  // 36 KB of shared memory per block
-  return (unsigned)((need < cap) ? (need < 1 ? 1 : need) : cap);
-}
-
 int m3g_tb_atom_fwd(const float* vec4, const float* bas, const int32_t* edge_ptr, const int32_t* tri_ptr, float r3,
                     const float* WdT, const float* WgT, const float* e_in, int64_t N, int n_sm, float* red,
                     float* e_out, void* stream) {
   if (N == 0) return M3G_OK;
   M3G_REQUIRE(vec4 && bas && edge_ptr && tri_ptr && WdT && WgT && e_in && red && e_out,
               "m3g_tb_atom_fwd: null pointer");
-  tb_atom_fwd_kernel<<<atom_grid(N, n_sm), 32 * AWARPS, 0, as_stream(stream)>>>(
+  tb_atom_fwd_kernel<<<atom_grid(tb_atom_fwd_kernel, N, n_sm), 32 * AWARPS, 0, as_stream(stream)>>>(
       (const float4*)vec4, bas, edge_ptr, tri_ptr, r3, WdT, WgT, e_in, N, red, e_out);
   M3G_LAUNCH_CHECK("m3g_tb_atom_fwd");
   return M3G_OK;
@@ -338,7 +367,7 @@ int m3g_tb_atom_bwd(const float* vec4, const float* bas, const float* red, const
   if (N == 0) return M3G_OK;
   M3G_REQUIRE(vec4 && bas && red && g_e && edge_ptr && tri_ptr && WdT && WgT && g_vec4 && g_bas,
               "m3g_tb_atom_bwd: null pointer");
-  tb_atom_bwd_kernel<<<atom_grid(N, n_sm), 32 * AWARPS, 0, as_stream(stream)>>>(
+  tb_atom_bwd_kernel<<<atom_grid(tb_atom_bwd_kernel, N, n_sm), 32 * AWARPS, 0, as_stream(stream)>>>(
       (const float4*)vec4, bas, red, g_e, edge_ptr, tri_ptr, r3, WdT, WgT, N, (float4*)g_vec4, g_bas);
   M3G_LAUNCH_CHECK("m3g_tb_atom_bwd");
   return M3G_OK;
