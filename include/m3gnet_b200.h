@@ -77,12 +77,25 @@ int m3g_csr_is_symmetric(const int32_t* row_ptr, const int32_t* cols, int64_t n_
  * self pairs dropped; images are relative to the unwrapped input coordinates; edges of atom i are
  * ordered by (j, s0, s1, s2) ascending.
  * ------------------------------------------------------------------------------------------- */
+/* Optional cell list: bins (B,3) int32 = bins per lattice axis of each structure (0,0,0 = sweep the whole structure;
+ * otherwise every axis needs >= 3 bins whose perpendicular width is >= cutoff), bin_base (B+1) = offset of each
+ * structure's bins.  m3g_nbr_bin_count writes atom_bin (N) and adds to bin_count (zeroed by the caller); after an
+ * exclusive scan into bin_ptr, m3g_nbr_bin_fill lists the atoms of every bin (bin_cursor zeroed by the caller).
+ * The bins only restrict the candidate atoms: accept test, edge set and edge order are unchanged.  Pass
+ * bins = NULL to m3g_nbr_count / m3g_nbr_fill for the plain sweep. */
+int m3g_nbr_bin_count(const double* lattice, const double* cart, const int32_t* atom_ptr, int64_t B, int64_t N,
+                      double cutoff, const int32_t* bins, const int32_t* bin_base, int32_t* atom_bin,
+                      int32_t* bin_count, void* stream);
+int m3g_nbr_bin_fill(const int32_t* atom_bin, const int32_t* bin_ptr, int64_t N, int32_t* bin_cursor,
+                     int32_t* bin_atoms, void* stream);
 int m3g_nbr_count(const double* lattice, const double* cart, const int32_t* atom_ptr, int64_t B, int64_t N,
-                  double cutoff, int32_t* edge_count /* (N) */, void* stream);
+                  double cutoff, const int32_t* bins, const int32_t* bin_base, const int32_t* bin_ptr,
+                  const int32_t* bin_atoms, int32_t* edge_count /* (N) */, void* stream);
 int m3g_exclusive_scan_i32(const int32_t* in, int32_t* out /* n+1 */, int64_t n, int32_t* work, void* stream);
 int64_t m3g_scan_work_elems(int64_t n);
 int m3g_nbr_fill(const double* lattice, const double* cart, const int32_t* atom_ptr, int64_t B, int64_t N,
-                 double cutoff, double threebody_cutoff, const int32_t* edge_ptr /* (N+1) */, int64_t E,
+                 double cutoff, double threebody_cutoff, const int32_t* bins, const int32_t* bin_base,
+                 const int32_t* bin_ptr, const int32_t* bin_atoms, const int32_t* edge_ptr /* (N+1) */, int64_t E,
                  int64_t* edge_index /* (2,E) */, int32_t* edge_shift /* (E,3) */, float* edge_dist /* (E) */,
                  int32_t* member /* (E) 1 if float32(d) <= float32(r3) */, void* stream);
 /* per-atom member degree n3 -> num_triplet_i (N) int64 = n3(n3-1), num_triplet_ij (E) int32,

@@ -103,3 +103,19 @@ def test_model_on_gpu_built_graph_matches_oracle(device):
     dF = (out["forces"].cpu() - ref["forces"]).abs().max().item()
     print(f"[parity] gpu-built graphs: |dE|={dE:.3e} (N={n}) max|dF|={dF:.3e} max|F|={ref['forces'].abs().max():.3e}")
     assert dE / n <= 1e-5 and dF <= 1e-4
+
+
+def test_cell_list_large_cells(device):
+    """Cells with >= 3 bins per axis take the cell-list path: identical edges / triplets, in the same order, as the
+    oracle's image sweep — orthogonal and sheared boxes, unwrapped coordinates, mixed with a small cell in one batch."""
+    lat, cart, z = O.fcc_supercell(5, jitter=0.3, seed=11)  # 500 atoms, 18.1 A box -> 3 bins per axis
+    shear = np.eye(3) + 0.08 * np.array([[0, 1, 0.5], [0, 0, 1], [0.3, 0, 0.0]])
+    lat_s, cart_s = lat @ shear, (cart @ shear) + np.array([31.0, -17.0, 4.0])  # far outside the home cell
+    small = O.fcc_supercell(2, jitter=0.05, seed=3)
+    from torch_m3gnet_b200.data.material_graph import Batch
+
+    width = 1.0 / np.linalg.norm(np.linalg.inv(lat_s), axis=0)
+    assert (np.floor(width / 5.0006) >= 3).all(), width
+    b, ref = _compare([(lat, cart, z), small, (lat_s, cart_s, z)], 5.0, 4.0, device)
+    print("[graph] cell list: N=%d E=%d T=%d" % (b.num_nodes, b["edge_index"].shape[1],
+                                                 b["triplet_edge_index"].shape[1]))

@@ -69,16 +69,77 @@ __device__ __forceinline__ int find_structure(const int32_t* __restrict__ atom_p
   return lo;
 }
 
+// ---- cell list (structures whose cell holds >= 3 bins of perpendicular width >= cutoff along every axis) ----
+// Bins only restrict the CANDIDATE atoms j; the accept test and the emission order are those of the brute-force
+// sweep, so the edge set and its order are identical.  bins (B,3): bin counts per axis, 0 = no cell list for that
+// structure; bin_base (B+1): offset of a structure's bins in the global bin arrays.
+constexpr int NBR_WARPS = 4;
+constexpr int CAND_MAX = 512;
+
+__device__ __forceinline__ int bin_coord(double f, int nb) {
+  double w = f - floor(f);
+  int k = (int)(w * (double)nb);
+  return k >= nb ? nb - 1 : (k < 0 ? 0 : k);
+}
+
+__global__ void bin_assign_kernel(const double* __restrict__ lattice, const double* __restrict__ cart,
+                                  const int32_t* __restrict__ atom_ptr, int B, int64_t N, double cutoff,
+                                  const int32_t* __restrict__ bins, const int32_t* __restrict__ bin_base,
+                                  int32_t* __restrict__ atom_bin, int32_t* __restrict__ bin_count) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  int b = find_structure(atom_ptr, B, (int)i);
+  const int nb0 = bins[b * 3], nb1 = bins[b * 3 + 1], nb2 = bins[b * 3 + 2];
+  if (nb0 <= 0) { atom_bin[i] = -1; return; }
+  Cell c;
+  load_cell(lattice, b, cutoff, c);
+  double p[3] = {cart[i * 3 + 0], cart[i * 3 + 1], cart[i * 3 + 2]};
+  double f[3];
+  frac_of(c, p, f);
+  int g = bin_base[b] + (bin_coord(f[0], nb0) * nb1 + bin_coord(f[1], nb1)) * nb2 + bin_coord(f[2], nb2);
+  atom_bin[i] = g;
+  atomicAdd(&bin_count[g], 1);
+}
+
+__global__ void bin_fill_kernel(const int32_t* __restrict__ atom_bin, const int32_t* __restrict__ bin_ptr, int64_t N,
+                                int32_t* __restrict__ bin_cursor, int32_t* __restrict__ bin_atoms) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  int g = atom_bin[i];
+  if (g < 0) return;
+  bin_atoms[bin_ptr[g] + atomicAdd(&bin_cursor[g], 1)] = (int)i;  // order inside a bin is irrelevant (sorted later)
+}
+
+// ascending bitonic sort of s[0..P) by one warp (P a power of two)
+__device__ __forceinline__ void warp_sort(int* s, int P, int lane) {
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < (P >> 1); t += 32) {
+        int i = ((t / j) * 2 * j) + (t % j);
+        int x = i + j;
+        bool up = (i & k) == 0;
+        int a = s[i], bv = s[x];
+        if ((a > bv) == up) { s[i] = bv; s[x] = a; }
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // FILL = false: edge_count[i]; FILL = true: ordered emission at edge_ptr[i]
 template <bool FILL>
-__global__ void nbr_kernel(const double* __restrict__ lattice, const double* __restrict__ cart,
-                           const int32_t* __restrict__ atom_ptr, int B, int64_t N, double cutoff, float r3_f32,
-                           const int32_t* __restrict__ edge_ptr, int32_t* __restrict__ edge_count,
-                           int64_t* __restrict__ edge_index, int64_t E, int32_t* __restrict__ edge_shift,
-                           float* __restrict__ edge_dist, int32_t* __restrict__ member) {
+__global__ void __launch_bounds__(32 * NBR_WARPS)
+nbr_kernel(const double* __restrict__ lattice, const double* __restrict__ cart, const int32_t* __restrict__ atom_ptr,
+           int B, int64_t N, double cutoff, float r3_f32, const int32_t* __restrict__ bins,
+           const int32_t* __restrict__ bin_base, const int32_t* __restrict__ bin_ptr,
+           const int32_t* __restrict__ bin_atoms, const int32_t* __restrict__ edge_ptr,
+           int32_t* __restrict__ edge_count, int64_t* __restrict__ edge_index, int64_t E,
+           int32_t* __restrict__ edge_shift, float* __restrict__ edge_dist, int32_t* __restrict__ member) {
+  __shared__ int cand_s[NBR_WARPS][CAND_MAX];
   int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (i >= N) return;
+  int* cand = cand_s[threadIdx.x >> 5];
   int b = find_structure(atom_ptr, B, (int)i);
   Cell c;
   load_cell(lattice, b, cutoff, c);
@@ -87,11 +148,38 @@ __global__ void nbr_kernel(const double* __restrict__ lattice, const double* __r
   double fi[3];
   frac_of(c, pi, fi);
   int a_beg = atom_ptr[b], a_end = atom_ptr[b + 1];
+  // candidate atoms: the whole structure, or the sorted content of the 27 bins around atom i
+  bool use_cells = false;
+  int n_c = a_end - a_beg;
+  if (bins != nullptr && bins[b * 3] > 0) {
+    const int nb[3] = {bins[b * 3], bins[b * 3 + 1], bins[b * 3 + 2]};
+    const int bc[3] = {bin_coord(fi[0], nb[0]), bin_coord(fi[1], nb[1]), bin_coord(fi[2], nb[2])};
+    int n = 0;
+    bool overflow = false;
+    for (int q = 0; q < 27 && !overflow; ++q) {
+      int dx = q / 9 - 1, dy = (q / 3) % 3 - 1, dz = q % 3 - 1;
+      int gx = (bc[0] + dx + nb[0]) % nb[0], gy = (bc[1] + dy + nb[1]) % nb[1], gz = (bc[2] + dz + nb[2]) % nb[2];
+      int g = bin_base[b] + (gx * nb[1] + gy) * nb[2] + gz;
+      int p0 = bin_ptr[g], p1 = bin_ptr[g + 1];
+      if (n + (p1 - p0) > CAND_MAX) { overflow = true; break; }
+      for (int p = p0 + lane; p < p1; p += 32) cand[n + (p - p0)] = bin_atoms[p];
+      n += p1 - p0;
+    }
+    if (!overflow) {
+      int P = 32;
+      while (P < n) P <<= 1;
+      for (int t = n + lane; t < P; t += 32) cand[t] = 0x7fffffff;
+      __syncwarp();
+      warp_sort(cand, P, lane);
+      use_cells = true;
+      n_c = n;
+    }
+  }
   int64_t base = FILL ? edge_ptr[i] : 0;
   int total = 0;
-  for (int j0 = a_beg; j0 < a_end; j0 += 32) {
-    int j = j0 + lane;
-    bool have = j < a_end;
+  for (int j0 = 0; j0 < n_c; j0 += 32) {
+    bool have = (j0 + lane) < n_c;
+    int j = have ? (use_cells ? cand[j0 + lane] : a_beg + j0 + lane) : a_end;
     double pj[3] = {0, 0, 0};
     int lo[3] = {0, 0, 0}, hi[3] = {-1, -1, -1};
     if (have) {
@@ -219,25 +307,51 @@ using namespace m3g;
 
 extern "C" {
 
+int m3g_nbr_bin_count(const double* lattice, const double* cart, const int32_t* atom_ptr, int64_t B, int64_t N,
+                      double cutoff, const int32_t* bins, const int32_t* bin_base, int32_t* atom_bin,
+                      int32_t* bin_count, void* stream) {
+  if (N == 0) return M3G_OK;
+  M3G_REQUIRE(lattice && cart && atom_ptr && bins && bin_base && atom_bin && bin_count && B > 0,
+              "m3g_nbr_bin_count: bad argument");
+  bin_assign_kernel<<<blocks_for(N, 256), 256, 0, as_stream(stream)>>>(lattice, cart, atom_ptr, (int)B, N, cutoff, bins,
+                                                                       bin_base, atom_bin, bin_count);
+  M3G_LAUNCH_CHECK("m3g_nbr_bin_count");
+  return M3G_OK;
+}
+
+int m3g_nbr_bin_fill(const int32_t* atom_bin, const int32_t* bin_ptr, int64_t N, int32_t* bin_cursor,
+                     int32_t* bin_atoms, void* stream) {
+  if (N == 0) return M3G_OK;
+  M3G_REQUIRE(atom_bin && bin_ptr && bin_cursor && bin_atoms, "m3g_nbr_bin_fill: null pointer");
+  bin_fill_kernel<<<blocks_for(N, 256), 256, 0, as_stream(stream)>>>(atom_bin, bin_ptr, N, bin_cursor, bin_atoms);
+  M3G_LAUNCH_CHECK("m3g_nbr_bin_fill");
+  return M3G_OK;
+}
+
 int m3g_nbr_count(const double* lattice, const double* cart, const int32_t* atom_ptr, int64_t B, int64_t N,
-                  double cutoff, int32_t* edge_count, void* stream) {
+                  double cutoff, const int32_t* bins, const int32_t* bin_base, const int32_t* bin_ptr,
+                  const int32_t* bin_atoms, int32_t* edge_count, void* stream) {
   if (N == 0) return M3G_OK;
   M3G_REQUIRE(lattice && cart && atom_ptr && edge_count && B > 0, "m3g_nbr_count: bad argument");
-  nbr_kernel<false><<<blocks_for(N * 32, 128), 128, 0, as_stream(stream)>>>(
-      lattice, cart, atom_ptr, (int)B, N, cutoff, 0.0f, nullptr, edge_count, nullptr, 0, nullptr, nullptr, nullptr);
+  M3G_REQUIRE(!bins || (bin_base && bin_ptr && bin_atoms), "m3g_nbr_count: incomplete cell list");
+  nbr_kernel<false><<<blocks_for(N * 32, 32 * NBR_WARPS), 32 * NBR_WARPS, 0, as_stream(stream)>>>(
+      lattice, cart, atom_ptr, (int)B, N, cutoff, 0.0f, bins, bin_base, bin_ptr, bin_atoms, nullptr, edge_count,
+      nullptr, 0, nullptr, nullptr, nullptr);
   M3G_LAUNCH_CHECK("m3g_nbr_count");
   return M3G_OK;
 }
 
 int m3g_nbr_fill(const double* lattice, const double* cart, const int32_t* atom_ptr, int64_t B, int64_t N,
-                 double cutoff, double threebody_cutoff, const int32_t* edge_ptr, int64_t E, int64_t* edge_index,
-                 int32_t* edge_shift, float* edge_dist, int32_t* member, void* stream) {
+                 double cutoff, double threebody_cutoff, const int32_t* bins, const int32_t* bin_base,
+                 const int32_t* bin_ptr, const int32_t* bin_atoms, const int32_t* edge_ptr, int64_t E,
+                 int64_t* edge_index, int32_t* edge_shift, float* edge_dist, int32_t* member, void* stream) {
   if (N == 0 || E == 0) return M3G_OK;
   M3G_REQUIRE(lattice && cart && atom_ptr && edge_ptr && edge_index && edge_shift && edge_dist && member && B > 0,
               "m3g_nbr_fill: bad argument");
-  nbr_kernel<true><<<blocks_for(N * 32, 128), 128, 0, as_stream(stream)>>>(
-      lattice, cart, atom_ptr, (int)B, N, cutoff, (float)threebody_cutoff, edge_ptr, nullptr, edge_index, E,
-      edge_shift, edge_dist, member);
+  M3G_REQUIRE(!bins || (bin_base && bin_ptr && bin_atoms), "m3g_nbr_fill: incomplete cell list");
+  nbr_kernel<true><<<blocks_for(N * 32, 32 * NBR_WARPS), 32 * NBR_WARPS, 0, as_stream(stream)>>>(
+      lattice, cart, atom_ptr, (int)B, N, cutoff, (float)threebody_cutoff, bins, bin_base, bin_ptr, bin_atoms, edge_ptr,
+      nullptr, edge_index, E, edge_shift, edge_dist, member);
   M3G_LAUNCH_CHECK("m3g_nbr_fill");
   return M3G_OK;
 }

@@ -188,6 +188,33 @@ class Batch(MaterialGraph):
         z = np.concatenate([np.array([site.specie.Z for site in s], dtype=np.int64) for s in structures])
         return cls.from_arrays(lat, cart, z, sizes, cutoff, threebody_cutoff, device=device)
 
+    @staticmethod
+    def _cell_list(lattices, B, N, cutoff, lat64, cart64, atom_ptr, device):
+        """Bins for structures whose cell holds >= 3 bins of perpendicular width >= cutoff along every axis (large
+        supercells); small cells keep the plain sweep over the structure's atoms."""
+        lat = np.ascontiguousarray(lattices, dtype=np.float64).reshape(B, 3, 3)
+        inv = np.linalg.inv(lat)  # columns b_k; 1/|b_k| = spacing of the lattice planes along axis k
+        width = 1.0 / np.linalg.norm(inv, axis=1)
+        nb = np.minimum(np.floor(width / (cutoff * 1.0001 + 1e-6)), 256).astype(np.int64)
+        nb[(nb < 3).any(axis=1)] = 0
+        if not nb.any():
+            return None, None, None, None
+        i32 = dict(dtype=torch.int32, device=device)
+        base_h = np.concatenate([[0], np.cumsum(nb.prod(axis=1))]).astype(np.int32)
+        n_bins = int(base_h[-1])
+        bins = torch.as_tensor(nb.astype(np.int32)).to(device)
+        bin_base = torch.as_tensor(base_h).to(device)
+        atom_bin = torch.empty(N, **i32)
+        bin_count = torch.zeros(n_bins, **i32)
+        _lib.call("nbr_bin_count", lat64, cart64, atom_ptr, B, N, cutoff, bins, bin_base, atom_bin, bin_count)
+        bin_ptr = torch.empty(n_bins + 1, **i32)
+        work = torch.empty(_lib.scan_work_elems(n_bins), **i32)
+        _lib.call("exclusive_scan_i32", bin_count, bin_ptr, n_bins, work)
+        bin_cursor = torch.zeros(n_bins, **i32)
+        bin_atoms = torch.empty(N, **i32)
+        _lib.call("nbr_bin_fill", atom_bin, bin_ptr, N, bin_cursor, bin_atoms)
+        return bins, bin_base, bin_ptr, bin_atoms
+
     @classmethod
     def from_arrays(cls, lattices: np.ndarray, cart: np.ndarray, atomic_numbers: np.ndarray, sizes: Sequence[int],
                     cutoff: float, threebody_cutoff: float, device: Optional[torch.device] = None,
@@ -208,8 +235,11 @@ class Batch(MaterialGraph):
             atom_ptr_h = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
             atom_ptr = torch.as_tensor(atom_ptr_h).to(device)
             i32 = dict(dtype=torch.int32, device=device)
+            bins, bin_base, bin_ptr, bin_atoms = cls._cell_list(lattices, B, N, float(cutoff), lat64, cart64, atom_ptr,
+                                                                device)
             counts = torch.empty(N, **i32)
-            _lib.call("nbr_count", lat64, cart64, atom_ptr, B, N, float(cutoff), counts)
+            _lib.call("nbr_count", lat64, cart64, atom_ptr, B, N, float(cutoff), bins, bin_base, bin_ptr, bin_atoms,
+                      counts)
             edge_ptr = torch.empty(N + 1, **i32)
             work = torch.empty(_lib.scan_work_elems(N), **i32)
             _lib.call("exclusive_scan_i32", counts, edge_ptr, N, work)
@@ -218,8 +248,8 @@ class Batch(MaterialGraph):
             shift = torch.empty((E, 3), **i32)
             dist = torch.empty(E, dtype=torch.float32, device=device)
             member = torch.empty(E, **i32)
-            _lib.call("nbr_fill", lat64, cart64, atom_ptr, B, N, float(cutoff), float(threebody_cutoff), edge_ptr, E,
-                      edge_index, shift, dist, member)
+            _lib.call("nbr_fill", lat64, cart64, atom_ptr, B, N, float(cutoff), float(threebody_cutoff), bins, bin_base,
+                      bin_ptr, bin_atoms, edge_ptr, E, edge_index, shift, dist, member)
             nti = torch.empty(N, dtype=torch.int64, device=device)
             ntij = torch.empty(E, **i32)
             tri_count = torch.empty(E, **i32)
