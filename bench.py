@@ -122,6 +122,25 @@ def batch_from_host(host, device):
     return b
 
 
+# ABI entry -> kernel name in the committed ncu launch list (profiles/traffic.json, written by tools/summarize_ncu.py)
+TRAFFIC_KERNEL = {
+    "conv_tc_bwd": "conv_tc_bwd2_kernel", "conv_tc_fwd": "conv_tc4_fwd_kernel", "tb_atom_fwd": "tb_atom_fwd_kernel",
+    "tb_atom_bwd": "tb_atom_bwd_kernel", "conv_gather_gz": "conv_gather_gz_kernel",
+    "segment_sum_add": "segment_sum_add_kernel", "tb_sigma_fwd": "tb_sigma_fwd_kernel",
+    "tb_sigma_bwd": "tb_sigma_bwd_kernel", "tb_edge_basis_fwd": "tb_edge_basis_fwd_kernel<3, 3>",
+    "tb_edge_basis_bwd": "tb_edge_basis_bwd_kernel<3, 3>",
+}
+
+
+def load_traffic():
+    """Measured DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum of the same bench command on
+    B200; static file, NOT measured in this run) or {} when the file is absent."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return {}
+    return json.load(open(path)).get("bytes_per_launch", {})
+
+
 def kernel_model(E, T, N, F=64, R=3, D=9):
     """Algorithmic bytes / flops per launch (restated in DESIGN.md §4).
 
@@ -161,10 +180,11 @@ def profile_pass(model, batch, steps, peaks):
     plan = batch._plan
     km, groups = kernel_model(plan.E, plan.T, plan.N)
     tensor_peak = peaks["bf16_sustained"] or peaks["bf16"]
+    traffic = load_traffic()
     rooflines = []
     for name, v in sorted(per.items(), key=lambda kv: -kv[1]["ms_per_step"]):
         entry = dict(kernel="m3g_" + name, share=v["ms_per_step"] / total, avg_ms=v["avg_ms"],
-                     launches_per_step=v["calls_per_step"])
+                     launches_per_step=v["calls_per_step"], traffic=traffic.get(TRAFFIC_KERNEL.get(name, "")))
         if name in km:
             bound, nbytes, flops = km[name]
             sec = v["avg_ms"] * 1e-3
@@ -181,7 +201,9 @@ def profile_pass(model, batch, steps, peaks):
         # one op instance = one launch of each member kernel
         sec = sum(per[m]["avg_ms"] for m in present) * 1e-3
         a = nbytes / sec / 1e9
+        tr = [traffic.get(TRAFFIC_KERNEL.get(m, "")) for m in present]
         rooflines.append(dict(kernel=gname + " (" + "+".join("m3g_" + m for m in present) + ")",
+                              traffic=(sum(tr) if all(t is not None for t in tr) else None),
                               share=sum(per[m]["ms_per_step"] for m in present) / total, avg_ms=sec * 1e3,
                               launches_per_step=per[present[0]]["calls_per_step"], bound=bound, achieved=a,
                               peak=peaks["hbm"], unit="GB/s", frac=a / peaks["hbm"],
@@ -373,8 +395,11 @@ def main():
         dominant = next((r for r in rooflines if "bound" in r), None)
         if dominant is not None:
             line["roofline"] = dict(bound=dominant["bound"], achieved=dominant["achieved"], peak=dominant["peak"],
-                                    unit=dominant["unit"], frac=dominant["frac"], traffic=None,
-                                    kernel=dominant["kernel"], peak_source=peaks["source"] + " (MEASURED_PEAKS.json)")
+                                    unit=dominant["unit"], frac=dominant["frac"], traffic=dominant.get("traffic"),
+                                    kernel=dominant["kernel"], peak_source=peaks["source"] + " (MEASURED_PEAKS.json)",
+                                    note="dominant kernel of the step; algorithmic flops (33.5 kflop/edge fwd, "
+                                         "82 kflop/edge bwd, DESIGN.md 4) / CUDA-event duration; traffic = ncu DRAM "
+                                         "bytes per launch from profiles/traffic.json (static, same command)")
         line["rooflines"] = rooflines[:14]
         line["kernel_ms_per_step"] = kernel_ms
     if not args.no_cpu_baseline:

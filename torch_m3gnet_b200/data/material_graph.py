@@ -303,6 +303,7 @@ class GraphPlan:
         p.atom_ptr, p.edge_ptr = atom_ptr, edge_ptr
         p._in_csr()
         p.tri_ptr, p.tri_e2 = tri_ptr, tri_e2
+        p.T = int(tri_e2.numel())  # also when the (2,T) int64 API list was not materialised
         p.trt_ptr, p.trt_e1 = tri_ptr, tri_e2  # builder output is the full off-diagonal: symmetric
         p.tri_symmetric = True
         p._pick_group()
