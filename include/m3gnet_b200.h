@@ -275,7 +275,14 @@ int m3g_tc_selftest(const float* A, const float* img_hi, const float* img_lo, in
                     int a_tmem, float* out, void* stream);
 int m3g_conv_tc_fwd(const float* P, int ldp, int po, const int32_t* src, const int32_t* dst, const float* e,
                     const float* h, const float* wimg, const float* b2d, const float* b2g, const float* WhT, int64_t E,
-                    int R, int mode, int passes, int variant, int n_sm, float* y, void* stream);
+                    int R, int mode, int passes, int variant, int n_sm, float* y, float* save, void* stream);
+/* save (optional, variant 4): activations for m3g_conv_tc_bwd_saved — ceil(E / 128) * 128 * 256 floats (1 KB per edge:
+ * SiLU'(z1) and the layer-2 pre-activations, in a tile-private fragment-major layout).  With them the backward needs
+ * neither the forward weights nor P / e: output adjoint -> two 64x64 adjoint GEMM pairs -> g_e, g_z1, g_h (same outputs
+ * and conventions as m3g_conv_tc_bwd; src is only read for mode 1, where g_up is indexed by source atom). */
+int m3g_conv_tc_bwd_saved(const int32_t* src, const float* h, const float* wimgT, const float* WhT, const float* save,
+                          const float* g_up, const float* g_e_base, int64_t E, int R, int mode, int passes, int n_sm,
+                          float* g_e, float* g_z1, float* g_h, void* stream);
 
 /* adjoint of m3g_conv_tc_fwd (same outputs as m3g_conv_mlp_bwd; forward recomputed on the tensor cores).
  * wimgT = [W2d^T hi|lo, W2g^T hi|lo, W1e_dense^T hi|lo, W1e_gate^T hi|lo]: four 64x64 image pairs from

@@ -216,7 +216,17 @@ struct ConvTcParams {
   const float* b2d; const float* b2g; const float* WhT;
   int64_t E; int R; int mode; int passes;
   float* y;
+  float* save;  // optional (variant 4): per-tile activations for m3g_conv_tc_bwd_saved, see save_offset()
 };
+
+// Activations kept for the backward pass (1 KB per edge): four 64-column blocks per 128-edge tile —
+// 0: SiLU'(z1 dense), 1: SiLU'(z1 gate), 2: z2 dense, 3: z2 gate (pre-activations, biases included).  The layout is
+// private to the kernel pair and "fragment-major": a thread's 16-column slice of its row is four float4 that land,
+// together with the other 31 rows of the warp, in four fully coalesced 512-byte segments:
+//   [tile][block 4][16-column chunk 4][row quadrant 4][float4 index 4][row in quadrant 32][4 floats]
+__device__ __forceinline__ int64_t save_offset(int64_t tile, int block, int chunk, int quadrant) {
+  return tile * (int64_t)(TILE_M * 256) + (((block * 4 + chunk) * 4 + quadrant) << 9);
+}
 
 constexpr int SMEM_W_BYTES = WIMG_FLOATS * 4;         // 131072
 constexpr int SMEM_X_BYTES = 2 * TILE_M * TC_F * 4;   // 65536 (hi | lo)
@@ -1009,13 +1019,20 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc4_fwd_kernel(ConvTcPara
       float v[16];
       tmem_ld16(t_lane + D1 + col, v);
       tmem_ld_wait();
+      float* sv = p.save ? p.save + save_offset(tile, sc >> 1, 2 * hsel + (sc & 1), q) + 4 * lane : nullptr;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float4 b = lds128(stg + stg_off(lane, c));
-        act[16 * (sc & 1) + 4 * c] = silu_fast(v[4 * c] + pi4[c].x + b.x);
-        act[16 * (sc & 1) + 4 * c + 1] = silu_fast(v[4 * c + 1] + pi4[c].y + b.y);
-        act[16 * (sc & 1) + 4 * c + 2] = silu_fast(v[4 * c + 2] + pi4[c].z + b.z);
-        act[16 * (sc & 1) + 4 * c + 3] = silu_fast(v[4 * c + 3] + pi4[c].w + b.w);
+        const float z[4] = {v[4 * c] + pi4[c].x + b.x, v[4 * c + 1] + pi4[c].y + b.y, v[4 * c + 2] + pi4[c].z + b.z,
+                            v[4 * c + 3] + pi4[c].w + b.w};
+        float g[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float sg = sigmoid_fast(z[u]);
+          act[16 * (sc & 1) + 4 * c + u] = z[u] * sg;
+          g[u] = sg * (1.0f + z[u] * (1.0f - sg));  // SiLU'(z1), kept for the backward pass
+        }
+        if (sv) *reinterpret_cast<float4*>(sv + 128 * c) = make_float4(g[0], g[1], g[2], g[3]);
       }
       __syncwarp();
       if (sc == 1) {
@@ -1051,13 +1068,16 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc4_fwd_kernel(ConvTcPara
       float v[16];
       tmem_ld16(t_lane + D2D + c0 + 16 * h2, v);
       tmem_ld_wait();
+      float* sv = p.save ? p.save + save_offset(tile, 2, 2 * hsel + h2, q) + 4 * lane : nullptr;
 #pragma unroll
       for (int c = 0; c < 16; c += 4) {
         float4 b = lds128(b2d_a + 4 * (c0 + 16 * h2 + c));
-        act[16 * h2 + c] = silu_fast(v[c] + b.x);
-        act[16 * h2 + c + 1] = silu_fast(v[c + 1] + b.y);
-        act[16 * h2 + c + 2] = silu_fast(v[c + 2] + b.z);
-        act[16 * h2 + c + 3] = silu_fast(v[c + 3] + b.w);
+        const float4 z = make_float4(v[c] + b.x, v[c + 1] + b.y, v[c + 2] + b.z, v[c + 3] + b.w);
+        if (sv) *reinterpret_cast<float4*>(sv + 32 * c) = z;
+        act[16 * h2 + c] = silu_fast(z.x);
+        act[16 * h2 + c + 1] = silu_fast(z.y);
+        act[16 * h2 + c + 2] = silu_fast(z.z);
+        act[16 * h2 + c + 3] = silu_fast(z.w);
       }
     }
     mbar_wait_warp(g2g_own, par);
@@ -1077,9 +1097,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc4_fwd_kernel(ConvTcPara
       float v[16];
       tmem_ld16(t_lane + D2G + col, v);
       tmem_ld_wait();
+      float* svg = p.save ? p.save + save_offset(tile, 3, 2 * hsel + h2, q) + 4 * lane : nullptr;
 #pragma unroll
       for (int c = 0; c < 16; c += 4) {
         float4 bg = lds128(b2g_a + 4 * (col + c));
+        if (svg) *reinterpret_cast<float4*>(svg + 32 * c) = make_float4(v[c] + bg.x, v[c + 1] + bg.y, v[c + 2] + bg.z,
+                                                                       v[c + 3] + bg.w);
         float bgv[4] = {bg.x, bg.y, bg.z, bg.w};
         float o[4];
 #pragma unroll
@@ -1858,6 +1881,267 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwd2_kernel(ConvTcBwd
 }
 
 // --------------------------------------------------------------------------------------------------------
+// Backward from SAVED activations (pairs with conv_tc4_fwd_kernel(save != NULL)).  The recompute version above
+// spends 43 % of its MMA instructions, both P gathers, the e load and half of its MUFU work on rebuilding z1 / z2;
+// here the forward leaves SiLU'(z1) and z2 behind (1 KB per edge, fragment-major so that both sides use plain coalesced
+// float4 accesses) and the backward is just   output adjoint -> GEMM3d/3g -> dz1 -> GEMM4a/4b -> outputs:
+// two MMA sync points per tile, no forward weights, all four transposed weight image pairs resident in shared memory.
+// TMEM columns: A [0,64)|[64,128) hi|lo, A2 [128,192)|[192,256), D3d [256,320), D3g [320,384), D4 [384,448).
+struct ConvTcBwdSParams {
+  const int32_t* src; const float* h;
+  const float* wimgT;  // [W2d^T hi|lo, W2g^T hi|lo, W1e_dense^T hi|lo, W1e_gate^T hi|lo]
+  const float* WhT; const float* save;
+  const float* g_up; const float* g_e_base;
+  int64_t E; int R; int mode; int passes;
+  float* g_e; float* g_z1; float* g_h;
+};
+constexpr int SMEM_BS_MISC = TC_BWD_MAX_R * 64 * 4 + 32;  // Wh^T, 2 mbarriers, TMEM slot
+constexpr int SMEM_BWDS_BYTES = SMEM_W_BYTES + 16 * STG_WARP_BYTES + SMEM_BS_MISC + 1024;
+
+__global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwdSParams p) {
+  extern __shared__ __align__(1024) char smem_raw[];
+  char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t wt[4] = {sbase, sbase + SMEM_S_BYTES, sbase + 2 * SMEM_S_BYTES, sbase + 3 * SMEM_S_BYTES};
+  const uint32_t stg_all = sbase + SMEM_W_BYTES;
+  float* misc = reinterpret_cast<float*>(smem + SMEM_W_BYTES + 16 * STG_WARP_BYTES);
+  const uint32_t wh_a = stg_all + 16 * STG_WARP_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc + TC_BWD_MAX_R * 64);
+  uint32_t* tmem_slot_p = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, cs = warp >> 2;
+  const int row = 32 * q + lane;
+  const int k0 = 16 * cs;
+  const uint32_t stg = stg_all + warp * STG_WARP_BYTES;
+  const int cr = lane >> 2, cc4 = lane & 3;
+  const int R = p.R;
+
+  for (int i = tid; i < WIMG_FLOATS / 4; i += TCB2_THREADS)
+    reinterpret_cast<float4*>(smem)[i] = reinterpret_cast<const float4*>(p.wimgT)[i];
+  for (int i = tid; i < TC_BWD_MAX_R * 64; i += TCB2_THREADS) misc[i] = (i < R * 64) ? p.WhT[i] : 0.0f;
+  if (warp == 0) tmem_alloc<512>(tmem_slot_p);
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  if (*tmem_slot_p != 0u) __trap();  // one CTA per SM owns all 512 columns: literal operand addresses (see bwd2)
+  constexpr uint32_t tmem = 0u;
+  const uint32_t t_lane = ((uint32_t)(32 * q) << 16);
+  constexpr uint32_t AH = 0, AL = 64, A2H = 128, A2L = 192, D3D = 256, D3G = 320, D4 = 384;
+  uint64_t *bar3 = &bars[0], *bar4 = &bars[1];
+
+  const int64_t n_tiles = (p.E + TILE_M - 1) / TILE_M;
+  uint32_t par = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, par ^= 1) {
+    const int64_t e0 = tile * TILE_M;
+    const int64_t eg = min(e0 + row, p.E - 1);
+    const bool live = (e0 + row) < p.E;
+    int64_t erow[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) erow[i] = e0 + 32 * q + 8 * i + cr;
+    {
+      // next tile: saved activations (128 KB = 1024 lines), upstream rows, residual rows, h into L2
+      const int64_t tn = tile + gridDim.x;
+      if (tn < n_tiles) {
+        const float* sv = p.save + tn * (int64_t)(TILE_M * 256);
+        prefetch_l2(sv + tid * 32);
+        prefetch_l2(sv + (tid + 512) * 32);
+        const int64_t en = tn * TILE_M;
+        const int64_t rn = min(en + (tid & 255) / 2, p.E - 1);
+        const int half = (tid & 1) * 32;
+        if (tid < 256) {
+          if (p.mode == 0) prefetch_l2(p.g_up + rn * TC_F + half);
+        } else {
+          if (p.g_e_base) prefetch_l2(p.g_e_base + rn * TC_F + half);
+          if (tid < 256 + 16) prefetch_l2(p.h + min(en * R + (tid - 256) * 32, p.E * R - 1));
+        }
+      }
+    }
+    // ---- T0: saved z2 slices, upstream gradient slice, h ----
+    float zd[16], zg[16], gu[16];
+    {
+      const float* s2 = p.save + save_offset(tile, 2, cs, q) + 4 * lane;
+      const float* s3 = p.save + save_offset(tile, 3, cs, q) + 4 * lane;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(s2 + 128 * c));
+        float4 b = __ldg(reinterpret_cast<const float4*>(s3 + 128 * c));
+        zd[4 * c] = a.x; zd[4 * c + 1] = a.y; zd[4 * c + 2] = a.z; zd[4 * c + 3] = a.w;
+        zg[4 * c] = b.x; zg[4 * c + 1] = b.y; zg[4 * c + 2] = b.z; zg[4 * c + 3] = b.w;
+      }
+    }
+    if (p.mode == 0) {
+      float4 c4v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        c4v[i] = __ldg(reinterpret_cast<const float4*>(p.g_up + min(erow[i], p.E - 1) * TC_F + k0 + 4 * cc4));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sts128(stg + stg_off(8 * i + cr, cc4), c4v[i]);
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float4 b = lds128(stg + stg_off(lane, c));
+        gu[4 * c] = b.x; gu[4 * c + 1] = b.y; gu[4 * c + 2] = b.z; gu[4 * c + 3] = b.w;
+      }
+      __syncwarp();
+    } else {
+      const float* gr = p.g_up + (int64_t)__ldg(p.src + eg) * TC_F + k0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float4 b = __ldg(reinterpret_cast<const float4*>(gr + 4 * c));
+        gu[4 * c] = b.x; gu[4 * c + 1] = b.y; gu[4 * c + 2] = b.z; gu[4 * c + 3] = b.w;
+      }
+    }
+    float hm[TC_BWD_MAX_R], ghp[TC_BWD_MAX_R];
+#pragma unroll
+    for (int m = 0; m < TC_BWD_MAX_R; ++m) {
+      hm[m] = (m < R) ? __ldg(p.h + eg * R + m) : 0.0f;
+      ghp[m] = 0.0f;
+    }
+    // ---- T5: output-stage adjoint -> dz2d (operand A), dz2g (operand A2) ; GEMM3d + GEMM3g ----
+#pragma unroll
+    for (int c = 0; c < 16; c += 4) {
+      float whv[TC_BWD_MAX_R][4];
+#pragma unroll
+      for (int m = 0; m < TC_BWD_MAX_R; ++m) {
+        float4 w4 = lds128(wh_a + 4 * (m * 64 + k0 + c));
+        whv[m][0] = w4.x; whv[m][1] = w4.y; whv[m][2] = w4.z; whv[m][3] = w4.w;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float z = zd[c + u];
+        const float sgm = sigmoid_fast(z);
+        const float sd = z * sgm;
+        const float sgr = sgm * (1.0f + z * (1.0f - sgm));
+        const float sg = sigmoid_fast(zg[c + u]);
+        float s = 0.0f;
+#pragma unroll
+        for (int m = 0; m < TC_BWD_MAX_R; ++m) s += hm[m] * whv[m][u];
+        const float gs = gu[c + u] * sd * sg;
+#pragma unroll
+        for (int m = 0; m < TC_BWD_MAX_R; ++m) ghp[m] += gs * whv[m][u];
+        const float gphi = gu[c + u] * s;
+        zd[c + u] = gphi * sg * sgr;               // dz2d
+        zg[c + u] = gphi * sd * sg * (1.0f - sg);  // dz2g
+      }
+    }
+    tmem_put_split16(t_lane + AH + k0, t_lane + AL + k0, zd);
+    tmem_put_split16(t_lane + A2H + k0, t_lane + A2L + k0, zg);
+    if (cs != 0) sts128(stg + lane * 16, make_float4(ghp[0], ghp[1], ghp[2], 0.0f));
+    tmem_st_wait();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_gemm_ts(tmem + D3D, tmem + AH, tmem + AL, wt[0], wt[0] + IMG_W2 * 4, 64, 64, false, p.passes);
+      issue_gemm_ts(tmem + D3G, tmem + A2H, tmem + A2L, wt[1], wt[1] + IMG_W2 * 4, 64, 64, false, p.passes);
+      commit(bar3);
+    }
+    if (cs == 0) {
+      float4 g1 = lds128(stg + 4 * STG_WARP_BYTES + lane * 16);
+      float4 g2 = lds128(stg + 8 * STG_WARP_BYTES + lane * 16);
+      float4 g3 = lds128(stg + 12 * STG_WARP_BYTES + lane * 16);
+      if (live) {
+        float tot[3] = {((ghp[0] + g1.x) + g2.x) + g3.x, ((ghp[1] + g1.y) + g2.y) + g3.y,
+                        ((ghp[2] + g1.z) + g2.z) + g3.z};
+#pragma unroll
+        for (int m = 0; m < TC_BWD_MAX_R; ++m)
+          if (m < R) p.g_h[eg * R + m] += tot[m];
+      }
+    }
+    // saved SiLU'(z1) slices (dense -> zd, gate -> zg), in flight while GEMM3 runs
+    {
+      const float* s0 = p.save + save_offset(tile, 0, cs, q) + 4 * lane;
+      const float* s1 = p.save + save_offset(tile, 1, cs, q) + 4 * lane;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(s0 + 128 * c));
+        float4 b = __ldg(reinterpret_cast<const float4*>(s1 + 128 * c));
+        zd[4 * c] = a.x; zd[4 * c + 1] = a.y; zd[4 * c + 2] = a.z; zd[4 * c + 3] = a.w;
+        zg[4 * c] = b.x; zg[4 * c + 1] = b.y; zg[4 * c + 2] = b.z; zg[4 * c + 3] = b.w;
+      }
+    }
+    // ---- T6: dz1 = D3 * SiLU'(z1) -> operands A (dense), A2 (gate) ; GEMM4a + GEMM4b ----
+    mbar_wait_warp(bar3, par);
+    fence_after_sync();
+    {
+      float v[16];
+      tmem_ld16(t_lane + D3D + k0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 16; ++c) zd[c] *= v[c];
+      tmem_put_split16(t_lane + AH + k0, t_lane + AL + k0, zd);
+      tmem_ld16(t_lane + D3G + k0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 16; ++c) zg[c] *= v[c];
+      tmem_put_split16(t_lane + A2H + k0, t_lane + A2L + k0, zg);
+    }
+    tmem_st_wait();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_gemm_ts(tmem + D4, tmem + AH, tmem + AL, wt[2], wt[2] + IMG_W2 * 4, 64, 64, false, p.passes);
+      issue_gemm_ts(tmem + D4, tmem + A2H, tmem + A2L, wt[3], wt[3] + IMG_W2 * 4, 64, 64, true, p.passes);
+      commit(bar4);
+    }
+    float4 gb[4];
+    if (p.g_e_base) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        gb[i] = __ldg(reinterpret_cast<const float4*>(p.g_e_base + min(erow[i], p.E - 1) * TC_F + k0 + 4 * cc4));
+    }
+    // g_z1 rows straight from registers (overlaps GEMM4), coalesced through the staging tile
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+      const float* dz = hb ? zg : zd;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        sts128(stg + stg_off(lane, c), make_float4(dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]));
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 r4 = lds128(stg + stg_off(8 * i + cr, cc4));
+        if (erow[i] < p.E) *reinterpret_cast<float4*>(p.g_z1 + erow[i] * 128 + 64 * hb + k0 + 4 * cc4) = r4;
+      }
+      __syncwarp();
+    }
+    // ---- T7: g_e ----
+    mbar_wait_warp(bar4, par);
+    fence_after_sync();
+    {
+      float v[16];
+      tmem_ld16(t_lane + D4 + k0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        sts128(stg + stg_off(lane, c), make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 r4 = lds128(stg + stg_off(8 * i + cr, cc4));
+        if (erow[i] < p.E) {
+          if (p.g_e_base) { r4.x += gb[i].x; r4.y += gb[i].y; r4.z += gb[i].z; r4.w += gb[i].w; }
+          *reinterpret_cast<float4*>(p.g_e + erow[i] * TC_F + k0 + 4 * cc4) = r4;
+        }
+      }
+      __syncwarp();
+    }
+    fence_before_sync();
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// --------------------------------------------------------------------------------------------------------
 // debug: issue rate of tcgen05.mma kind::tf32 M=128 for a given N, A from shared (0) or tensor memory (1)
 template <int N, int ATMEM>
 __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n_rep, long long* out) {
@@ -1969,8 +2253,9 @@ int m3g_tc_selftest(const float* A, const float* img_hi, const float* img_lo, in
 
 int m3g_conv_tc_fwd(const float* P, int ldp, int po, const int32_t* src, const int32_t* dst, const float* e,
                     const float* h, const float* wimg, const float* b2d, const float* b2g, const float* WhT, int64_t E,
-                    int R, int mode, int passes, int variant, int n_sm, float* y, void* stream) {
+                    int R, int mode, int passes, int variant, int n_sm, float* y, float* save, void* stream) {
   if (E == 0) return M3G_OK;
+  M3G_REQUIRE(!save || (variant == 4 && R <= TC3_MAX_R), "m3g_conv_tc_fwd: activations are only saved by variant 4");
   M3G_REQUIRE(P && src && dst && e && h && wimg && b2d && b2g && WhT && y, "m3g_conv_tc_fwd: null pointer");
   M3G_REQUIRE(R >= 1 && R <= M3G_MAX_RADIAL, "m3g_conv_tc_fwd: R=%d unsupported", R);
   M3G_REQUIRE(passes == 1 || passes == 3, "m3g_conv_tc_fwd: passes must be 1 or 3");
@@ -1981,7 +2266,7 @@ int m3g_conv_tc_fwd(const float* P, int ldp, int po, const int32_t* src, const i
     set_error("m3g_conv_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     return M3G_ERR_CUDA;
   }
-  ConvTcParams p{P, ldp, po, src, dst, e, h, wimg, b2d, b2g, WhT, E, R, mode, passes, y};
+  ConvTcParams p{P, ldp, po, src, dst, e, h, wimg, b2d, b2g, WhT, E, R, mode, passes, y, save};
   int64_t n_tiles = (E + TILE_M - 1) / TILE_M;
   if (variant == 4 && R <= TC3_MAX_R) {
     err = cudaFuncSetAttribute(conv_tc4_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD4_BYTES);
@@ -2022,6 +2307,27 @@ int m3g_conv_tc_fwd(const float* P, int ldp, int po, const int32_t* src, const i
   unsigned grid = (unsigned)((n_tiles < n_sm) ? n_tiles : n_sm);
   conv_tc_fwd_kernel<<<grid, TC_THREADS, SMEM_FWD_BYTES, as_stream(stream)>>>(p);
   M3G_LAUNCH_CHECK("m3g_conv_tc_fwd");
+  return M3G_OK;
+}
+
+int m3g_conv_tc_bwd_saved(const int32_t* src, const float* h, const float* wimgT, const float* WhT, const float* save,
+                          const float* g_up, const float* g_e_base, int64_t E, int R, int mode, int passes, int n_sm,
+                          float* g_e, float* g_z1, float* g_h, void* stream) {
+  if (E == 0) return M3G_OK;
+  M3G_REQUIRE(src && h && wimgT && WhT && save && g_up && g_e && g_z1 && g_h, "m3g_conv_tc_bwd_saved: null pointer");
+  M3G_REQUIRE(R >= 1 && R <= TC_BWD_MAX_R, "m3g_conv_tc_bwd_saved: R=%d unsupported (max %d)", R, TC_BWD_MAX_R);
+  M3G_REQUIRE(passes == 1 || passes == 3, "m3g_conv_tc_bwd_saved: passes must be 1 or 3");
+  cudaError_t err =
+      cudaFuncSetAttribute(conv_tc_bwds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWDS_BYTES);
+  if (err != cudaSuccess) {
+    set_error("m3g_conv_tc_bwd_saved: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+    return M3G_ERR_CUDA;
+  }
+  ConvTcBwdSParams p{src, h, wimgT, WhT, save, g_up, g_e_base, E, R, mode, passes, g_e, g_z1, g_h};
+  int64_t n_tiles = (E + TILE_M - 1) / TILE_M;
+  unsigned grid = (unsigned)((n_tiles < n_sm) ? n_tiles : n_sm);
+  conv_tc_bwds_kernel<<<grid, TCB2_THREADS, SMEM_BWDS_BYTES, as_stream(stream)>>>(p);
+  M3G_LAUNCH_CHECK("m3g_conv_tc_bwd_saved");
   return M3G_OK;
 }
 

@@ -225,13 +225,18 @@ class ConvFn(Function):
         msg = torch.empty_like(e)
         ed, nd = w["edge"], w["node"]
         path = conv_path()
+        save_e = save_n = None
         if F == 64 and "wimg" in ed and path in ("tc3", "tc1"):
             passes = 3 if path == "tc3" else 1
             n_sm = sm_count(x.device)
+            if tc_variant() == 4 and tc_bwd_variant() == 4 and R <= 3 and any(ctx.needs_input_grad[:3]):
+                # activations for the backward (1 KB per edge and MLP): SiLU'(z1) and the layer-2 pre-activations
+                n_save = ((E + 127) // 128) * 128 * 256
+                save_e, save_n = _empty((n_save,), x), _empty((n_save,), x)
             call("conv_tc_fwd", P, 8 * F, 0, plan.src, plan.dst, e, h, ed["wimg"], ed["b2d"], ed["b2g"], ed["WhT"], E, R,
-                 0, passes, tc_variant(), n_sm, e2)
+                 0, passes, tc_variant(), n_sm, e2, save_e)
             call("conv_tc_fwd", P, 8 * F, 4 * F, plan.src, plan.dst, e2, h, nd["wimg"], nd["b2d"], nd["b2g"], nd["WhT"],
-                 E, R, 1, passes, tc_variant(), n_sm, msg)
+                 E, R, 1, passes, tc_variant(), n_sm, msg, save_n)
         else:
             call("conv_mlp_fwd", P, 8 * F, 0, plan.src, plan.dst, e, h, ed["W1eT"], ed["W2dT"], ed["b2d"], ed["W2gT"],
                  ed["b2g"], ed["WhT"], E, F, R, 0, e2)
@@ -240,6 +245,7 @@ class ConvFn(Function):
         x2 = torch.empty_like(x)
         call("segment_sum_add", x, msg, plan.edge_ptr, N, F, x2)
         ctx.plan, ctx.w = plan, w
+        ctx.saved_acts = (save_e, save_n)
         ctx.save_for_backward(x, e, e2, h, P)
         return x2, e2
 
@@ -259,7 +265,16 @@ class ConvFn(Function):
         g_e = torch.empty_like(e)
         gz_edge = _empty((E, 2 * F), x)
         path = conv_path()
-        if F == 64 and "wimgT" in ed and path in ("tc3", "tc1") and R <= 3:
+        save_e, save_n = ctx.saved_acts
+        if save_e is not None:
+            passes = 3 if path == "tc3" else 1
+            n_sm = sm_count(x.device)
+            call("conv_tc_bwd_saved", plan.src, h, nd["wimgT"], nd["WhT"], save_n, g_x2, g_e2, E, R, 1, passes, n_sm, ge2,
+                 gz_node, g_h)
+            call("conv_tc_bwd_saved", plan.src, h, ed["wimgT"], ed["WhT"], save_e, ge2, ge2, E, R, 0, passes, n_sm, g_e,
+                 gz_edge, g_h)
+            ctx.saved_acts = (None, None)
+        elif F == 64 and "wimgT" in ed and path in ("tc3", "tc1") and R <= 3:
             passes = 3 if path == "tc3" else 1
             n_sm = sm_count(x.device)
             call("conv_tc_bwd", P, 8 * F, 4 * F, plan.src, plan.dst, e2, h, nd["wimg"], nd["wimgT"], nd["b2d"], nd["b2g"],

@@ -18,8 +18,9 @@ CONV_PATH = os.environ.get("M3G_CONV_PATH", "tc3")
 # per-warp staging (csrc/conv_tc.cu)
 TC_VARIANT = int(os.environ.get("M3G_TC_VARIANT", "4"))
 # backward: 1 = one tile per CTA through shared operand buffers; 2 = all A operands in tensor memory, coalesced
-# traffic, bulk-copied transposed weight images (csrc/conv_tc.cu)
-TC_BWD_VARIANT = int(os.environ.get("M3G_TC_BWD_VARIANT", "2"))
+# traffic, bulk-copied transposed weight images; 4 = no recompute: the forward (variant 4) leaves SiLU'(z1) and the
+# layer-2 pre-activations behind (1 KB per edge and MLP) and the backward runs only the adjoint GEMMs (csrc/conv_tc.cu)
+TC_BWD_VARIANT = int(os.environ.get("M3G_TC_BWD_VARIANT", "4"))
 
 
 def _tc_images(w1e: torch.Tensor, w2d: torch.Tensor, w2g: torch.Tensor) -> torch.Tensor:
