@@ -124,7 +124,8 @@ def batch_from_host(host, device):
 
 # ABI entry -> kernel name in the committed ncu launch list (profiles/traffic.json, written by tools/summarize_ncu.py)
 TRAFFIC_KERNEL = {
-    "conv_tc_bwd": "conv_tc_bwd2_kernel", "conv_tc_fwd": "conv_tc4_fwd_kernel", "tb_atom_fwd": "tb_atom_fwd_kernel",
+    "conv_tc_bwd": "conv_tc_bwd2_kernel", "conv_tc_bwd_saved": "conv_tc_bwds_kernel",
+    "conv_tc_fwd": "conv_tc4_fwd_kernel", "tb_atom_fwd": "tb_atom_fwd_kernel",
     "tb_atom_bwd": "tb_atom_bwd_kernel", "conv_gather_gz": "conv_gather_gz_kernel",
     "segment_sum_add": "segment_sum_add_kernel", "tb_sigma_fwd": "tb_sigma_fwd_kernel",
     "tb_sigma_bwd": "tb_sigma_bwd_kernel", "tb_edge_basis_fwd": "tb_edge_basis_fwd_kernel<3, 3>",
@@ -152,8 +153,11 @@ def kernel_model(E, T, N, F=64, R=3, D=9):
         "conv_mlp_fwd": ("tensor", 532 * E // 2 + 512 * N // 2, 2 * E * (mlp_mac + 2 * R * F)),
         "conv_mlp_bwd": ("tensor", 800 * E // 2 + 768 * N // 2, 2 * E * (2 * mlp_mac + F * 2 * F)),
     }
-    single["conv_tc_fwd"] = single["conv_mlp_fwd"]
+    # tensor-core pair actually used for F = 64: the forward also writes 1 KB/edge of activations, the backward reads
+    # them instead of recomputing the forward GEMMs (flops = adjoint GEMMs only: 4 x 64x64 per edge)
+    single["conv_tc_fwd"] = ("tensor", 532 * E // 2 + 512 * N // 2 + 1024 * E, 2 * E * (mlp_mac + 2 * R * F))
     single["conv_tc_bwd"] = single["conv_mlp_bwd"]
+    single["conv_tc_bwd_saved"] = ("tensor", 800 * E // 2 + 768 * N // 2 + 1024 * E, 2 * E * (4 * F * F))
     groups = {
         "threebody_fwd": (("tb_sigma_fwd", "tb_edge_basis_fwd", "tb_reduce_fwd", "tb_reduce_fwd_fast", "tb_atom_fwd"),
                           "hbm", 4 * T + 536 * E + 36 * N),
@@ -189,10 +193,19 @@ def profile_pass(model, batch, steps, peaks):
             bound, nbytes, flops = km[name]
             sec = v["avg_ms"] * 1e-3
             a = flops / sec / 1e12
-            entry.update(bound="tensor", achieved=a, peak=tensor_peak, unit="TFLOP/s", frac=a / tensor_peak,
-                         tf32x3_frac=a / (tensor_peak / 2 / 3), hbm_frac=nbytes / sec / 1e9 / peaks["hbm"],
-                         note="tcgen05 kind::tf32, 3 passes (3xTF32 split); peak = measured sustained bf16 cuBLAS; "
-                              "tf32x3_frac = against bf16_peak/2/3; hbm_frac = algorithmic bytes vs measured HBM")
+            gbs = nbytes / sec / 1e9
+            if gbs / peaks["hbm"] >= a / tensor_peak:
+                # the narrow (F = 64) gated MLPs sit closer to the HBM roof than to the tensor roof
+                entry.update(bound="hbm", achieved=gbs, peak=peaks["hbm"], unit="GB/s", frac=gbs / peaks["hbm"],
+                             tensor_tflops=a, tensor_frac=a / tensor_peak, tf32x3_frac=a / (tensor_peak / 2 / 3),
+                             note="algorithmic bytes (DESIGN.md 4, incl. the 1 KB/edge of saved activations) against "
+                                  "the measured HBM peak; tensor_frac = algorithmic flops against the measured bf16 "
+                                  "peak, tf32x3_frac against bf16_peak/2/3 (tcgen05 kind::tf32, 3xTF32 split)")
+            else:
+                entry.update(bound="tensor", achieved=a, peak=tensor_peak, unit="TFLOP/s", frac=a / tensor_peak,
+                             tf32x3_frac=a / (tensor_peak / 2 / 3), hbm_frac=gbs / peaks["hbm"],
+                             note="tcgen05 kind::tf32, 3 passes (3xTF32 split); peak = measured sustained bf16 cuBLAS; "
+                                  "tf32x3_frac = against bf16_peak/2/3; hbm_frac = algorithmic bytes vs measured HBM")
         rooflines.append(entry)
     for gname, (members, bound, nbytes) in groups.items():
         present = [m for m in members if m in per]
@@ -397,9 +410,10 @@ def main():
             line["roofline"] = dict(bound=dominant["bound"], achieved=dominant["achieved"], peak=dominant["peak"],
                                     unit=dominant["unit"], frac=dominant["frac"], traffic=dominant.get("traffic"),
                                     kernel=dominant["kernel"], peak_source=peaks["source"] + " (MEASURED_PEAKS.json)",
-                                    note="dominant kernel of the step; algorithmic flops (33.5 kflop/edge fwd, "
-                                         "82 kflop/edge bwd, DESIGN.md 4) / CUDA-event duration; traffic = ncu DRAM "
-                                         "bytes per launch from profiles/traffic.json (static, same command)")
+                                    tensor_frac=dominant.get("tensor_frac"),
+                                    note="dominant kernel of the step; algorithmic bytes or flops (DESIGN.md 4) / "
+                                         "CUDA-event duration against the measured peak of the nearer roof; traffic = "
+                                         "ncu DRAM bytes per launch from profiles/traffic.json (static, same command)")
         line["rooflines"] = rooflines[:14]
         line["kernel_ms_per_step"] = kernel_ms
     if not args.no_cpu_baseline:
