@@ -365,20 +365,40 @@ def main():
     f_host = torch.empty((n_atoms, 3), dtype=torch.float32).pin_memory()
     d2h = e_host.numel() * 4 + f_host.numel() * 4
 
-    def e2e_step():
-        b = batch_from_host(host, device)
-        out = model(b)
-        e_host.copy_(out["total_energy"], non_blocking=True)
-        f_host.copy_(out["forces"], non_blocking=True)
-        torch.cuda.synchronize()
+    # Two-stage pipeline, as a serving loop would run it: while step k computes on the main stream, the side stream
+    # uploads step k+1's graph from pinned host memory and derives its plan (integer kernels).  Every step's H2D copy,
+    # plan build, model call and D2H of energies + forces happens inside the timed region; the result of step k is on
+    # the host (stream synchronised) before step k+1 is launched.
+    from torch_m3gnet_b200.data.material_graph import get_plan
+
+    main_stream = torch.cuda.current_stream()
+    side = torch.cuda.Stream(device=device)
+
+    def stage_in():
+        with torch.cuda.stream(side):
+            b = batch_from_host(host, device)
+            get_plan(b)
+            ready = torch.cuda.Event()
+            ready.record(side)
+        return b, ready
+
+    def e2e_run(n):
+        nxt = stage_in() if n > 0 else None
+        for k in range(n):
+            b, ready = nxt
+            main_stream.wait_event(ready)
+            out = model(b)
+            e_host.copy_(out["total_energy"], non_blocking=True)
+            f_host.copy_(out["forces"], non_blocking=True)
+            nxt = stage_in() if k + 1 < n else None  # overlaps the kernels of step k
+            main_stream.synchronize()               # step k's energies and forces are on the host
+            del b, out                               # released only after the main stream has finished with them
 
     e2e_steps = 0 if args.no_e2e else args.steps
-    for _ in range(0 if args.no_e2e else 2):
-        e2e_step()
+    e2e_run(0 if args.no_e2e else 2)
     sync_all()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
+    e2e_run(e2e_steps)
     sync_all()
     e2e_s = torch.tensor([max(time.perf_counter() - t0, 1e-9)], device=device)
     if distributed:
@@ -401,7 +421,8 @@ def main():
                 triplets_per_s=n_tri * world * args.steps / (ms_max * 1e-3),
                 clocks=clocks.summary(),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                         note="pinned host graph -> H2D -> plan -> model(batch) -> D2H energies+forces"),
+                         note="pinned host graph -> H2D -> plan -> model(batch) -> D2H energies+forces; the upload + plan of step k+1 "
+                              "overlap the kernels of step k (side stream), every step's copies are inside the timed region"),
                 gpu_launches=int(launches))
     if not args.no_profile:
         rooflines, kernel_ms = profile_pass(model, batch, 2, peaks)
