@@ -66,6 +66,27 @@ __device__ __forceinline__ int stage_members(float4 (*ent)[ENT], int beg, int en
   return n3;
 }
 
+// sum of 9 per-lane values over the warp; returns, in lane l, the total of component 5 b4 + 3 b3 + 2 b2 + b1
+__device__ __forceinline__ float reduce9(const float* v, int lane) {
+  const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+  float a[5];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {  // 9 -> 5: lower half keeps {0..4}, upper half keeps {5..8}
+    const float keep = h4 ? v[5 + i] : v[i], send = h4 ? v[i] : v[5 + i];
+    a[i] = keep + __shfl_xor_sync(FULL, send, 16);
+  }
+  a[4] = (h4 ? 0.0f : v[4]) + __shfl_xor_sync(FULL, h4 ? v[4] : 0.0f, 16);
+  float c[3];  // 5 -> 3: {0,1,2} | {3,4}
+  c[0] = (h3 ? a[3] : a[0]) + __shfl_xor_sync(FULL, h3 ? a[0] : a[3], 8);
+  c[1] = (h3 ? a[4] : a[1]) + __shfl_xor_sync(FULL, h3 ? a[1] : a[4], 8);
+  c[2] = (h3 ? 0.0f : a[2]) + __shfl_xor_sync(FULL, h3 ? a[2] : 0.0f, 8);
+  float d[2];  // 3 -> 2: {0,1} | {2}
+  d[0] = (h2 ? c[2] : c[0]) + __shfl_xor_sync(FULL, h2 ? c[0] : c[2], 4);
+  d[1] = (h2 ? 0.0f : c[1]) + __shfl_xor_sync(FULL, h2 ? c[1] : 0.0f, 4);
+  const float e = (h1 ? d[1] : d[0]) + __shfl_xor_sync(FULL, h1 ? d[0] : d[1], 2);  // 2 -> 1
+  return e + __shfl_xor_sync(FULL, e, 1);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -218,13 +239,15 @@ __global__ void __launch_bounds__(32 * AWARPS) tb_atom_bwd_kernel(
 #pragma unroll
         for (int d = 0; d < AD; ++d)
           part[d] = (du0 * wd[d][0] + du1 * wd[d][1]) + (dg0 * wg[d][0] + dg1 * wg[d][1]);
-#pragma unroll
-        for (int d = 0; d < AD; ++d) part[d] = warp_sum(part[d]);
+        // 9 sums over the 32 lanes with a value-halving butterfly: 12 shuffles instead of 45.  After the five levels
+        // lane l holds the total of component d(l) = 5 b4 + 3 b3 + 2 b2 + b1 (bits of l); fixed tree -> fixed order.
+        const float tot = reduce9(part, lane);
+        const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1;
+        const int dsel = 5 * b4 + 3 * b3 + 2 * b2 + b1;
         __syncwarp();
-        if (lane == 0) {
-          ent[pos][4] = make_float4(part[0], part[1], part[2], part[3]);
-          ent[pos][5] = make_float4(part[4], part[5], part[6], part[7]);
-          ent[pos][3].w = part[8];
+        if (!(lane & 1) && !(b3 & b2) && !(b2 & b1) && dsel < AD) {
+          float* slot = (dsel < 8) ? reinterpret_cast<float*>(&ent[pos][4]) + dsel : &ent[pos][3].w;
+          *slot = tot;
         }
       }
     };
