@@ -259,8 +259,8 @@ int m3g_linear_bwd_input(const float* g, const float* W, const float* base, int6
  * m3g_tc_pack_b writes the hi / lo SWIZZLE_128B operand images of a (rows x cols) row-major weight matrix
  * (rows % 8 == 0, cols % 32 == 0; each image rows*cols floats).  wimg = [W1e hi | W1e lo | W2d hi | W2d lo |
  * W2g hi | W2g lo] with W1e (128 x 64) = rows [dense | gate] of the e-part of layer 1, W2d/W2g (64 x 64), all in
- * the reference's (out,in) orientation.  n_sm = number of SMs (persistent grid).  variant 1 = one tile per CTA at
- * a time (8 warps); variant 2 = two warp groups per CTA ping-pong two tiles over the shared operand buffer.
+ * the reference's (out,in) orientation.  n_sm = number of SMs (persistent grid: two warp groups per CTA ping-pong
+ * two 128-edge tiles; R <= 4).
  * ------------------------------------------------------------------------------------------- */
 int m3g_tc_pack_b(const float* W, int rows, int cols, float* img_hi, float* img_lo, void* stream);
 /* debug: per-phase cycle sums of the backward kernel (HOST buffer of 16 int64; all zero unless the library was built
@@ -275,7 +275,7 @@ int m3g_tc_selftest(const float* A, const float* img_hi, const float* img_lo, in
                     int a_tmem, float* out, void* stream);
 int m3g_conv_tc_fwd(const float* P, int ldp, int po, const int32_t* src, const int32_t* dst, const float* e,
                     const float* h, const float* wimg, const float* b2d, const float* b2g, const float* WhT, int64_t E,
-                    int R, int mode, int passes, int variant, int n_sm, float* y, float* save, void* stream);
+                    int R, int mode, int passes, int n_sm, float* y, float* save, void* stream);
 /* save (optional, variant 4): activations for m3g_conv_tc_bwd_saved — ceil(E / 128) * 128 * 256 floats (1 KB per edge:
  * SiLU'(z1) and the layer-2 pre-activations, in a tile-private fragment-major layout).  With them the backward needs
  * neither the forward weights nor P / e: output adjoint -> two 64x64 adjoint GEMM pairs -> g_e, g_z1, g_h (same outputs
@@ -290,7 +290,7 @@ int m3g_conv_tc_bwd_saved(const int32_t* src, const float* h, const float* wimgT
 int m3g_conv_tc_bwd(const float* P, int ldp, int po, const int32_t* src, const int32_t* dst, const float* e,
                     const float* h, const float* wimg, const float* wimgT, const float* b2d, const float* b2g,
                     const float* WhT, const float* g_up, const float* g_e_base, int64_t E, int R, int mode, int passes,
-                    int variant, int n_sm, float* g_e, float* g_z1, float* g_h, void* stream);
+                    int n_sm, float* g_e, float* g_z1, float* g_h, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * AtomWiseReadout (nn/readout.py:39-58) + virial (nn/gradient.py:39-62)

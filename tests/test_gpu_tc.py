@@ -28,8 +28,10 @@ def test_umma_selftest(device, rows, cols):
             report(f"umma rows={rows} cols={cols} passes={passes} a_tmem={a_tmem}", out, want, 0, tol)
 
 
-@pytest.mark.parametrize("path", ["tc3", "tc1"])
-def test_conv_tc_matches_fma(device, path):
+@pytest.mark.parametrize("path,bwd_variant", [("tc3", 4), ("tc3", 2), ("tc1", 4)])
+def test_conv_tc_matches_fma(device, path, bwd_variant):
+    """tensor-core gated MLPs (backward from saved activations = 4, with the forward recomputed = 2) against the generic
+    fp32 FMA kernels and the live-reference fixture"""
     from torch_m3gnet_b200.data.material_graph import get_plan
     from torch_m3gnet_b200.nn import conv as conv_mod
     from torch_m3gnet_b200.nn.conv import M3GNetConv
@@ -41,8 +43,9 @@ def test_conv_tc_matches_fma(device, path):
     cv = M3GNetConv(3, 64, 64, device=device)
     cv.load_state_dict(state_dict_of(g))
     outs = {}
-    old = conv_mod.CONV_PATH
+    old, old_bwd = conv_mod.CONV_PATH, conv_mod.TC_BWD_VARIANT
     try:
+        conv_mod.TC_BWD_VARIANT = bwd_variant
         for p in ("fma", path):
             conv_mod.CONV_PATH = p
             b["x"] = torch.from_numpy(g["x"]).to(device)
@@ -58,7 +61,7 @@ def test_conv_tc_matches_fma(device, path):
             torch.cuda.synchronize()
             outs[p] = (out["x"].detach().clone(), out["edge_attr"].detach().clone()) + tuple(grads)
     finally:
-        conv_mod.CONV_PATH = old
+        conv_mod.CONV_PATH, conv_mod.TC_BWD_VARIANT = old, old_bwd
     tol = 1e-5 if path == "tc3" else 5e-3
     report(f"conv {path} e_out vs fma", outs[path][1], outs["fma"][1], tol, tol)
     report(f"conv {path} x_out vs fma", outs[path][0], outs["fma"][0], tol * 4, tol)

@@ -233,391 +233,14 @@ constexpr int SMEM_X_BYTES = 2 * TILE_M * TC_F * 4;   // 65536 (hi | lo)
 constexpr int SMEM_MISC_FLOATS = 64 + 64 + M3G_MAX_RADIAL * 64;
 constexpr int SMEM_FWD_BYTES = SMEM_W_BYTES + SMEM_X_BYTES + SMEM_MISC_FLOATS * 4 + 1024;
 
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(ConvTcParams p) {
-  extern __shared__ __align__(1024) char smem_raw[];
-  char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  char* w1_hi = smem;
-  char* w1_lo = w1_hi + IMG_W1 * 4;
-  char* w2d_hi = w1_lo + IMG_W1 * 4;
-  char* w2d_lo = w2d_hi + IMG_W2 * 4;
-  char* w2g_hi = w2d_lo + IMG_W2 * 4;
-  char* w2g_lo = w2g_hi + IMG_W2 * 4;
-  char* x_hi = smem + SMEM_W_BYTES;
-  char* x_lo = x_hi + TILE_M * TC_F * 4;
-  float* b2d_s = reinterpret_cast<float*>(smem + SMEM_W_BYTES + SMEM_X_BYTES);
-  float* b2g_s = b2d_s + 64;
-  float* wh_s = b2g_s + 64;
-  __shared__ uint64_t bar;
-  __shared__ uint32_t tmem_slot;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, hsel = warp >> 2;
-  const int row = 32 * q + lane;
-
-  for (int i = tid; i < WIMG_FLOATS / 4; i += TC_THREADS)
-    reinterpret_cast<float4*>(smem)[i] = reinterpret_cast<const float4*>(p.wimg)[i];
-  if (tid < 64) { b2d_s[tid] = p.b2d[tid]; b2g_s[tid] = p.b2g[tid]; }
-  for (int i = tid; i < p.R * 64; i += TC_THREADS) wh_s[i] = p.WhT[i];
-  if (warp == 0) tmem_alloc<256>(&tmem_slot);
-  if (tid == 0) {
-    mbar_init(&bar, 1);
-    mbar_fence_init();
-  }
-  fence_proxy_async();
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tmem = tmem_slot;
-  const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
-  const uint32_t D1 = 0, D2D = 128, D2G = 192;
-  uint32_t phase = 0;
-  const uint32_t xh = smem_u32(x_hi), xl = smem_u32(x_lo);
-
-  const int64_t n_tiles = (p.E + TILE_M - 1) / TILE_M;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t e0 = tile * TILE_M;
-    // ---- P0: e rows -> X (hi | lo) ----
-#pragma unroll
-    for (int i = 0; i < (TILE_M * TC_F / 4) / TC_THREADS; ++i) {
-      int idx = tid + TC_THREADS * i;
-      int r = idx >> 4, c = idx & 15;
-      int64_t eg = e0 + r;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (eg < p.E) v = __ldg(reinterpret_cast<const float4*>(p.e + eg * TC_F) + c);
-      store_split4(x_hi, x_lo, r, 4 * c, v);
-    }
-    fence_proxy_async();
-    fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      fence_after_sync();
-      issue_gemm(tmem + D1, xh, xl, smem_u32(w1_hi), smem_u32(w1_lo), 128, 64, false, p.passes);
-      commit(&bar);
-    }
-    const int64_t eg = min(e0 + row, p.E - 1);
-    const bool live = (e0 + row) < p.E;
-    const float* Pi = p.P + (int64_t)p.src[eg] * p.ldp + p.po;
-    const float* Pj = p.P + (int64_t)p.dst[eg] * p.ldp + p.po + 128;
-    // ---- P2: dense half of layer 1 -> X ----
-    mbar_wait(&bar, phase); phase ^= 1;
-    fence_after_sync();
-    {
-      float v[32];
-      tmem_ld32(t_lane + D1 + 32 * hsel, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 32; c += 4) {
-        float4 a = __ldg(reinterpret_cast<const float4*>(Pi + 32 * hsel + c));
-        float4 b = __ldg(reinterpret_cast<const float4*>(Pj + 32 * hsel + c));
-        float4 z = make_float4(silu_fast(v[c] + a.x + b.x), silu_fast(v[c + 1] + a.y + b.y),
-                               silu_fast(v[c + 2] + a.z + b.z), silu_fast(v[c + 3] + a.w + b.w));
-        store_split4(x_hi, x_lo, row, 32 * hsel + c, z);
-      }
-    }
-    fence_proxy_async();
-    fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      fence_after_sync();
-      issue_gemm(tmem + D2D, xh, xl, smem_u32(w2d_hi), smem_u32(w2d_lo), 64, 64, false, p.passes);
-      commit(&bar);
-    }
-    // ---- P4: gate half of layer 1 (overlaps GEMM2d), then -> X ----
-    float ag[32];
-    {
-      float v[32];
-      tmem_ld32(t_lane + D1 + 64 + 32 * hsel, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 32; c += 4) {
-        float4 a = __ldg(reinterpret_cast<const float4*>(Pi + 64 + 32 * hsel + c));
-        float4 b = __ldg(reinterpret_cast<const float4*>(Pj + 64 + 32 * hsel + c));
-        ag[c] = silu_fast(v[c] + a.x + b.x);
-        ag[c + 1] = silu_fast(v[c + 1] + a.y + b.y);
-        ag[c + 2] = silu_fast(v[c + 2] + a.z + b.z);
-        ag[c + 3] = silu_fast(v[c + 3] + a.w + b.w);
-      }
-    }
-    mbar_wait(&bar, phase); phase ^= 1;  // GEMM2d has consumed X
-    fence_after_sync();
-#pragma unroll
-    for (int c = 0; c < 32; c += 4)
-      store_split4(x_hi, x_lo, row, 32 * hsel + c, make_float4(ag[c], ag[c + 1], ag[c + 2], ag[c + 3]));
-    fence_proxy_async();
-    fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      fence_after_sync();
-      issue_gemm(tmem + D2G, xh, xl, smem_u32(w2g_hi), smem_u32(w2g_lo), 64, 64, false, p.passes);
-      commit(&bar);
-    }
-    // ---- P6: output stage (dense branch overlaps GEMM2g) ----
-    float sd[32];
-    {
-      float v[32];
-      tmem_ld32(t_lane + D2D + 32 * hsel, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 32; ++c) sd[c] = silu_fast(v[c] + b2d_s[32 * hsel + c]);
-    }
-    float hm[M3G_MAX_RADIAL];
-#pragma unroll
-    for (int m = 0; m < M3G_MAX_RADIAL; ++m) hm[m] = (m < p.R) ? p.h[eg * p.R + m] : 0.0f;
-    mbar_wait(&bar, phase); phase ^= 1;
-    fence_after_sync();
-    {
-      float v[32];
-      tmem_ld32(t_lane + D2G + 32 * hsel, v);
-      tmem_ld_wait();
-      if (live) {
-#pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          float o[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            int col = 32 * hsel + c + u;
-            float s = 0.0f;
-#pragma unroll
-            for (int m = 0; m < M3G_MAX_RADIAL; ++m)
-              if (m < p.R) s += hm[m] * wh_s[m * 64 + col];
-            o[u] = sd[c + u] * sigmoid_fast(v[c + u] + b2g_s[col]) * s;
-          }
-          float4 res = make_float4(o[0], o[1], o[2], o[3]);
-          if (p.mode == 0) {
-            float4 ev = __ldg(reinterpret_cast<const float4*>(p.e + eg * TC_F + 32 * hsel + c));
-            res.x += ev.x; res.y += ev.y; res.z += ev.z; res.w += ev.w;
-          }
-          *reinterpret_cast<float4*>(p.y + eg * TC_F + 32 * hsel + c) = res;
-        }
-      }
-    }
-    fence_before_sync();
-    __syncthreads();  // TMEM and X are free for the next tile
-  }
-  if (warp == 0) tmem_dealloc<256>(tmem);
-}
-
-// --------------------------------------------------------------------------------------------------------
-// Forward, two-group pipeline: 512 threads = 2 groups x 8 warps.  Each group owns a tile of 128 edges and half
-// of TMEM (256 columns); the operand buffer X and the tensor core are shared and handed back and forth in
-// strict alternation  A1 B1 A2 B2 A3 B3 A1' ...  (A1 = group A's GEMM1 window, A2 = GEMM2d, A3 = GEMM2g).
-// While one group's MMAs run, the other group does its epilogue math (TMEM loads, P gathers, SiLU, stores), so
-// global-load latency and ALU work overlap with tensor work.  Hand-off uses one mbarrier per group that
-// receives that group's tcgen05.commit arrivals: a group may write X when the other group's previous window has
-// completed; it reads its own accumulators when its own commit has completed.
-constexpr int TC2_THREADS = 512;
+constexpr int TC2_THREADS = 512;  // two groups of 8 warps
 constexpr int GRP_THREADS = 256;
 
-__global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_fwd_kernel(ConvTcParams p) {
-  extern __shared__ __align__(1024) char smem_raw[];
-  char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  char* w1_hi = smem;
-  char* w1_lo = w1_hi + IMG_W1 * 4;
-  char* w2d_hi = w1_lo + IMG_W1 * 4;
-  char* w2d_lo = w2d_hi + IMG_W2 * 4;
-  char* w2g_hi = w2d_lo + IMG_W2 * 4;
-  char* w2g_lo = w2g_hi + IMG_W2 * 4;
-  char* x_hi = smem + SMEM_W_BYTES;
-  char* x_lo = x_hi + TILE_M * TC_F * 4;
-  float* b2d_s = reinterpret_cast<float*>(smem + SMEM_W_BYTES + SMEM_X_BYTES);
-  float* b2g_s = b2d_s + 64;
-  float* wh_s = b2g_s + 64;
-  __shared__ uint64_t bars[2];
-  __shared__ uint32_t tmem_slot;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int grp = warp >> 3, wg = warp & 7;
-  const int q = wg & 3, hsel = wg >> 2;
-  const int gtid = tid & (GRP_THREADS - 1);
-  const int row = 32 * q + lane;
-  const int c0 = 32 * hsel;
-
-  for (int i = tid; i < WIMG_FLOATS / 4; i += TC2_THREADS)
-    reinterpret_cast<float4*>(smem)[i] = reinterpret_cast<const float4*>(p.wimg)[i];
-  if (tid < 64) { b2d_s[tid] = p.b2d[tid]; b2g_s[tid] = p.b2g[tid]; }
-  for (int i = tid; i < p.R * 64; i += TC2_THREADS) wh_s[i] = p.WhT[i];
-  if (warp == 0) tmem_alloc<512>(&tmem_slot);
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_fence_init();
-  }
-  fence_proxy_async();
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tmem = tmem_slot + grp * 256;
-  const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
-  const uint32_t D1 = 0, D2D = 128, D2G = 192;
-  uint64_t* own = &bars[grp];
-  uint64_t* other = &bars[grp ^ 1];
-  uint32_t own_phase = 0, other_phase = 0;
-  bool skip_wait = (grp == 0);  // the very first window of group 0 has no predecessor
-  const uint32_t xh = smem_u32(x_hi), xl = smem_u32(x_lo);
-  const int bar_id = 1 + grp;
-
-  const int64_t n_tiles = (p.E + TILE_M - 1) / TILE_M;
-  const int64_t per_iter = 2 * (int64_t)gridDim.x;
-  const int64_t n_iter = (n_tiles + per_iter - 1) / per_iter;
-  for (int64_t it = 0; it < n_iter; ++it) {
-    const int64_t tile = (it * gridDim.x + blockIdx.x) * 2 + grp;
-    const bool has_tile = tile < n_tiles;
-    const int64_t e0 = tile * TILE_M;
-    if (!has_tile) {
-      // keep the hand-off protocol going: three empty windows
-      for (int w = 0; w < 3; ++w) {
-        if (skip_wait) skip_wait = false; else { mbar_wait(other, other_phase); other_phase ^= 1; }
-        named_bar_sync(bar_id, GRP_THREADS);
-        if (gtid == 0) commit(own);
-        mbar_wait(own, own_phase); own_phase ^= 1;
-      }
-      continue;
-    }
-    // ---- prefetch the e rows of this tile into registers (coalesced) ----
-    float4 ev[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int idx = gtid + GRP_THREADS * i;
-      int64_t eg_ = min(e0 + (idx >> 4), p.E - 1);
-      ev[i] = __ldg(reinterpret_cast<const float4*>(p.e + eg_ * TC_F) + (idx & 15));
-    }
-    const int64_t eg = min(e0 + row, p.E - 1);
-    const bool live = (e0 + row) < p.E;
-    const float* Pi = p.P + (int64_t)p.src[eg] * p.ldp + p.po;
-    const float* Pj = p.P + (int64_t)p.dst[eg] * p.ldp + p.po + 128;
-    // ---- window 1: X <- e ; GEMM1 ----
-    if (skip_wait) skip_wait = false; else { mbar_wait(other, other_phase); other_phase ^= 1; }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int idx = gtid + GRP_THREADS * i;
-      store_split4(x_hi, x_lo, idx >> 4, 4 * (idx & 15), ev[i]);
-    }
-    fence_proxy_async();
-    fence_before_sync();
-    named_bar_sync(bar_id, GRP_THREADS);
-    if (gtid == 0) {
-      fence_after_sync();
-      issue_gemm(tmem + D1, xh, xl, smem_u32(w1_hi), smem_u32(w1_lo), 128, 64, false, p.passes);
-      commit(own);
-    }
-    // ---- a1 dense -> registers (needs own GEMM1) ----
-    float act[32];
-    mbar_wait(own, own_phase); own_phase ^= 1;
-    fence_after_sync();
-#pragma unroll
-    for (int h2 = 0; h2 < 2; ++h2) {
-      float v[16];
-      tmem_ld16(t_lane + D1 + c0 + 16 * h2, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 16; c += 4) {
-        float4 a = __ldg(reinterpret_cast<const float4*>(Pi + c0 + 16 * h2 + c));
-        float4 b = __ldg(reinterpret_cast<const float4*>(Pj + c0 + 16 * h2 + c));
-        act[16 * h2 + c] = silu_fast(v[c] + a.x + b.x);
-        act[16 * h2 + c + 1] = silu_fast(v[c + 1] + a.y + b.y);
-        act[16 * h2 + c + 2] = silu_fast(v[c + 2] + a.z + b.z);
-        act[16 * h2 + c + 3] = silu_fast(v[c + 3] + a.w + b.w);
-      }
-    }
-    // ---- window 2: X <- a1 dense ; GEMM2d ----
-    mbar_wait(other, other_phase); other_phase ^= 1;
-#pragma unroll
-    for (int c = 0; c < 32; c += 4)
-      store_split4(x_hi, x_lo, row, c0 + c, make_float4(act[c], act[c + 1], act[c + 2], act[c + 3]));
-    fence_proxy_async();
-    fence_before_sync();
-    named_bar_sync(bar_id, GRP_THREADS);
-    if (gtid == 0) {
-      fence_after_sync();
-      issue_gemm(tmem + D2D, xh, xl, smem_u32(w2d_hi), smem_u32(w2d_lo), 64, 64, false, p.passes);
-      commit(own);
-    }
-    // ---- a1 gate -> registers (D1 gate half is already complete) ----
-#pragma unroll
-    for (int h2 = 0; h2 < 2; ++h2) {
-      float v[16];
-      tmem_ld16(t_lane + D1 + 64 + c0 + 16 * h2, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 16; c += 4) {
-        float4 a = __ldg(reinterpret_cast<const float4*>(Pi + 64 + c0 + 16 * h2 + c));
-        float4 b = __ldg(reinterpret_cast<const float4*>(Pj + 64 + c0 + 16 * h2 + c));
-        act[16 * h2 + c] = silu_fast(v[c] + a.x + b.x);
-        act[16 * h2 + c + 1] = silu_fast(v[c + 1] + a.y + b.y);
-        act[16 * h2 + c + 2] = silu_fast(v[c + 2] + a.z + b.z);
-        act[16 * h2 + c + 3] = silu_fast(v[c + 3] + a.w + b.w);
-      }
-    }
-    // ---- window 3: X <- a1 gate ; GEMM2g ----
-    mbar_wait(other, other_phase); other_phase ^= 1;
-    // own GEMM2d precedes the other group's window 2 in the tensor queue, so it has completed too; consume its
-    // phase HERE (before the next commit) — a parity wait that falls two phases behind would never return
-    mbar_wait(own, own_phase); own_phase ^= 1;
-#pragma unroll
-    for (int c = 0; c < 32; c += 4)
-      store_split4(x_hi, x_lo, row, c0 + c, make_float4(act[c], act[c + 1], act[c + 2], act[c + 3]));
-    fence_proxy_async();
-    fence_before_sync();
-    named_bar_sync(bar_id, GRP_THREADS);
-    if (gtid == 0) {
-      fence_after_sync();
-      issue_gemm(tmem + D2G, xh, xl, smem_u32(w2g_hi), smem_u32(w2g_lo), 64, 64, false, p.passes);
-      commit(own);
-    }
-    // ---- output stage ----
-    float hm[M3G_MAX_RADIAL];
-#pragma unroll
-    for (int m = 0; m < M3G_MAX_RADIAL; ++m) hm[m] = (m < p.R) ? p.h[eg * p.R + m] : 0.0f;
-    fence_after_sync();  // GEMM2d: phase consumed in window 3
-#pragma unroll
-    for (int h2 = 0; h2 < 2; ++h2) {
-      float v[16];
-      tmem_ld16(t_lane + D2D + c0 + 16 * h2, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 16; ++c) act[16 * h2 + c] = silu_fast(v[c] + b2d_s[c0 + 16 * h2 + c]);
-    }
-    mbar_wait(own, own_phase); own_phase ^= 1;  // GEMM2g
-    fence_after_sync();
-#pragma unroll
-    for (int h2 = 0; h2 < 2; ++h2) {
-      float v[16];
-      tmem_ld16(t_lane + D2G + c0 + 16 * h2, v);
-      tmem_ld_wait();
-      if (live) {
-#pragma unroll
-        for (int c = 0; c < 16; c += 4) {
-          float o[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            int col = c0 + 16 * h2 + c + u;
-            float sacc = 0.0f;
-#pragma unroll
-            for (int m = 0; m < M3G_MAX_RADIAL; ++m)
-              if (m < p.R) sacc += hm[m] * wh_s[m * 64 + col];
-            o[u] = act[16 * h2 + c + u] * sigmoid_fast(v[c + u] + b2g_s[col]) * sacc;
-          }
-          float4 res = make_float4(o[0], o[1], o[2], o[3]);
-          if (p.mode == 0) {
-            float4 e4 = __ldg(reinterpret_cast<const float4*>(p.e + eg * TC_F + c0 + 16 * h2 + c));
-            res.x += e4.x; res.y += e4.y; res.z += e4.z; res.w += e4.w;
-          }
-          *reinterpret_cast<float4*>(p.y + eg * TC_F + c0 + 16 * h2 + c) = res;
-        }
-      }
-    }
-    fence_before_sync();
-  }
-  fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<512>(tmem_slot);
-}
-
 // --------------------------------------------------------------------------------------------------------
-// Forward, two-group pipeline with COALESCED global traffic (variant 3).
-// The accumulator layout is row-per-lane (tcgen05.ld 32x32b), so a naive epilogue gathers P[dst] and writes y
-// with 32 different cache lines per warp instruction (ncu: the L1 wavefront queue, not the tensor pipe, paced
-// variants 1 and 2).  Here every gather/scatter goes through a private 2 KB per-warp staging buffer:
+// Coalesced global traffic for row-per-lane accumulators.  The accumulator layout is row-per-lane (tcgen05.ld
+// 32x32b), so a naive epilogue gathers P[dst] and writes y with 32 different cache lines per warp instruction (ncu:
+// the L1 wavefront queue, not the tensor pipe, paced the first tcgen05 version).  Every gather / scatter therefore
+// goes through a private 2 KB per-warp staging tile:
 //   P[dst] rows:  coalesced LDG.128 (8 rows x 64 B per instruction, dst indices broadcast by shuffle)
 //                 -> staging (XOR-swizzled 16 B slots, conflict-free both ways) -> row-per-lane LDS.128
 //   y rows:       row-per-lane -> staging -> coalesced STG.128 (+ the residual e rows, read coalesced)
@@ -625,245 +248,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_fwd_kernel(ConvTcPara
 // two source atoms and the load is (nearly) a broadcast.
 constexpr int STG_WARP_BYTES = 32 * 16 * 4;  // 32 rows x 16 floats
 constexpr int TC3_MAX_R = 4;
-constexpr int SMEM_MISC3_BYTES = (64 + 64 + TC3_MAX_R * 64) * 4 + 32;  // biases, Wh^T, 2 mbarriers + TMEM slot
-constexpr int SMEM_FWD3_BYTES = SMEM_W_BYTES + SMEM_X_BYTES + SMEM_MISC3_BYTES + 16 * STG_WARP_BYTES + 1024;
-static_assert(SMEM_FWD3_BYTES <= 232448, "variant-3 forward exceeds the 227 KB shared-memory limit");
 
 // 16-byte slot of (row r, 4-column group c4) in a 32 x 16 float staging tile
 __device__ __forceinline__ uint32_t stg_off(int r, int c4) { return (uint32_t)((r * 4 + (c4 ^ ((r >> 1) & 3))) << 4); }
 
-__global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc3_fwd_kernel(ConvTcParams p) {
-  extern __shared__ __align__(1024) char smem_raw[];
-  char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  char* w1_hi = smem;
-  char* w1_lo = w1_hi + IMG_W1 * 4;
-  char* w2d_hi = w1_lo + IMG_W1 * 4;
-  char* w2d_lo = w2d_hi + IMG_W2 * 4;
-  char* w2g_hi = w2d_lo + IMG_W2 * 4;
-  char* w2g_lo = w2g_hi + IMG_W2 * 4;
-  char* x_hi = smem + SMEM_W_BYTES;
-  char* x_lo = x_hi + TILE_M * TC_F * 4;
-  float* b2d_s = reinterpret_cast<float*>(smem + SMEM_W_BYTES + SMEM_X_BYTES);
-  float* b2g_s = b2d_s + 64;
-  float* wh_s = b2g_s + 64;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wh_s + TC3_MAX_R * 64);
-  uint32_t* tmem_slot_p = reinterpret_cast<uint32_t*>(bars + 2);
-  char* stg_base = smem + SMEM_W_BYTES + SMEM_X_BYTES + SMEM_MISC3_BYTES;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int grp = warp >> 3, wg = warp & 7;
-  const int q = wg & 3, hsel = wg >> 2;
-  const int gtid = tid & (GRP_THREADS - 1);
-  const int row = 32 * q + lane;
-  const int c0 = 32 * hsel;
-  char* stg = stg_base + warp * STG_WARP_BYTES;
-  const int cr = lane >> 2, cc4 = lane & 3;  // coalesced layout: row 8*i + cr, 4-column group cc4
-
-  for (int i = tid; i < WIMG_FLOATS / 4; i += TC2_THREADS)
-    reinterpret_cast<float4*>(smem)[i] = reinterpret_cast<const float4*>(p.wimg)[i];
-  if (tid < 64) { b2d_s[tid] = p.b2d[tid]; b2g_s[tid] = p.b2g[tid]; }
-  for (int i = tid; i < TC3_MAX_R * 64; i += TC2_THREADS) wh_s[i] = (i < p.R * 64) ? p.WhT[i] : 0.0f;
-  if (warp == 0) tmem_alloc<512>(tmem_slot_p);
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_fence_init();
-  }
-  fence_proxy_async();
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot_p;
-  const uint32_t tmem = tmem_base + grp * 256;
-  const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
-  const uint32_t D1 = 0, D2D = 128, D2G = 192;
-  uint64_t* own = &bars[grp];
-  uint64_t* other = &bars[grp ^ 1];
-  uint32_t own_phase = 0, other_phase = 0;
-  bool skip_wait = (grp == 0);  // the very first window of group 0 has no predecessor
-  const uint32_t xh = smem_u32(x_hi), xl = smem_u32(x_lo);
-  const int bar_id = 1 + grp;
-
-  const int64_t n_tiles = (p.E + TILE_M - 1) / TILE_M;
-  const int64_t per_iter = 2 * (int64_t)gridDim.x;
-  const int64_t n_iter = (n_tiles + per_iter - 1) / per_iter;
-  for (int64_t it = 0; it < n_iter; ++it) {
-    const int64_t tile = (it * gridDim.x + blockIdx.x) * 2 + grp;
-    const bool has_tile = tile < n_tiles;
-    const int64_t e0 = tile * TILE_M;
-    if (!has_tile) {
-      // keep the hand-off protocol going: three empty windows
-      for (int w = 0; w < 3; ++w) {
-        if (skip_wait) skip_wait = false; else { mbar_wait(other, other_phase); other_phase ^= 1; }
-        named_bar_sync(bar_id, GRP_THREADS);
-        if (gtid == 0) commit(own);
-        mbar_wait(own, own_phase); own_phase ^= 1;
-      }
-      continue;
-    }
-    // ---- prefetch the e rows of this tile into registers (coalesced: 2 rows x 256 B per warp instruction) ----
-    float4 ev[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int idx = gtid + GRP_THREADS * i;
-      int64_t eg_ = min(e0 + (idx >> 4), p.E - 1);
-      ev[i] = __ldg(reinterpret_cast<const float4*>(p.e + eg_ * TC_F) + (idx & 15));
-    }
-    const int64_t eg = min(e0 + row, p.E - 1);
-    const int d_row = __ldg(p.dst + eg);
-    const float* Pi = p.P + (int64_t)__ldg(p.src + eg) * p.ldp + p.po;
-    // P[dst] row pointers of the four rows this lane serves in the coalesced layout
-    const float* Pj[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      Pj[i] = p.P + (int64_t)__shfl_sync(FULL, d_row, 8 * i + cr) * p.ldp + p.po + 128 + 4 * cc4;
-    float4 pj[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) pj[i] = __ldg(reinterpret_cast<const float4*>(Pj[i] + c0));
-    // ---- window 1: X <- e ; GEMM1 ----
-    if (skip_wait) skip_wait = false; else { mbar_wait(other, other_phase); other_phase ^= 1; }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int idx = gtid + GRP_THREADS * i;
-      store_split4(x_hi, x_lo, idx >> 4, 4 * (idx & 15), ev[i]);
-    }
-    fence_proxy_async();
-    fence_before_sync();
-    named_bar_sync(bar_id, GRP_THREADS);
-    if (gtid == 0) {
-      fence_after_sync();
-      issue_gemm(tmem + D1, xh, xl, smem_u32(w1_hi), smem_u32(w1_lo), 128, 64, false, p.passes);
-      commit(own);
-    }
-    float act[32];
-    // ---- layer-1 activations: four 16-column sub-chunks (dense c0, c0+16 ; gate c0, c0+16) ----
-#pragma unroll
-    for (int sc = 0; sc < 4; ++sc) {
-      const int col = ((sc >> 1) << 6) + c0 + ((sc & 1) << 4);  // column inside the 128-wide z1 row
-      // staging <- P[dst] sub-chunk (coalesced layout), then prefetch the next one
-#pragma unroll
-      for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(stg + stg_off(8 * i + cr, cc4)) = pj[i];
-      if (sc < 3) {
-        const int ncol = (((sc + 1) >> 1) << 6) + c0 + (((sc + 1) & 1) << 4);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) pj[i] = __ldg(reinterpret_cast<const float4*>(Pj[i] + ncol));
-      }
-      float4 pi4[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) pi4[c] = __ldg(reinterpret_cast<const float4*>(Pi + col + 4 * c));
-      __syncwarp();
-      if (sc == 0) {  // own GEMM1
-        mbar_wait(own, own_phase); own_phase ^= 1;
-        fence_after_sync();
-      }
-      float v[16];
-      tmem_ld16(t_lane + D1 + col, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float4 b = *reinterpret_cast<const float4*>(stg + stg_off(lane, c));
-        act[16 * (sc & 1) + 4 * c] = silu_fast(v[4 * c] + pi4[c].x + b.x);
-        act[16 * (sc & 1) + 4 * c + 1] = silu_fast(v[4 * c + 1] + pi4[c].y + b.y);
-        act[16 * (sc & 1) + 4 * c + 2] = silu_fast(v[4 * c + 2] + pi4[c].z + b.z);
-        act[16 * (sc & 1) + 4 * c + 3] = silu_fast(v[4 * c + 3] + pi4[c].w + b.w);
-      }
-      __syncwarp();
-      if (sc & 1) {
-        // ---- window 2 (dense) / window 3 (gate): X <- a1 ; GEMM2 ----
-        mbar_wait(other, other_phase); other_phase ^= 1;
-        if (sc == 3) {
-          // own GEMM2d precedes the other group's window 2 in the tensor queue: complete; consume its phase HERE
-          // (a parity wait that falls two phases behind never returns)
-          mbar_wait(own, own_phase); own_phase ^= 1;
-        }
-#pragma unroll
-        for (int c = 0; c < 32; c += 4)
-          store_split4(x_hi, x_lo, row, c0 + c, make_float4(act[c], act[c + 1], act[c + 2], act[c + 3]));
-        fence_proxy_async();
-        fence_before_sync();
-        named_bar_sync(bar_id, GRP_THREADS);
-        if (gtid == 0) {
-          fence_after_sync();
-          if (sc == 1)
-            issue_gemm(tmem + D2D, xh, xl, smem_u32(w2d_hi), smem_u32(w2d_lo), 64, 64, false, p.passes);
-          else
-            issue_gemm(tmem + D2G, xh, xl, smem_u32(w2g_hi), smem_u32(w2g_lo), 64, 64, false, p.passes);
-          commit(own);
-        }
-      }
-    }
-    // ---- output stage ----
-    float hm[TC3_MAX_R];
-#pragma unroll
-    for (int m = 0; m < TC3_MAX_R; ++m) hm[m] = (m < p.R) ? __ldg(p.h + eg * p.R + m) : 0.0f;
-    fence_after_sync();  // GEMM2d: phase consumed in window 3
-#pragma unroll
-    for (int h2 = 0; h2 < 2; ++h2) {
-      float v[16];
-      tmem_ld16(t_lane + D2D + c0 + 16 * h2, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 16; c += 4) {
-        float4 b = *reinterpret_cast<const float4*>(b2d_s + c0 + 16 * h2 + c);
-        act[16 * h2 + c] = silu_fast(v[c] + b.x);
-        act[16 * h2 + c + 1] = silu_fast(v[c + 1] + b.y);
-        act[16 * h2 + c + 2] = silu_fast(v[c + 2] + b.z);
-        act[16 * h2 + c + 3] = silu_fast(v[c + 3] + b.w);
-      }
-    }
-    mbar_wait(own, own_phase); own_phase ^= 1;  // GEMM2g
-    fence_after_sync();
-#pragma unroll
-    for (int h2 = 0; h2 < 2; ++h2) {
-      const int col = c0 + 16 * h2;
-      // residual rows (mode 0), coalesced layout; issued before the TMEM read so that they overlap it
-      float4 er[4];
-      if (p.mode == 0) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          int64_t er_ = min(e0 + 32 * q + 8 * i + cr, p.E - 1);
-          er[i] = __ldg(reinterpret_cast<const float4*>(p.e + er_ * TC_F + col + 4 * cc4));
-        }
-      }
-      float v[16];
-      tmem_ld16(t_lane + D2G + col, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 16; c += 4) {
-        float4 bg = *reinterpret_cast<const float4*>(b2g_s + col + c);
-        float bgv[4] = {bg.x, bg.y, bg.z, bg.w};
-        float o[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) o[u] = 0.0f;
-#pragma unroll
-        for (int m = 0; m < TC3_MAX_R; ++m) {
-          float4 w4 = *reinterpret_cast<const float4*>(wh_s + m * 64 + col + c);
-          o[0] += hm[m] * w4.x; o[1] += hm[m] * w4.y; o[2] += hm[m] * w4.z; o[3] += hm[m] * w4.w;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) o[u] *= act[16 * h2 + c + u] * sigmoid_fast(v[c + u] + bgv[u]);
-        *reinterpret_cast<float4*>(stg + stg_off(lane, c >> 2)) = make_float4(o[0], o[1], o[2], o[3]);
-      }
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float4 r4 = *reinterpret_cast<const float4*>(stg + stg_off(8 * i + cr, cc4));
-        if (p.mode == 0) { r4.x += er[i].x; r4.y += er[i].y; r4.z += er[i].z; r4.w += er[i].w; }
-        int64_t er_ = e0 + 32 * q + 8 * i + cr;
-        if (er_ < p.E) *reinterpret_cast<float4*>(p.y + er_ * TC_F + col + 4 * cc4) = r4;
-      }
-      __syncwarp();
-    }
-    fence_before_sync();
-  }
-  fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<512>(tmem_base);
-}
-
 // --------------------------------------------------------------------------------------------------------
-// Forward, variant 4 = variant 3 + layer-2 A operands in TENSOR MEMORY.
-// ncu on variant 3: the shared-memory data pipe is ~95 % busy (LSU wavefronts 69 % + tensor-core operand fetch
+// Forward: two groups of 8 warps ping-pong two tiles; layer-2 A operands in TENSOR MEMORY.
+// ncu on the version that staged activations in shared memory: the shared-memory data pipe is ~95 % busy (LSU wavefronts 69 % + tensor-core operand fetch
 // 26 %), so the layer-1 activations no longer round-trip through shared memory: the epilogue threads write their
 // hi / lo split with tcgen05.st into TMEM columns they own (the consumed D1 columns, and the idle D2g columns) and
 // GEMM2d / GEMM2g read A from TMEM ([a_tmem] operand form).  Only the e tile still uses the shared operand buffer X,
@@ -1149,319 +540,16 @@ struct ConvTcBwdParams {
 
 constexpr int SMEM_S_BYTES = 2 * IMG_W2 * 4;  // 32768: one staged 64x64 image pair
 constexpr int TC_BWD_MAX_R = 3;
-constexpr int SMEM_BWD_MISC = TILE_M * TC_BWD_MAX_R * 4 + 16;
-constexpr int SMEM_BWD_BYTES = SMEM_W_BYTES + SMEM_X_BYTES + SMEM_S_BYTES + SMEM_BWD_MISC + 1024;
-static_assert(SMEM_BWD_BYTES <= 232448, "backward kernel exceeds the 227 KB shared-memory limit");
 
 __device__ __forceinline__ float silu_grad_fast(float z) {
   float s = sigmoid_fast(z);
   return s * (1.0f + z * (1.0f - s));
 }
 
-__device__ __forceinline__ void stage_image(char* dst, const float* __restrict__ src, int tid) {
-#pragma unroll
-  for (int i = 0; i < (SMEM_S_BYTES / 16) / TC_THREADS; ++i)
-    reinterpret_cast<float4*>(dst)[tid + TC_THREADS * i] = __ldg(reinterpret_cast<const float4*>(src) + tid + TC_THREADS * i);
-}
-
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_bwd_kernel(ConvTcBwdParams p) {
-  extern __shared__ __align__(1024) char smem_raw[];
-  char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  char* w1_hi = smem;
-  char* w1_lo = w1_hi + IMG_W1 * 4;
-  char* w2d_hi = w1_lo + IMG_W1 * 4;
-  char* w2d_lo = w2d_hi + IMG_W2 * 4;
-  char* w2g_hi = w2d_lo + IMG_W2 * 4;
-  char* w2g_lo = w2g_hi + IMG_W2 * 4;
-  char* x_hi = smem + SMEM_W_BYTES;
-  char* x_lo = x_hi + TILE_M * TC_F * 4;
-  char* s_hi = smem + SMEM_W_BYTES + SMEM_X_BYTES;
-  char* s_lo = s_hi + IMG_W2 * 4;
-  float* gh_s = reinterpret_cast<float*>(smem + SMEM_W_BYTES + SMEM_X_BYTES + SMEM_S_BYTES);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(gh_s + TILE_M * TC_BWD_MAX_R);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, hsel = warp >> 2;
-  const int row = 32 * q + lane;
-  const int R = p.R;
-
-  for (int i = tid; i < WIMG_FLOATS / 4; i += TC_THREADS)
-    reinterpret_cast<float4*>(smem)[i] = reinterpret_cast<const float4*>(p.wimg)[i];
-  if (warp == 0) tmem_alloc<512>(tmem_slot);
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    mbar_fence_init();
-  }
-  fence_proxy_async();
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
-  const uint32_t D1 = 0, D2D = 128, D2G = 192, D3D = 256, D3G = 320, D4 = 384;
-  uint32_t phase = 0;
-  const uint32_t xh = smem_u32(x_hi), xl = smem_u32(x_lo), sh = smem_u32(s_hi), sl = smem_u32(s_lo);
-  const int c0 = 32 * hsel;  // this thread's 32-column slice of every 64-column block
-
-  const int64_t n_tiles = (p.E + TILE_M - 1) / TILE_M;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t e0 = tile * TILE_M;
-    // ---- e rows -> X ; GEMM1 ----
-#pragma unroll
-    for (int i = 0; i < (TILE_M * TC_F / 4) / TC_THREADS; ++i) {
-      int idx = tid + TC_THREADS * i;
-      int r = idx >> 4, c = idx & 15;
-      int64_t eg = e0 + r;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (eg < p.E) v = __ldg(reinterpret_cast<const float4*>(p.e + eg * TC_F) + c);
-      store_split4(x_hi, x_lo, r, 4 * c, v);
-    }
-    fence_proxy_async();
-    fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      fence_after_sync();
-      issue_gemm(tmem + D1, xh, xl, smem_u32(w1_hi), smem_u32(w1_lo), 128, 64, false, p.passes);
-      commit(bar);
-    }
-    const int64_t eg = min(e0 + row, p.E - 1);
-    const bool live = (e0 + row) < p.E;
-    const int s_atom = p.src[eg];
-    const float* Pi = p.P + (int64_t)s_atom * p.ldp + p.po;
-    const float* Pj = p.P + (int64_t)p.dst[eg] * p.ldp + p.po + 128;
-    // ---- a1 dense -> X ; GEMM2d ----
-    mbar_wait(bar, phase); phase ^= 1;
-    fence_after_sync();
-    {
-      float v[32];
-      tmem_ld32(t_lane + D1 + c0, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 32; c += 4) {
-        float4 a = __ldg(reinterpret_cast<const float4*>(Pi + c0 + c));
-        float4 b = __ldg(reinterpret_cast<const float4*>(Pj + c0 + c));
-        store_split4(x_hi, x_lo, row, c0 + c,
-                     make_float4(silu_fast(v[c] + a.x + b.x), silu_fast(v[c + 1] + a.y + b.y),
-                                 silu_fast(v[c + 2] + a.z + b.z), silu_fast(v[c + 3] + a.w + b.w)));
-      }
-    }
-    fence_proxy_async();
-    fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      fence_after_sync();
-      issue_gemm(tmem + D2D, xh, xl, smem_u32(w2d_hi), smem_u32(w2d_lo), 64, 64, false, p.passes);
-      commit(bar);
-    }
-    // ---- a1 gate (regs) ; stage W2d^T ; -> X ; GEMM2g ----
-    float ra[32];
-    {
-      float v[32];
-      tmem_ld32(t_lane + D1 + 64 + c0, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 32; c += 4) {
-        float4 a = __ldg(reinterpret_cast<const float4*>(Pi + 64 + c0 + c));
-        float4 b = __ldg(reinterpret_cast<const float4*>(Pj + 64 + c0 + c));
-        ra[c] = silu_fast(v[c] + a.x + b.x);
-        ra[c + 1] = silu_fast(v[c + 1] + a.y + b.y);
-        ra[c + 2] = silu_fast(v[c + 2] + a.z + b.z);
-        ra[c + 3] = silu_fast(v[c + 3] + a.w + b.w);
-      }
-    }
-    stage_image(s_hi, p.wimgT + 0 * 2 * IMG_W2, tid);  // S is free: the previous tile's last GEMM has completed
-    mbar_wait(bar, phase); phase ^= 1;                 // GEMM2d has consumed X
-    fence_after_sync();
-#pragma unroll
-    for (int c = 0; c < 32; c += 4)
-      store_split4(x_hi, x_lo, row, c0 + c, make_float4(ra[c], ra[c + 1], ra[c + 2], ra[c + 3]));
-    fence_proxy_async();
-    fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      fence_after_sync();
-      issue_gemm(tmem + D2G, xh, xl, smem_u32(w2g_hi), smem_u32(w2g_lo), 64, 64, false, p.passes);
-      commit(bar);
-    }
-    // ---- output-stage adjoint ----
-    float sd[32], dzg[32];
-    {
-      float v[32];
-      tmem_ld32(t_lane + D2D + c0, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        float zd = v[c] + __ldg(p.b2d + c0 + c);
-        sd[c] = silu_fast(zd);
-        ra[c] = silu_grad_fast(zd);  // ra now holds SiLU'(z2d)
-      }
-    }
-    float hm[TC_BWD_MAX_R], ghp[TC_BWD_MAX_R];
-#pragma unroll
-    for (int m = 0; m < TC_BWD_MAX_R; ++m) {
-      hm[m] = (m < R) ? p.h[eg * R + m] : 0.0f;
-      ghp[m] = 0.0f;
-    }
-    const float* gu_row = (p.mode == 0) ? p.g_up + eg * TC_F : p.g_up + (int64_t)s_atom * TC_F;
-    mbar_wait(bar, phase); phase ^= 1;  // GEMM2g done: D2g valid, X free
-    fence_after_sync();
-    {
-      float v[32];
-      tmem_ld32(t_lane + D2G + c0, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 32; c += 4) {
-        float4 gu4 = __ldg(reinterpret_cast<const float4*>(gu_row + c0 + c));
-        float gu[4] = {gu4.x, gu4.y, gu4.z, gu4.w};
-        float dzd[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          int col = c0 + c + u;
-          float sg = sigmoid_fast(v[c + u] + __ldg(p.b2g + col));
-          float s = 0.0f;
-          float wh[TC_BWD_MAX_R];
-#pragma unroll
-          for (int m = 0; m < TC_BWD_MAX_R; ++m) {
-            wh[m] = (m < R) ? __ldg(p.WhT + m * 64 + col) : 0.0f;
-            s += hm[m] * wh[m];
-          }
-          float gs = gu[u] * sd[c + u] * sg;
-#pragma unroll
-          for (int m = 0; m < TC_BWD_MAX_R; ++m) ghp[m] += gs * wh[m];
-          float gphi = gu[u] * s;
-          dzd[u] = gphi * sg * ra[c + u];
-          dzg[c + u] = gphi * sd[c + u] * sg * (1.0f - sg);
-        }
-        store_split4(x_hi, x_lo, row, c0 + c, make_float4(dzd[0], dzd[1], dzd[2], dzd[3]));
-      }
-    }
-    if (hsel == 1) {
-#pragma unroll
-      for (int m = 0; m < TC_BWD_MAX_R; ++m) gh_s[row * TC_BWD_MAX_R + m] = ghp[m];
-    }
-    fence_proxy_async();
-    fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      fence_after_sync();
-      issue_gemm(tmem + D3D, xh, xl, sh, sl, 64, 64, false, p.passes);  // da1d = dz2d · W2d  (B = image of W2d^T)
-      commit(bar);
-    }
-    if (hsel == 0 && live) {
-#pragma unroll
-      for (int m = 0; m < TC_BWD_MAX_R; ++m)
-        if (m < R) p.g_h[eg * R + m] += ghp[m] + gh_s[row * TC_BWD_MAX_R + m];
-    }
-    // ---- GEMM3g ----
-    mbar_wait(bar, phase); phase ^= 1;  // GEMM3d done: X and S free
-    fence_after_sync();
-    stage_image(s_hi, p.wimgT + 1 * 2 * IMG_W2, tid);
-#pragma unroll
-    for (int c = 0; c < 32; c += 4)
-      store_split4(x_hi, x_lo, row, c0 + c, make_float4(dzg[c], dzg[c + 1], dzg[c + 2], dzg[c + 3]));
-    fence_proxy_async();
-    fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      fence_after_sync();
-      issue_gemm(tmem + D3G, xh, xl, sh, sl, 64, 64, false, p.passes);
-      commit(bar);
-    }
-    // dz1 dense = da1d * SiLU'(z1 dense)   (overlaps GEMM3g)
-    {
-      float v[32], z[32];
-      tmem_ld32(t_lane + D3D + c0, v);
-      tmem_ld32(t_lane + D1 + c0, z);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 32; c += 4) {
-        float4 a = __ldg(reinterpret_cast<const float4*>(Pi + c0 + c));
-        float4 b = __ldg(reinterpret_cast<const float4*>(Pj + c0 + c));
-        sd[c] = v[c] * silu_grad_fast(z[c] + a.x + b.x);
-        sd[c + 1] = v[c + 1] * silu_grad_fast(z[c + 1] + a.y + b.y);
-        sd[c + 2] = v[c + 2] * silu_grad_fast(z[c + 2] + a.z + b.z);
-        sd[c + 3] = v[c + 3] * silu_grad_fast(z[c + 3] + a.w + b.w);
-        if (live)
-          *reinterpret_cast<float4*>(p.g_z1 + eg * 128 + c0 + c) = make_float4(sd[c], sd[c + 1], sd[c + 2], sd[c + 3]);
-      }
-    }
-    // ---- GEMM4a ----
-    mbar_wait(bar, phase); phase ^= 1;  // GEMM3g done
-    fence_after_sync();
-    stage_image(s_hi, p.wimgT + 2 * 2 * IMG_W2, tid);
-#pragma unroll
-    for (int c = 0; c < 32; c += 4)
-      store_split4(x_hi, x_lo, row, c0 + c, make_float4(sd[c], sd[c + 1], sd[c + 2], sd[c + 3]));
-    fence_proxy_async();
-    fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      fence_after_sync();
-      issue_gemm(tmem + D4, xh, xl, sh, sl, 64, 64, false, p.passes);  // g_e = dz1d · W1e[dense rows]
-      commit(bar);
-    }
-    // dz1 gate (overlaps GEMM4a)
-    {
-      float v[32], z[32];
-      tmem_ld32(t_lane + D3G + c0, v);
-      tmem_ld32(t_lane + D1 + 64 + c0, z);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 32; c += 4) {
-        float4 a = __ldg(reinterpret_cast<const float4*>(Pi + 64 + c0 + c));
-        float4 b = __ldg(reinterpret_cast<const float4*>(Pj + 64 + c0 + c));
-        sd[c] = v[c] * silu_grad_fast(z[c] + a.x + b.x);
-        sd[c + 1] = v[c + 1] * silu_grad_fast(z[c + 1] + a.y + b.y);
-        sd[c + 2] = v[c + 2] * silu_grad_fast(z[c + 2] + a.z + b.z);
-        sd[c + 3] = v[c + 3] * silu_grad_fast(z[c + 3] + a.w + b.w);
-        if (live)
-          *reinterpret_cast<float4*>(p.g_z1 + eg * 128 + 64 + c0 + c) = make_float4(sd[c], sd[c + 1], sd[c + 2], sd[c + 3]);
-      }
-    }
-    // ---- GEMM4b ----
-    mbar_wait(bar, phase); phase ^= 1;  // GEMM4a done
-    fence_after_sync();
-    stage_image(s_hi, p.wimgT + 3 * 2 * IMG_W2, tid);
-#pragma unroll
-    for (int c = 0; c < 32; c += 4)
-      store_split4(x_hi, x_lo, row, c0 + c, make_float4(sd[c], sd[c + 1], sd[c + 2], sd[c + 3]));
-    fence_proxy_async();
-    fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      fence_after_sync();
-      issue_gemm(tmem + D4, xh, xl, sh, sl, 64, 64, true, p.passes);  // += dz1g · W1e[gate rows]
-      commit(bar);
-    }
-    // ---- g_e ----
-    mbar_wait(bar, phase); phase ^= 1;
-    fence_after_sync();
-    {
-      float v[32];
-      tmem_ld32(t_lane + D4 + c0, v);
-      tmem_ld_wait();
-      if (live) {
-#pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          float4 r4 = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-          if (p.g_e_base) {
-            float4 b4 = __ldg(reinterpret_cast<const float4*>(p.g_e_base + eg * TC_F + c0 + c));
-            r4.x += b4.x; r4.y += b4.y; r4.z += b4.z; r4.w += b4.w;
-          }
-          *reinterpret_cast<float4*>(p.g_e + eg * TC_F + c0 + c) = r4;
-        }
-      }
-    }
-    fence_before_sync();
-    __syncthreads();
-  }
-  if (warp == 0) tmem_dealloc<512>(tmem);
-}
 
 // --------------------------------------------------------------------------------------------------------
-// Backward, variant 2.  One persistent CTA per SM, 16 warps (4 threads per edge row, 16-column slices), one
-// 128-edge tile in flight; what changed against conv_tc_bwd_kernel (ncu: L1 wavefront queue + exposed latency):
+// Backward with the forward RECOMPUTED (used when no saved activations exist; M3G_TC_BWD_VARIANT=2).  One persistent
+// CTA per SM, 16 warps (4 threads per edge row, 16-column slices), one 128-edge tile in flight:
 //  * EVERY A operand lives in tensor memory: the epilogue threads write hi / lo splits with tcgen05.st into columns
 //    they own, so no activation / adjoint tile round-trips through shared memory and the tensor core only fetches B
 //    from shared memory.  The layer-1 SiLU derivative is stashed in the D1 columns for the later dz1 stage.
@@ -2253,59 +1341,23 @@ int m3g_tc_selftest(const float* A, const float* img_hi, const float* img_lo, in
 
 int m3g_conv_tc_fwd(const float* P, int ldp, int po, const int32_t* src, const int32_t* dst, const float* e,
                     const float* h, const float* wimg, const float* b2d, const float* b2g, const float* WhT, int64_t E,
-                    int R, int mode, int passes, int variant, int n_sm, float* y, float* save, void* stream) {
+                    int R, int mode, int passes, int n_sm, float* y, float* save, void* stream) {
   if (E == 0) return M3G_OK;
-  M3G_REQUIRE(!save || (variant == 4 && R <= TC3_MAX_R), "m3g_conv_tc_fwd: activations are only saved by variant 4");
   M3G_REQUIRE(P && src && dst && e && h && wimg && b2d && b2g && WhT && y, "m3g_conv_tc_fwd: null pointer");
-  M3G_REQUIRE(R >= 1 && R <= M3G_MAX_RADIAL, "m3g_conv_tc_fwd: R=%d unsupported", R);
+  M3G_REQUIRE(R >= 1 && R <= TC3_MAX_R, "m3g_conv_tc_fwd: R=%d unsupported (max %d)", R, TC3_MAX_R);
   M3G_REQUIRE(passes == 1 || passes == 3, "m3g_conv_tc_fwd: passes must be 1 or 3");
   M3G_REQUIRE(ldp % 4 == 0 && po % 4 == 0, "m3g_conv_tc_fwd: P rows must be 16-byte aligned");
   cudaError_t err =
-      cudaFuncSetAttribute(conv_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD_BYTES);
+      cudaFuncSetAttribute(conv_tc4_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD4_BYTES);
   if (err != cudaSuccess) {
     set_error("m3g_conv_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     return M3G_ERR_CUDA;
   }
   ConvTcParams p{P, ldp, po, src, dst, e, h, wimg, b2d, b2g, WhT, E, R, mode, passes, y, save};
   int64_t n_tiles = (E + TILE_M - 1) / TILE_M;
-  if (variant == 4 && R <= TC3_MAX_R) {
-    err = cudaFuncSetAttribute(conv_tc4_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD4_BYTES);
-    if (err != cudaSuccess) {
-      set_error("m3g_conv_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
-      return M3G_ERR_CUDA;
-    }
-    int64_t pairs = (n_tiles + 1) / 2;
-    unsigned grid4 = (unsigned)((pairs < n_sm) ? pairs : n_sm);
-    conv_tc4_fwd_kernel<<<grid4, TC2_THREADS, SMEM_FWD4_BYTES, as_stream(stream)>>>(p);
-    M3G_LAUNCH_CHECK("m3g_conv_tc_fwd");
-    return M3G_OK;
-  }
-  if (variant == 3 && R <= TC3_MAX_R) {
-    err = cudaFuncSetAttribute(conv_tc3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD3_BYTES);
-    if (err != cudaSuccess) {
-      set_error("m3g_conv_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
-      return M3G_ERR_CUDA;
-    }
-    int64_t pairs = (n_tiles + 1) / 2;
-    unsigned grid3 = (unsigned)((pairs < n_sm) ? pairs : n_sm);
-    conv_tc3_fwd_kernel<<<grid3, TC2_THREADS, SMEM_FWD3_BYTES, as_stream(stream)>>>(p);
-    M3G_LAUNCH_CHECK("m3g_conv_tc_fwd");
-    return M3G_OK;
-  }
-  if (variant == 2) {
-    err = cudaFuncSetAttribute(conv_tc2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD_BYTES);
-    if (err != cudaSuccess) {
-      set_error("m3g_conv_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
-      return M3G_ERR_CUDA;
-    }
-    int64_t pairs = (n_tiles + 1) / 2;
-    unsigned grid2 = (unsigned)((pairs < n_sm) ? pairs : n_sm);
-    conv_tc2_fwd_kernel<<<grid2, TC2_THREADS, SMEM_FWD_BYTES, as_stream(stream)>>>(p);
-    M3G_LAUNCH_CHECK("m3g_conv_tc_fwd");
-    return M3G_OK;
-  }
-  unsigned grid = (unsigned)((n_tiles < n_sm) ? n_tiles : n_sm);
-  conv_tc_fwd_kernel<<<grid, TC_THREADS, SMEM_FWD_BYTES, as_stream(stream)>>>(p);
+  int64_t pairs = (n_tiles + 1) / 2;
+  unsigned grid = (unsigned)((pairs < n_sm) ? pairs : n_sm);
+  conv_tc4_fwd_kernel<<<grid, TC2_THREADS, SMEM_FWD4_BYTES, as_stream(stream)>>>(p);
   M3G_LAUNCH_CHECK("m3g_conv_tc_fwd");
   return M3G_OK;
 }
@@ -2334,7 +1386,7 @@ int m3g_conv_tc_bwd_saved(const int32_t* src, const float* h, const float* wimgT
 int m3g_conv_tc_bwd(const float* P, int ldp, int po, const int32_t* src, const int32_t* dst, const float* e,
                     const float* h, const float* wimg, const float* wimgT, const float* b2d, const float* b2g,
                     const float* WhT, const float* g_up, const float* g_e_base, int64_t E, int R, int mode, int passes,
-                    int variant, int n_sm, float* g_e, float* g_z1, float* g_h, void* stream) {
+                    int n_sm, float* g_e, float* g_z1, float* g_h, void* stream) {
   if (E == 0) return M3G_OK;
   M3G_REQUIRE(P && src && dst && e && h && wimg && wimgT && b2d && b2g && WhT && g_up && g_e && g_z1 && g_h,
               "m3g_conv_tc_bwd: null pointer");
@@ -2342,7 +1394,7 @@ int m3g_conv_tc_bwd(const float* P, int ldp, int po, const int32_t* src, const i
   M3G_REQUIRE(passes == 1 || passes == 3, "m3g_conv_tc_bwd: passes must be 1 or 3");
   M3G_REQUIRE(ldp % 4 == 0 && po % 4 == 0, "m3g_conv_tc_bwd: P rows must be 16-byte aligned");
   cudaError_t err =
-      cudaFuncSetAttribute(conv_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES);
+      cudaFuncSetAttribute(conv_tc_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD2_BYTES);
   if (err != cudaSuccess) {
     set_error("m3g_conv_tc_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     return M3G_ERR_CUDA;
@@ -2351,17 +1403,7 @@ int m3g_conv_tc_bwd(const float* P, int ldp, int po, const int32_t* src, const i
                     g_e, g_z1, g_h};
   int64_t n_tiles = (E + TILE_M - 1) / TILE_M;
   unsigned grid = (unsigned)((n_tiles < n_sm) ? n_tiles : n_sm);
-  if (variant == 2) {
-    err = cudaFuncSetAttribute(conv_tc_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD2_BYTES);
-    if (err != cudaSuccess) {
-      set_error("m3g_conv_tc_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
-      return M3G_ERR_CUDA;
-    }
-    conv_tc_bwd2_kernel<<<grid, TCB2_THREADS, SMEM_BWD2_BYTES, as_stream(stream)>>>(p);
-    M3G_LAUNCH_CHECK("m3g_conv_tc_bwd");
-    return M3G_OK;
-  }
-  conv_tc_bwd_kernel<<<grid, TC_THREADS, SMEM_BWD_BYTES, as_stream(stream)>>>(p);
+  conv_tc_bwd2_kernel<<<grid, TCB2_THREADS, SMEM_BWD2_BYTES, as_stream(stream)>>>(p);
   M3G_LAUNCH_CHECK("m3g_conv_tc_bwd");
   return M3G_OK;
 }

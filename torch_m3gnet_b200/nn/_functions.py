@@ -28,12 +28,6 @@ def tb_path() -> str:
     return interaction.TB_PATH
 
 
-def tc_variant() -> int:
-    from torch_m3gnet_b200.nn import conv
-
-    return conv.TC_VARIANT
-
-
 def tc_bwd_variant() -> int:
     from torch_m3gnet_b200.nn import conv
 
@@ -226,17 +220,17 @@ class ConvFn(Function):
         ed, nd = w["edge"], w["node"]
         path = conv_path()
         save_e = save_n = None
-        if F == 64 and "wimg" in ed and path in ("tc3", "tc1"):
+        if F == 64 and "wimg" in ed and path in ("tc3", "tc1") and R <= 4:
             passes = 3 if path == "tc3" else 1
             n_sm = sm_count(x.device)
-            if tc_variant() == 4 and tc_bwd_variant() == 4 and R <= 3 and any(ctx.needs_input_grad[:3]):
+            if tc_bwd_variant() == 4 and R <= 3 and any(ctx.needs_input_grad[:3]):
                 # activations for the backward (1 KB per edge and MLP): SiLU'(z1) and the layer-2 pre-activations
                 n_save = ((E + 127) // 128) * 128 * 256
                 save_e, save_n = _empty((n_save,), x), _empty((n_save,), x)
             call("conv_tc_fwd", P, 8 * F, 0, plan.src, plan.dst, e, h, ed["wimg"], ed["b2d"], ed["b2g"], ed["WhT"], E, R,
-                 0, passes, tc_variant(), n_sm, e2, save_e)
+                 0, passes, n_sm, e2, save_e)
             call("conv_tc_fwd", P, 8 * F, 4 * F, plan.src, plan.dst, e2, h, nd["wimg"], nd["b2d"], nd["b2g"], nd["WhT"],
-                 E, R, 1, passes, tc_variant(), n_sm, msg, save_n)
+                 E, R, 1, passes, n_sm, msg, save_n)
         else:
             call("conv_mlp_fwd", P, 8 * F, 0, plan.src, plan.dst, e, h, ed["W1eT"], ed["W2dT"], ed["b2d"], ed["W2gT"],
                  ed["b2g"], ed["WhT"], E, F, R, 0, e2)
@@ -278,9 +272,9 @@ class ConvFn(Function):
             passes = 3 if path == "tc3" else 1
             n_sm = sm_count(x.device)
             call("conv_tc_bwd", P, 8 * F, 4 * F, plan.src, plan.dst, e2, h, nd["wimg"], nd["wimgT"], nd["b2d"], nd["b2g"],
-                 nd["WhT"], g_x2, g_e2, E, R, 1, passes, tc_bwd_variant(), n_sm, ge2, gz_node, g_h)
+                 nd["WhT"], g_x2, g_e2, E, R, 1, passes, n_sm, ge2, gz_node, g_h)
             call("conv_tc_bwd", P, 8 * F, 0, plan.src, plan.dst, e, h, ed["wimg"], ed["wimgT"], ed["b2d"], ed["b2g"],
-                 ed["WhT"], ge2, ge2, E, R, 0, passes, tc_bwd_variant(), n_sm, g_e, gz_edge, g_h)
+                 ed["WhT"], ge2, ge2, E, R, 0, passes, n_sm, g_e, gz_edge, g_h)
         else:
             call("conv_mlp_bwd", P, 8 * F, 4 * F, plan.src, plan.dst, e2, h, nd["W1eT"], nd["W2dT"], nd["b2d"],
                  nd["W2gT"], nd["b2g"], nd["WhT"], nd["W1e"], nd["W2d"], nd["W2g"], nd["Wh"], g_x2, g_e2, E, F, R, 1,

@@ -14,12 +14,8 @@ from torch_m3gnet_b200.nn.core import GatedMLP
 
 # "tc3": tcgen05 3xTF32 (fp32-faithful, default for F = 64 on CUDA), "tc1": plain TF32, "fma": generic fp32 kernels
 CONV_PATH = os.environ.get("M3G_CONV_PATH", "tc3")
-# 1: one 128-edge tile per CTA at a time; 2: two warp groups ping-pong two tiles; 3: 2 + coalesced gathers through
-# per-warp staging (csrc/conv_tc.cu)
-TC_VARIANT = int(os.environ.get("M3G_TC_VARIANT", "4"))
-# backward: 1 = one tile per CTA through shared operand buffers; 2 = all A operands in tensor memory, coalesced
-# traffic, bulk-copied transposed weight images; 4 = no recompute: the forward (variant 4) leaves SiLU'(z1) and the
-# layer-2 pre-activations behind (1 KB per edge and MLP) and the backward runs only the adjoint GEMMs (csrc/conv_tc.cu)
+# backward of the tensor-core gated MLPs: 4 = from the activations the forward leaves behind (SiLU'(z1) and the layer-2
+# pre-activations, 1 KB per edge and MLP; default); 2 = forward recomputed inside the backward kernel (no extra memory)
 TC_BWD_VARIANT = int(os.environ.get("M3G_TC_BWD_VARIANT", "4"))
 
 
