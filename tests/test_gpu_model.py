@@ -196,3 +196,27 @@ def test_length_and_energy_scale(device):
     report("scaled.energy", out["total_energy"], ref["total_energy"], 32 * 1e-5, 0)
     report("scaled.forces", out["forces"], ref["forces"], 1e-6, 1e-3)
     report("scaled.elemental", out["elemental_energies"], ref["elemental_energies"], 0, 0)
+
+
+def test_cuda_graph_replay_matches_eager(device):
+    """GraphedStep (CUDA-graph replay of forward + adjoint kernels on a fixed graph) reproduces the eager call, also
+    after the positions were changed in the static buffer (neighbour list kept, as between Verlet rebuilds)."""
+    from torch_m3gnet_b200.graphed import GraphedStep
+
+    g = golden("c1_default")
+    sd = {k: (v * 3 if k.endswith("weight") else v) for k, v in state_dict_of(g).items()}
+    model = _default_model(device, sd)
+    b = to_batch(graph_dict(g), device)
+    step = GraphedStep(model, b)
+    out = step()
+    ref = model(to_batch(graph_dict(g), device))
+    assert torch.equal(out["total_energy"], ref["total_energy"]) and torch.equal(out["forces"], ref["forces"])
+    torch.manual_seed(1)
+    new_pos = ref["pos"] + 0.01 * torch.randn_like(ref["pos"])
+    out = step(pos=new_pos)
+    b2 = to_batch(graph_dict(g), device)
+    b2["pos"] = new_pos.clone()
+    ref2 = model(b2)
+    assert not torch.equal(ref2["forces"], ref["forces"])
+    report("graphed.E", out["total_energy"], ref2["total_energy"], 1e-6, 1e-6)
+    report("graphed.F", out["forces"], ref2["forces"], 1e-6, 1e-5)
