@@ -126,7 +126,7 @@ def batch_from_host(host, device):
 TRAFFIC_KERNEL = {
     "conv_tc_bwd": "conv_tc_bwd2_kernel", "conv_tc_bwd_saved": "conv_tc_bwds_kernel",
     "conv_tc_fwd": "conv_tc4_fwd_kernel", "tb_atom_fwd": "tb_atom_fwd_kernel",
-    "tb_atom_bwd": "tb_atom_bwd_kernel", "conv_gather_gz": "conv_gather_gz_kernel",
+    "tb_atom_bwd": "tb_atom_bwd_kernel", "conv_gather_gz": "conv_gather_gz128_kernel",
     "segment_sum_add": "segment_sum_add_kernel", "tb_sigma_fwd": "tb_sigma_fwd_kernel",
     "tb_sigma_bwd": "tb_sigma_bwd_kernel", "tb_edge_basis_fwd": "tb_edge_basis_fwd_kernel<3, 3>",
     "tb_edge_basis_bwd": "tb_edge_basis_bwd_kernel<3, 3>",

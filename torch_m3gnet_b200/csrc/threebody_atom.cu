@@ -20,7 +20,7 @@ constexpr int AD = 9;     // D = 3 x 3
 constexpr int AF = 64;    // feature width
 constexpr int ACAP = 96;  // member bonds per atom held in shared memory
 constexpr int AWARPS = 4;
-constexpr int ENT = 6;    // float4 per entry: [v.xyz, r] [c, b0..b2] [b3..b6] [b7, b8, eidx, -] [q0..q3] [q4..q7] + q8 in slot 3.w
+constexpr int ENT = 6;    // float4 per entry: [u.xyz (unit vector), r] [c, b0..b2] [b3..b6] [b7, b8, eidx, q8] [q0..q3] [q4..q7]
 
 __device__ __constant__ float kY[3] = {0.28209479177387814f, 0.4886025119029199f, 0.6307831305050401f};
 
@@ -45,7 +45,8 @@ __device__ __forceinline__ int stage_members(float4 (*ent)[ENT], int beg, int en
       float bb[AD];
 #pragma unroll
       for (int d = 0; d < AD; ++d) bb[d] = __ldg(b + d);
-      ent[pos][0] = v;
+      const float ir = 1.0f / v.w;  // unit bond vector: the pair loops need cos = u_j . u_k only (no division inside)
+      ent[pos][0] = make_float4(v.x * ir, v.y * ir, v.z * ir, v.w);
       ent[pos][1] = make_float4(cutoff_poly(v.w, r3), bb[0], bb[1], bb[2]);
       ent[pos][2] = make_float4(bb[3], bb[4], bb[5], bb[6]);
       float q8 = 0.0f;
@@ -127,8 +128,7 @@ __global__ void __launch_bounds__(32 * AWARPS) tb_atom_fwd_kernel(
       for (int k = 0; k < n3; ++k) {
         if (k == j) continue;
         const float4 v2 = ent[k][0], p1 = ent[k][1], p2 = ent[k][2], p3 = ent[k][3];
-        const float dot = __fadd_rn(__fadd_rn(__fmul_rn(v1.x, v2.x), __fmul_rn(v1.y, v2.y)), __fmul_rn(v1.z, v2.z));
-        const float cs = fminf(fmaxf(__fdiv_rn(dot, __fmul_rn(v1.w, v2.w)), -1.0f), 1.0f);
+        const float cs = fminf(fmaxf(v1.x * v2.x + v1.y * v2.y + v1.z * v2.z, -1.0f), 1.0f);
         const float y0 = kY[0], y1 = kY[1] * cs, y2 = kY[2] * ((3.0f * cs * cs - 1.0f) * 0.5f);
         acc[0] += y0 * p1.y; acc[1] += y0 * p1.z; acc[2] += y0 * p1.w;
         acc[3] += y1 * p2.x; acc[4] += y1 * p2.y; acc[5] += y1 * p2.z;
@@ -277,8 +277,7 @@ __global__ void __launch_bounds__(32 * AWARPS) tb_atom_bwd_kernel(
         const float cp = p1.x;
         const float b[AD] = {p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w, p3.x, p3.y};
         const float q[AD] = {q0.x, q0.y, q0.z, q0.w, q4.x, q4.y, q4.z, q4.w, p3.w};
-        const float inv = 1.0f / (ve.w * vp.w);
-        const float craw = (ve.x * vp.x + ve.y * vp.y + ve.z * vp.z) * inv;
+        const float craw = ve.x * vp.x + ve.y * vp.y + ve.z * vp.z;  // unit vectors
         const bool inside = (craw >= -1.0f) && (craw <= 1.0f);
         const float cs = fminf(fmaxf(craw, -1.0f), 1.0f);
         const float y0 = kY[0], y1 = kY[1] * cs, y2 = kY[2] * ((3.0f * cs * cs - 1.0f) * 0.5f);
@@ -298,13 +297,14 @@ __global__ void __launch_bounds__(32 * AWARPS) tb_atom_bwd_kernel(
         const float goA1 = kY[1] * ce * s1, goA2 = kY[2] * ce * s2;
         const float goB1 = kY[1] * cp * t1, goB2 = kY[2] * cp * t2;
         const float gcos = goA1 + goA2 * (2.0f * cs + cs * goA2) + goB1 + goB2 * (2.0f * cs + cs * goB2);
-        if (inside) {
-          const float w = gcos * inv;
-          gx += w * vp.x; gy += w * vp.y; gz += w * vp.z;
-          gr -= gcos * craw / ve.w;
+        if (inside) {  // d cos / d v_j = (u_k - cos u_j) / r_j ; the 1 / r_j factors are applied after the loop
+          gx += gcos * vp.x; gy += gcos * vp.y; gz += gcos * vp.z;
+          gr -= gcos * craw;
         }
       }
-      gr += gc * cutoff_poly_grad(ve.w, r3);
+      const float ire = 1.0f / ve.w;
+      gx *= ire; gy *= ire; gz *= ire;
+      gr = gr * ire + gc * cutoff_poly_grad(ve.w, r3);
       const int e = __float_as_int(e3.z);
       g_vec4[e] = make_float4(gx, gy, gz, gr);
       float* gb = g_bas + (int64_t)e * AD;
