@@ -1,4 +1,5 @@
-"""Dev tool: per-phase cycle breakdown of the backward gated-MLP kernel (library built with -DM3G_TC_TIMING).
+"""Dev tool: per-phase cycle breakdown of the saved-activation backward gated-MLP kernel, thread 0 of every CTA
+(library built with -DM3G_TC_TIMING; the recompute variant carries its own marks: M3G_TC_BWD_VARIANT=2).
 
   M3G_EXTRA_NVCC_FLAGS=-DM3G_TC_TIMING python -m torch_m3gnet_b200.csrc.build -f && python tools/tc_timing.py
 """
@@ -13,8 +14,8 @@ import bench  # noqa: E402
 import torch_m3gnet_b200 as m3g  # noqa: E402
 from torch_m3gnet_b200 import _lib  # noqa: E402
 
-NAMES = ["loop", "T1 e->TMEM", "issue G1", "wait G1", "T3 act", "issue G2", "wait G2", "T5 adjoint", "issue G3",
-         "wait G3", "T6 dz1", "issue G4", "wait G4", "T7 out", "T2/T4 gathers", "pre-wait G3/G4"]
+NAMES = ["loop+prefetch", "T0 loads (z2, g_up, h)", "T5 adjoint math + TMEM st", "T5 barrier", "issue G3", "g_h + stash loads",
+         "wait G3", "-", "T6 dz1 + TMEM st", "T6 barrier", "issue G4", "g_z1 stores", "wait G4", "T7 g_e stores", "-", "-"]
 
 
 def main():
@@ -36,7 +37,7 @@ def main():
     n_tiles = (batch._plan.E + 127) // 128
     per_tile = [v / (steps * 6 * n_tiles) for v in vals]  # 6 backward launches per step
     tot = sum(per_tile)
-    order = [0, 1, 2, 14, 3, 4, 5, 6, 7, 8, 15, 9, 10, 11, 12, 13]
+    order = [0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 11, 12, 13]
     for k in order:
         print(f"{NAMES[k]:>16s} {per_tile[k]:9.0f} cyc/tile {100 * per_tile[k] / max(tot, 1):5.1f}%")
     print(f"{'total':>16s} {tot:9.0f} cyc/tile")

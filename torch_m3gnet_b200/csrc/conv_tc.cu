@@ -1026,7 +1026,11 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
 
   const int64_t n_tiles = (p.E + TILE_M - 1) / TILE_M;
   uint32_t par = 0;
+#ifdef M3G_TC_TIMING
+  long long tct_prev = clock64();
+#endif
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, par ^= 1) {
+    TCT(0);
     const int64_t e0 = tile * TILE_M;
     const int64_t eg = min(e0 + row, p.E - 1);
     const bool live = (e0 + row) < p.E;
@@ -1092,6 +1096,7 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
       hm[m] = (m < R) ? __ldg(p.h + eg * R + m) : 0.0f;
       ghp[m] = 0.0f;
     }
+    TCT(1);
     // ---- T5: output-stage adjoint -> dz2d (operand A), dz2g (operand A2) ; GEMM3d + GEMM3g ----
 #pragma unroll
     for (int c = 0; c < 16; c += 4) {
@@ -1124,13 +1129,16 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
     if (cs != 0) sts128(stg + lane * 16, make_float4(ghp[0], ghp[1], ghp[2], 0.0f));
     tmem_st_wait();
     fence_before_sync();
+    TCT(2);
     __syncthreads();
+    TCT(3);
     if (tid == 0) {
       fence_after_sync();
       issue_gemm_ts(tmem + D3D, tmem + AH, tmem + AL, wt[0], wt[0] + IMG_W2 * 4, 64, 64, false, p.passes);
       issue_gemm_ts(tmem + D3G, tmem + A2H, tmem + A2L, wt[1], wt[1] + IMG_W2 * 4, 64, 64, false, p.passes);
       commit(bar3);
     }
+    TCT(4);
     if (cs == 0) {
       float4 g1 = lds128(stg + 4 * STG_WARP_BYTES + lane * 16);
       float4 g2 = lds128(stg + 8 * STG_WARP_BYTES + lane * 16);
@@ -1155,8 +1163,10 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
         zg[4 * c] = b.x; zg[4 * c + 1] = b.y; zg[4 * c + 2] = b.z; zg[4 * c + 3] = b.w;
       }
     }
+    TCT(5);
     // ---- T6: dz1 = D3 * SiLU'(z1) -> operands A (dense), A2 (gate) ; GEMM4a + GEMM4b ----
     mbar_wait_warp(bar3, par);
+    TCT(6);
     fence_after_sync();
     {
       float v[16];
@@ -1173,13 +1183,16 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
     }
     tmem_st_wait();
     fence_before_sync();
+    TCT(8);
     __syncthreads();
+    TCT(9);
     if (tid == 0) {
       fence_after_sync();
       issue_gemm_ts(tmem + D4, tmem + AH, tmem + AL, wt[2], wt[2] + IMG_W2 * 4, 64, 64, false, p.passes);
       issue_gemm_ts(tmem + D4, tmem + A2H, tmem + A2L, wt[3], wt[3] + IMG_W2 * 4, 64, 64, true, p.passes);
       commit(bar4);
     }
+    TCT(10);
     float4 gb[4];
     if (p.g_e_base) {
 #pragma unroll
@@ -1201,8 +1214,10 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
       }
       __syncwarp();
     }
+    TCT(11);
     // ---- T7: g_e ----
     mbar_wait_warp(bar4, par);
+    TCT(12);
     fence_after_sync();
     {
       float v[16];
@@ -1223,6 +1238,7 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
       __syncwarp();
     }
     fence_before_sync();
+    TCT(13);
   }
   fence_before_sync();
   __syncthreads();
