@@ -220,3 +220,57 @@ def test_cuda_graph_replay_matches_eager(device):
     assert not torch.equal(ref2["forces"], ref["forces"])
     report("graphed.E", out["total_energy"], ref2["total_energy"], 1e-6, 1e-6)
     report("graphed.F", out["forces"], ref2["forces"], 1e-6, 1e-5)
+
+
+@pytest.mark.parametrize("l_max,n_max,dim,blocks", [(3, 4, 64, 2), (4, 4, 64, 1), (2, 2, 64, 2), (3, 3, 128, 1),
+                                                    (1, 1, 32, 3)])
+def test_off_default_hyper_parameters(device, l_max, n_max, dim, blocks):
+    """Other (l_max, n_max, width, depth): n_max = 4 takes the tensor-core forward with the FMA backward, l_max = 4
+    and width != 64 the generic kernels; whole model against the oracle on a two-species cell with O(1) factors."""
+    from torch_m3gnet_b200 import build_model
+
+    hp = O.HyperParams(l_max=l_max, n_max=n_max, embedding_dim=dim, num_blocks=blocks)
+    sd = O.init_params(hp, seed=7, gain=2.0)
+    lat, cart, z = O.mpf_like_structure(2)
+    gd = O.collate([O.build_graph(lat, cart, z, 5.0, 4.0), O.build_graph(*O.fcc_supercell(2, jitter=0.1, seed=4), 5.0, 4.0)])
+    fac = torch.rand(l_max, n_max, generator=torch.Generator().manual_seed(1)) + 0.5
+    model = build_model(5.0, 4.0, l_max, n_max, 95, dim, blocks, device=device)
+    model.load_state_dict(sd)
+    for m in model.model:
+        if hasattr(m, "nsb"):
+            m.nsb.factors = fac.to(device)
+    out = model(to_batch(gd, device))
+    ref = O.forward(sd, hp, {k: v.clone() for k, v in gd.items()}, factors=fac, create_graph=False)
+    n = gd["pos"].shape[0]
+    report("hp.energy", out["total_energy"], ref["total_energy"], n * 1e-5, 1e-5)
+    report("hp.forces", out["forces"], ref["forces"], 1e-4, 1e-3)
+    report("hp.x", out["x"], ref["x"], 2e-5, 2e-5)
+
+
+def test_degenerate_graphs(device):
+    """An isolated atom (no bonds), a dimer (bonds, no triplets) and a normal cell in one batch; and a batch whose only
+    structure has no bond at all."""
+    from torch_m3gnet_b200.data.material_graph import Batch
+    from torch_m3gnet_b200.data.structure import Structure
+
+    big = 30.0 * np.eye(3)
+    structs = [(big, np.array([[1.0, 2.0, 3.0]]), np.array([6])),
+               (big, np.array([[0.0, 0.0, 0.0], [0.0, 0.0, 2.2]]), np.array([8, 1])),
+               O.fcc_supercell(2, jitter=0.05, seed=2)]
+    g = golden("c1_default")
+    sd = {k: (v * 2 if k.endswith("weight") else v) for k, v in state_dict_of(g).items()}
+    model = _default_model(device, sd)
+    b = Batch.from_structures([Structure(l, [int(v) for v in zz], c, coords_are_cartesian=True) for l, c, zz in structs],
+                              5.0, 4.0, device=device)
+    out = model(b)
+    gd = O.collate([O.build_graph(l, c, zz, 5.0, 4.0) for l, c, zz in structs])
+    assert torch.equal(b["edge_index"].cpu(), gd["edge_index"])
+    ref = O.forward(sd, O.HyperParams(), {k: v.clone() for k, v in gd.items()}, create_graph=False)
+    report("degenerate.energy", out["total_energy"], ref["total_energy"], 35 * 1e-5, 1e-5)
+    report("degenerate.forces", out["forces"], ref["forces"], 1e-4, 1e-3)
+    assert out["forces"][0].abs().max().item() == 0.0
+    lone = Batch.from_structures([Structure(big, [6], np.array([[1.0, 2.0, 3.0]]), coords_are_cartesian=True)], 5.0, 4.0,
+                                 device=device)
+    out1 = model(lone)
+    assert lone["edge_index"].shape[1] == 0 and torch.isfinite(out1["total_energy"]).all()
+    assert out1["forces"].abs().max().item() == 0.0

@@ -91,6 +91,16 @@ _KERNELS_PER_CALL = {"exclusive_scan_i32": 3, "csr_by_key": 7, "check_sorted": 2
 PROFILE = None
 
 
+_DUMMY = {}
+
+
+def _dummy(device):
+    buf = _DUMMY.get(device)
+    if buf is None:
+        buf = _DUMMY[device] = torch.zeros(64, dtype=torch.int64, device=device)
+    return buf
+
+
 def _ptr(t):
     if t is None:
         return None
@@ -100,6 +110,10 @@ def _ptr(t):
         raise RuntimeError("torch_m3gnet_b200 kernels need CUDA tensors (there is no CPU fallback)")
     if not t.is_contiguous():
         raise RuntimeError("torch_m3gnet_b200 kernels need contiguous tensors")
+    if t.numel() == 0:
+        # empty tensors have a null data pointer; the ABI's null checks are about missing arguments, so hand over a
+        # valid (never dereferenced) address instead: batches without bonds or triplets are legal inputs
+        return ctypes.c_void_p(_dummy(t.device).data_ptr())
     return ctypes.c_void_p(t.data_ptr())
 
 
