@@ -246,7 +246,9 @@ def evaluate_distributed(model, dbatch: DomainBatch, group=None) -> Dict[str, to
         if isinstance(m, M3GNetConv) and i != last_conv:
             graph[K.NODE_FEATURES] = DistHaloFn.apply(graph[K.NODE_FEATURES], dbatch, group)
     energy = graph[K.TOTAL_ENERGY]
-    weight = torch.tensor([1.0, 0.0], device=energy.device)
+    weight = getattr(dbatch, "_energy_weight", None)
+    if weight is None:  # built once: a host -> device copy would not be capturable in a CUDA graph
+        weight = dbatch._energy_weight = torch.tensor([1.0, 0.0], device=energy.device)
     (g_pos,) = torch.autograd.grad(energy, pos, grad_outputs=weight)
     pos.requires_grad_(False)
     # reverse halo of dE/dpos: ghost gradients go home
@@ -287,3 +289,4 @@ def evaluate_emulated(model, dbatches: List[DomainBatch]) -> Dict[str, torch.Ten
             forces.index_add_(0, ghost_global, -gp[d.n_own:])
         graphs[r]._private.clear()
     return {"total_energy": total.detach().reshape(1), "forces": forces}
+
