@@ -161,7 +161,7 @@ int m3g_tb_sigma_fwd(const float* x, const float* Ws, const float* bs, int64_t N
                      void* stream);
 /* per edge: bas[e][d] = chi_d(r_e)·fc(r_e)·sig[dst[e]][d]   (chi uses rc, fc uses r3; quirk Q5) */
 int m3g_tb_edge_basis_fwd(const float* vec4, const int32_t* dst, const float* sig, const float* tb_consts,
-                          int64_t E, int L, int R, float* bas, void* stream);
+                          int64_t E, int L, int R, const int32_t* edge_list, int64_t n_list, float* bas, void* stream);
 /* red[e1][d] = fc(r_e1)·sum_{e2 in tri(e1)} Y_l(cos(e1,e2))·bas[e2][d];
  * e_out = e_in + SiLU(red·WdT) * sigmoid(red·WgT), WdT/WgT (D,F) */
 int m3g_tb_reduce_fwd(const float* vec4, const float* bas, const int32_t* tri_ptr, const int32_t* tri_e2,
@@ -177,10 +177,13 @@ int m3g_tb_gate_bwd(const float* red, const float* g_e, const float* WdT, const 
 int m3g_tb_reduce_bwd(const float* vec4, const float* bas, const float* g_red, const int32_t* tri_ptr,
                       const int32_t* tri_e2, const int32_t* trt_ptr, const int32_t* trt_e1, const float* tb_consts,
                       int64_t E, int L, int R, int group, float* g_vec4, float* g_bas, void* stream);
-/* adjoint of m3g_tb_edge_basis_fwd: g_vec4[e].w += d/dr terms; g_sig_e (E,D) per-edge sigma gradient */
+/* adjoint of m3g_tb_edge_basis_fwd: g_vec4[e].w += d/dr terms; g_sig_e (E,D) per-edge sigma gradient.
+ * edge_list (optional, both directions): only the n_list listed bonds (the member bonds of the triplet list) are
+ * evaluated — bas rows of other bonds are never read by the reduce kernels; for the adjoint the caller zero-fills
+ * g_sig_e, whose unlisted rows stay zero. */
 int m3g_tb_edge_basis_bwd(const float* vec4, const int32_t* dst, const float* sig, const float* g_bas,
-                          const float* tb_consts, int64_t E, int L, int R, float* g_vec4, float* g_sig_e,
-                          void* stream);
+                          const float* tb_consts, int64_t E, int L, int R, const int32_t* edge_list, int64_t n_list,
+                          float* g_vec4, float* g_sig_e, void* stream);
 /* g_x (N,F) = (sum_{e in in(k)} g_sig_e[e]) * sig(1-sig) · Ws, Ws (D,F) */
 int m3g_tb_sigma_bwd(const float* g_sig_e, const int32_t* in_ptr, const int32_t* in_perm, const float* sig,
                      const float* Ws, int64_t N, int F, int D, float* g_x, void* stream);

@@ -112,9 +112,11 @@ __global__ void tb_sigma_fwd_kernel(const float* __restrict__ x, const float* __
 template <int LC, int RC>
 __global__ void tb_edge_basis_fwd_kernel(const float4* __restrict__ vec4, const int32_t* __restrict__ dst,
                                          const float* __restrict__ sig, const float* __restrict__ consts, int64_t E,
-                                         int L, int R, float* __restrict__ bas) {
+                                         int L, int R, const int32_t* __restrict__ edge_list,
+                                         float* __restrict__ bas) {
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
+  if (e >= E) return;  // E = number of work items: all bonds, or the listed (member) bonds only
+  if (edge_list) e = edge_list[e];
   const int D = L * R;
   float r = vec4[e].w;
   float r3 = consts[2 * D + 1];
@@ -368,9 +370,11 @@ template <int LC, int RC>
 __global__ void tb_edge_basis_bwd_kernel(const float4* __restrict__ vec4, const int32_t* __restrict__ dst,
                                          const float* __restrict__ sig, const float* __restrict__ g_bas,
                                          const float* __restrict__ consts, int64_t E, int L, int R,
-                                         float* __restrict__ g_vec4, float* __restrict__ g_sig_e) {
+                                         const int32_t* __restrict__ edge_list, float* __restrict__ g_vec4,
+                                         float* __restrict__ g_sig_e) {
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
+  if (edge_list) e = edge_list[e];
   const int D = L * R;
   float r = vec4[e].w;
   float r3 = consts[2 * D + 1];
@@ -690,13 +694,14 @@ int m3g_tb_sigma_fwd(const float* x, const float* Ws, const float* bs, int64_t N
 }
 
 int m3g_tb_edge_basis_fwd(const float* vec4, const int32_t* dst, const float* sig, const float* tb_consts, int64_t E,
-                          int L, int R, float* bas, void* stream) {
-  if (E == 0) return M3G_OK;
+                          int L, int R, const int32_t* edge_list, int64_t n_list, float* bas, void* stream) {
+  const int64_t n_work = edge_list ? n_list : E;
+  if (n_work == 0) return M3G_OK;
   M3G_REQUIRE(vec4 && dst && sig && tb_consts && bas, "m3g_tb_edge_basis_fwd: null pointer");
   M3G_CHECK_LR("m3g_tb_edge_basis_fwd");
 #define K_(LC, RC, ...) \
-  tb_edge_basis_fwd_kernel<LC, RC><<<blocks_for(E, 128), 128, 0, as_stream(stream)>>>(__VA_ARGS__)
-  M3G_DISPATCH_LR(K_, (const float4*)vec4, dst, sig, tb_consts, E, L, R, bas);
+  tb_edge_basis_fwd_kernel<LC, RC><<<blocks_for(n_work, 128), 128, 0, as_stream(stream)>>>(__VA_ARGS__)
+  M3G_DISPATCH_LR(K_, (const float4*)vec4, dst, sig, tb_consts, n_work, L, R, edge_list, bas);
 #undef K_
   M3G_LAUNCH_CHECK("m3g_tb_edge_basis_fwd");
   return M3G_OK;
@@ -756,14 +761,15 @@ int m3g_tb_reduce_bwd(const float* vec4, const float* bas, const float* g_red, c
 }
 
 int m3g_tb_edge_basis_bwd(const float* vec4, const int32_t* dst, const float* sig, const float* g_bas,
-                          const float* tb_consts, int64_t E, int L, int R, float* g_vec4, float* g_sig_e,
-                          void* stream) {
-  if (E == 0) return M3G_OK;
+                          const float* tb_consts, int64_t E, int L, int R, const int32_t* edge_list, int64_t n_list,
+                          float* g_vec4, float* g_sig_e, void* stream) {
+  const int64_t n_work = edge_list ? n_list : E;
+  if (n_work == 0) return M3G_OK;
   M3G_REQUIRE(vec4 && dst && sig && g_bas && tb_consts && g_vec4 && g_sig_e, "m3g_tb_edge_basis_bwd: null pointer");
   M3G_CHECK_LR("m3g_tb_edge_basis_bwd");
 #define K_(LC, RC, ...) \
-  tb_edge_basis_bwd_kernel<LC, RC><<<blocks_for(E, 128), 128, 0, as_stream(stream)>>>(__VA_ARGS__)
-  M3G_DISPATCH_LR(K_, (const float4*)vec4, dst, sig, g_bas, tb_consts, E, L, R, g_vec4, g_sig_e);
+  tb_edge_basis_bwd_kernel<LC, RC><<<blocks_for(n_work, 128), 128, 0, as_stream(stream)>>>(__VA_ARGS__)
+  M3G_DISPATCH_LR(K_, (const float4*)vec4, dst, sig, g_bas, tb_consts, n_work, L, R, edge_list, g_vec4, g_sig_e);
 #undef K_
   M3G_LAUNCH_CHECK("m3g_tb_edge_basis_bwd");
   return M3G_OK;

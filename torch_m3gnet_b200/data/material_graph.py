@@ -344,6 +344,13 @@ class GraphPlan:
     def _pick_group(self):
         avg = self.T / max(self.E, 1)
         self.tri_group = 8 if avg <= 12 else (16 if avg <= 28 else 32)
+        # bonds that are the first bond of at least one triplet ("member" bonds): the only ones whose Bessel basis
+        # is ever read
+        used = self.tri_ptr[1:] > self.tri_ptr[:-1]
+        if self.trt_ptr is not self.tri_ptr:  # non-symmetric list: bonds that only occur as second bond count too
+            used = used | (self.trt_ptr[1:] > self.trt_ptr[:-1])
+        self.member_edges = torch.nonzero(used).flatten().to(torch.int32)
+        self.n_members = int(self.member_edges.numel())
         # canonical per-atom layout (full off-diagonal of the member-bond pair matrix)?  -> per-atom kernels
         flags = torch.empty(2, dtype=torch.int32, device=self.device)
         _lib.call("tri_dense_check", self.edge_ptr, self.tri_ptr, self.tri_e2, self.N, flags)

@@ -154,7 +154,7 @@ class ThreeBodyFn(Function):
         sig = _empty((N, D), x)
         call("tb_sigma_fwd", x, w["Ws"], w["bs"], N, F, D, sig)
         bas = _empty((E, D), x)
-        call("tb_edge_basis_fwd", vec4, plan.dst, sig, w["consts"], E, L, R, bas)
+        call("tb_edge_basis_fwd", vec4, plan.dst, sig, w["consts"], E, L, R, plan.member_edges, plan.n_members, bas)
         red = _empty((E, D), x)
         e_out = torch.empty_like(e)
         fast = (L, R, F) == (3, 3, 64) and tb_path() in ("fast", "atom")
@@ -198,7 +198,9 @@ class ThreeBodyFn(Function):
             call("tb_reduce_bwd", vec4, bas, g_red, plan.tri_ptr, plan.tri_e2, plan.trt_ptr, plan.trt_e1, w["consts"],
                  E, L, R, plan.tri_group, g_vec4, g_bas)
         g_sig_e = g_red  # reuse the buffer: g_red is dead after tb_reduce_bwd
-        call("tb_edge_basis_bwd", vec4, plan.dst, sig, g_bas, w["consts"], E, L, R, g_vec4, g_sig_e)
+        g_sig_e.zero_()  # rows of bonds without triplets stay zero (only member bonds are evaluated)
+        call("tb_edge_basis_bwd", vec4, plan.dst, sig, g_bas, w["consts"], E, L, R, plan.member_edges, plan.n_members,
+             g_vec4, g_sig_e)
         g_x = _empty((N, F), vec4)
         call("tb_sigma_bwd", g_sig_e, plan.in_ptr, plan.in_perm, sig, w["Ws"], N, F, D, g_x)
         return g_x, g_e, g_vec4, None, None, None, None
