@@ -191,7 +191,8 @@ int m3g_tb_sigma_bwd(const float* g_sig_e, const int32_t* in_ptr, const int32_t*
 /* Canonical triplet layout (what compute_threebody, data/material_graph.py:239-248, emits): for every atom the
  * rows of its member bonds (bonds with a non-empty triplet row) list exactly all other member bonds of that atom,
  * ascending.  m3g_tri_dense_check: flags[0] = 1 if the CSR has that layout, flags[1] = max members per atom.
- * m3g_tb_atom_fwd / _bwd (csrc/threebody_atom.cu; l_max = n_max = 3, F = 64, members per atom <=
+ * m3g_tb_atom_fwd / _bwd (csrc/threebody_atom.cu; replaces nn/interaction.py:187-223 and its autograd; l_max = n_max =
+ * 3, F = 64, members per atom <=
  * m3g_tb_atom_capacity()) evaluate the three-body op with one warp per centre atom out of shared memory: no
  * triplet index list is read.  fwd writes red for member bonds only and e_out for all bonds; bwd writes g_vec4 /
  * g_bas for all bonds (zeros for non-members).  The gradient w.r.t. e_in is g_e itself. */
@@ -279,7 +280,8 @@ int m3g_tc_selftest(const float* A, const float* img_hi, const float* img_lo, in
 int m3g_conv_tc_fwd(const float* P, int ldp, int po, const int32_t* src, const int32_t* dst, const float* e,
                     const float* h, const float* wimg, const float* b2d, const float* b2g, const float* WhT, int64_t E,
                     int R, int mode, int passes, int n_sm, float* y, float* save, void* stream);
-/* save (optional, variant 4): activations for m3g_conv_tc_bwd_saved — ceil(E / 128) * 128 * 256 floats (1 KB per edge:
+/* (nn/conv.py:63-89 with nn/core.py:30-62 for m3g_conv_tc_fwd; the two functions below replace its autograd)
+ * save (optional): activations for m3g_conv_tc_bwd_saved — ceil(E / 128) * 128 * 256 floats (1 KB per edge:
  * SiLU'(z1) and the layer-2 pre-activations, in a tile-private fragment-major layout).  With them the backward needs
  * neither the forward weights nor P / e: output adjoint -> two 64x64 adjoint GEMM pairs -> g_e, g_z1, g_h (same outputs
  * and conventions as m3g_conv_tc_bwd; src is only read for mode 1, where g_up is indexed by source atom). */

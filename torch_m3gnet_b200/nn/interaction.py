@@ -13,7 +13,9 @@ from torch_m3gnet_b200.nn._packing import PackedWeights, c_, t_
 from torch_m3gnet_b200.nn.core import GatedMLP
 from torch_m3gnet_b200.nn.invariant import PAIR_VEC4
 
-# "fast": specialised kernels for (l_max, n_max, F) = (3, 3, 64); "generic": the width-agnostic kernels everywhere
+# "atom" (default): per-centre-atom kernels for (l_max, n_max, F) = (3, 3, 64) when the plan certifies the canonical
+# triplet layout (csrc/threebody_atom.cu), otherwise "fast"; "fast": specialised CSR kernels for (3, 3, 64);
+# "generic": the width-agnostic CSR kernels everywhere
 TB_PATH = os.environ.get("M3G_TB_PATH", "atom")
 
 __all__ = ["ThreeBodyInteration", "NormalizedSphericalBessel", "SPHERICAL_BESSEL_ZEROS", "spherical_bessel",
@@ -71,7 +73,8 @@ class NormalizedSphericalBessel(torch.nn.Module):
 
 class ThreeBodyInteration(torch.nn.Module):
     """Three-body update of the edge features (reference nn/interaction.py:138-223), fused on the GPU: the
-    triplet gather, basis product and segmented sum into bond features run in one kernel (csrc/threebody.cu).
+    triplet gather, basis product and segmented sum into bond features run in one kernel (csrc/threebody_atom.cu,
+    csrc/threebody.cu).
     Updates EDGE_ATTR."""
 
     def __init__(self, cutoff: float, threebody_cutoff: float, l_max: int, n_max: int, num_node_features: int,
