@@ -196,8 +196,8 @@ int m3g_tb_sigma_bwd(const float* g_sig_e, const int32_t* in_ptr, const int32_t*
  * m3g_tb_atom_capacity()) evaluate the three-body op with one warp per centre atom out of shared memory: no
  * triplet index list is read.  fwd writes red for member bonds only and e_out for all bonds; bwd writes g_vec4 /
  * g_bas for all bonds (zeros for non-members).  The gradient w.r.t. e_in is g_e itself. */
-int m3g_tri_dense_check(const int32_t* edge_ptr, const int32_t* tri_ptr, const int32_t* tri_e2, int64_t N,
-                        int32_t* flags, void* stream);
+int m3g_tri_dense_check(const int32_t* src, const int32_t* edge_ptr, const int32_t* tri_ptr, const int32_t* tri_e2,
+                        int64_t E, int32_t* flags, void* stream);
 int m3g_tb_atom_capacity(void);
 int m3g_tb_atom_fwd(const float* vec4, const float* bas, const int32_t* edge_ptr, const int32_t* tri_ptr, float r3,
                     const float* WdT, const float* WgT, const float* e_in, int64_t N, int n_sm, float* red,

@@ -318,27 +318,29 @@ __global__ void __launch_bounds__(32 * AWARPS) tb_atom_bwd_kernel(
 // ------------------------------------------------------------------------------------------------
 // layout certificate: for every atom, the rows of its member bonds (non-empty triplet rows) are exactly "all other
 // member bonds of the same atom, ascending".  flags[0] = 1 if so, flags[1] = max member count of an atom.
-__global__ void tri_dense_check_kernel(const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ tri_ptr,
-                                       const int32_t* __restrict__ tri_e2, int64_t N, int32_t* __restrict__ flags) {
-  const int64_t atom = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (atom >= N) return;
+// one thread per bond e1 (the per-atom version serialised deg x n3 steps in one thread and cost 0.5 ms per plan)
+__global__ void tri_dense_check_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ edge_ptr,
+                                       const int32_t* __restrict__ tri_ptr, const int32_t* __restrict__ tri_e2,
+                                       int64_t E, int32_t* __restrict__ flags) {
+  const int64_t e1 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e1 >= E) return;
+  const int rb = tri_ptr[e1], re = tri_ptr[e1 + 1];
+  if (re == rb) return;  // not a member bond: nothing to certify
+  const int atom = src[e1];
   const int beg = edge_ptr[atom], end = edge_ptr[atom + 1];
-  int n3 = 0;
-  for (int e = beg; e < end; ++e) n3 += (tri_ptr[e + 1] > tri_ptr[e]);
-  bool ok = true;
-  for (int e1 = beg; e1 < end && ok; ++e1) {
-    const int rb = tri_ptr[e1], re = tri_ptr[e1 + 1];
-    if (re == rb) continue;
-    if (re - rb != n3 - 1) { ok = false; break; }
-    int p = rb;
-    for (int e2 = beg; e2 < end; ++e2) {
-      if (e2 == e1 || !(tri_ptr[e2 + 1] > tri_ptr[e2])) continue;
-      if (tri_e2[p] != e2) { ok = false; break; }
-      ++p;
-    }
+  int n3 = 0, p = rb;
+  bool ok = true, first = true;
+  for (int e2 = beg; e2 < end; ++e2) {
+    if (!(tri_ptr[e2 + 1] > tri_ptr[e2])) continue;
+    ++n3;
+    if (e2 < (int)e1) first = false;
+    if (e2 == (int)e1) continue;
+    if (p >= re || tri_e2[p] != e2) ok = false;
+    ++p;
   }
+  if (p != re) ok = false;
   if (!ok) atomicExch(&flags[0], 0);
-  atomicMax(&flags[1], n3);
+  if (first) atomicMax(&flags[1], n3);  // one update per atom: by its first member bond
 }
 
 __global__ void tri_dense_init_kernel(int32_t* flags) { flags[0] = 1; flags[1] = 0; }
@@ -360,12 +362,12 @@ static inline unsigned atom_grid(Kernel kernel, int64_t N, int n_sm) {
 
 extern "C" {
 
-int m3g_tri_dense_check(const int32_t* edge_ptr, const int32_t* tri_ptr, const int32_t* tri_e2, int64_t N,
-                        int32_t* flags, void* stream) {
-  M3G_REQUIRE(edge_ptr && tri_ptr && flags, "m3g_tri_dense_check: null pointer");
+int m3g_tri_dense_check(const int32_t* src, const int32_t* edge_ptr, const int32_t* tri_ptr, const int32_t* tri_e2,
+                        int64_t E, int32_t* flags, void* stream) {
+  M3G_REQUIRE(edge_ptr && tri_ptr && flags && (E == 0 || src), "m3g_tri_dense_check: null pointer");
   tri_dense_init_kernel<<<1, 1, 0, as_stream(stream)>>>(flags);
-  if (N > 0)
-    tri_dense_check_kernel<<<blocks_for(N, 128), 128, 0, as_stream(stream)>>>(edge_ptr, tri_ptr, tri_e2, N, flags);
+  if (E > 0)
+    tri_dense_check_kernel<<<blocks_for(E, 256), 256, 0, as_stream(stream)>>>(src, edge_ptr, tri_ptr, tri_e2, E, flags);
   M3G_LAUNCH_CHECK("m3g_tri_dense_check");
   return M3G_OK;
 }

@@ -353,7 +353,7 @@ class GraphPlan:
         self.n_members = int(self.member_edges.numel())
         # canonical per-atom layout (full off-diagonal of the member-bond pair matrix)?  -> per-atom kernels
         flags = torch.empty(2, dtype=torch.int32, device=self.device)
-        _lib.call("tri_dense_check", self.edge_ptr, self.tri_ptr, self.tri_e2, self.N, flags)
+        _lib.call("tri_dense_check", self.src, self.edge_ptr, self.tri_ptr, self.tri_e2, self.E, flags)
         dense, self.max_members = flags.tolist()
         self.tri_dense = bool(dense) and self.max_members <= _lib.tb_atom_capacity()
 
