@@ -983,8 +983,10 @@ struct ConvTcBwdSParams {
   int64_t E; int R; int mode; int passes;
   float* g_e; float* g_z1; float* g_h;
 };
-constexpr int SMEM_BS_MISC = TC_BWD_MAX_R * 64 * 4 + 32;  // Wh^T, 2 mbarriers, TMEM slot
-constexpr int SMEM_BWDS_BYTES = SMEM_W_BYTES + 16 * STG_WARP_BYTES + SMEM_BS_MISC + 1024;
+constexpr int SMEM_BS_MISC = TC_BWD_MAX_R * 64 * 4 + 32;  // Wh^T, 3 mbarriers, TMEM slot
+constexpr int SMEM_Z2_BYTES = 2 * 16 * 2048;           // blocks 2, 3 of one tile
+constexpr int SMEM_BWDS_BYTES = SMEM_W_BYTES + 16 * STG_WARP_BYTES + SMEM_Z2_BYTES + SMEM_BS_MISC + 1024;
+static_assert(SMEM_BWDS_BYTES <= 232448, "saved-activation backward exceeds the 227 KB shared-memory limit");
 
 __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwdSParams p) {
   extern __shared__ __align__(1024) char smem_raw[];
@@ -992,10 +994,11 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
   const uint32_t sbase = smem_u32(smem);
   const uint32_t wt[4] = {sbase, sbase + SMEM_S_BYTES, sbase + 2 * SMEM_S_BYTES, sbase + 3 * SMEM_S_BYTES};
   const uint32_t stg_all = sbase + SMEM_W_BYTES;
-  float* misc = reinterpret_cast<float*>(smem + SMEM_W_BYTES + 16 * STG_WARP_BYTES);
-  const uint32_t wh_a = stg_all + 16 * STG_WARP_BYTES;
+  const uint32_t z2buf = stg_all + 16 * STG_WARP_BYTES;  // this tile's saved z2 blocks (64 KB), bulk-copied one tile ahead
+  float* misc = reinterpret_cast<float*>(smem + SMEM_W_BYTES + 16 * STG_WARP_BYTES + SMEM_Z2_BYTES);
+  const uint32_t wh_a = z2buf + SMEM_Z2_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc + TC_BWD_MAX_R * 64);
-  uint32_t* tmem_slot_p = reinterpret_cast<uint32_t*>(bars + 2);
+  uint32_t* tmem_slot_p = reinterpret_cast<uint32_t*>(bars + 3);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, cs = warp >> 2;
@@ -1012,6 +1015,7 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
     mbar_fence_init();
   }
   fence_proxy_async();
@@ -1022,9 +1026,14 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
   constexpr uint32_t tmem = 0u;
   const uint32_t t_lane = ((uint32_t)(32 * q) << 16);
   constexpr uint32_t AH = 0, AL = 64, A2H = 128, A2L = 192, D3D = 256, D3G = 320, D4 = 384;
-  uint64_t *bar3 = &bars[0], *bar4 = &bars[1];
+  uint64_t *bar3 = &bars[0], *bar4 = &bars[1], *zb = &bars[2];
 
   const int64_t n_tiles = (p.E + TILE_M - 1) / TILE_M;
+  // blocks 2 and 3 (z2 dense | gate) of a tile are 64 KB contiguous in the save layout
+  if (tid == 0 && (int64_t)blockIdx.x < n_tiles) {
+    mbar_arrive_expect_tx(zb, SMEM_Z2_BYTES);
+    bulk_g2s(z2buf, p.save + save_offset(blockIdx.x, 2, 0, 0), SMEM_Z2_BYTES, zb);
+  }
   uint32_t par = 0;
 #ifdef M3G_TC_TIMING
   long long tct_prev = clock64();
@@ -1042,8 +1051,7 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
       const int64_t tn = tile + gridDim.x;
       if (tn < n_tiles) {
         const float* sv = p.save + tn * (int64_t)(TILE_M * 256);
-        prefetch_l2(sv + tid * 32);
-        prefetch_l2(sv + (tid + 512) * 32);
+        prefetch_l2(sv + tid * 32);  // blocks 0, 1 (SiLU'(z1)); blocks 2, 3 arrive by bulk copy
         const int64_t en = tn * TILE_M;
         const int64_t rn = min(en + (tid & 255) / 2, p.E - 1);
         const int half = (tid & 1) * 32;
@@ -1058,12 +1066,13 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
     // ---- T0: saved z2 slices, upstream gradient slice, h ----
     float zd[16], zg[16], gu[16];
     {
-      const float* s2 = p.save + save_offset(tile, 2, cs, q) + 4 * lane;
-      const float* s3 = p.save + save_offset(tile, 3, cs, q) + 4 * lane;
+      mbar_wait_warp(zb, par);  // the bulk copy issued one tile ago has landed
+      const uint32_t s2 = z2buf + ((cs * 4 + q) << 11) + 16 * lane;
+      const uint32_t s3 = s2 + (16 << 11);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        float4 a = __ldg(reinterpret_cast<const float4*>(s2 + 128 * c));
-        float4 b = __ldg(reinterpret_cast<const float4*>(s3 + 128 * c));
+        float4 a = lds128(s2 + 512 * c);
+        float4 b = lds128(s3 + 512 * c);
         zd[4 * c] = a.x; zd[4 * c + 1] = a.y; zd[4 * c + 2] = a.z; zd[4 * c + 3] = a.w;
         zg[4 * c] = b.x; zg[4 * c + 1] = b.y; zg[4 * c + 2] = b.z; zg[4 * c + 3] = b.w;
       }
@@ -1134,6 +1143,11 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
     TCT(3);
     if (tid == 0) {
       fence_after_sync();
+      if (tile + gridDim.x < n_tiles) {  // every thread has consumed this tile's z2: refill for the next tile
+        fence_proxy_async();
+        mbar_arrive_expect_tx(zb, SMEM_Z2_BYTES);
+        bulk_g2s(z2buf, p.save + save_offset(tile + gridDim.x, 2, 0, 0), SMEM_Z2_BYTES, zb);
+      }
       issue_gemm_ts(tmem + D3D, tmem + AH, tmem + AL, wt[0], wt[0] + IMG_W2 * 4, 64, 64, false, p.passes);
       issue_gemm_ts(tmem + D3G, tmem + A2H, tmem + A2L, wt[1], wt[1] + IMG_W2 * 4, 64, 64, false, p.passes);
       commit(bar3);
