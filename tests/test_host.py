@@ -162,3 +162,24 @@ def test_structure_record():
     s = Structure(np.eye(3) * 4.0, ["Ti", "O", 8], [[0, 0, 0], [0.5, 0.5, 0.5], [0.25, 0, 0]])
     assert len(s) == 3 and [site.specie.Z for site in s] == [22, 8, 8]
     assert np.allclose(s.cart_coords[1], [2, 2, 2]) and np.allclose(s.frac_coords[2], [0.25, 0, 0])
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's CPU path = oracle port, no GPU needed) prints one JSON line with the
+    keys the driver reads; the product arm's keys are checked on the GPU box by the bench itself."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "energy+forces atom-steps/sec" and d["unit"] == "atom-steps/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["config"]["workload"].startswith("C2")
