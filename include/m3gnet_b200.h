@@ -194,8 +194,9 @@ int m3g_tb_sigma_bwd(const float* g_sig_e, const int32_t* in_ptr, const int32_t*
  * m3g_tb_atom_fwd / _bwd (csrc/threebody_atom.cu; replaces nn/interaction.py:187-223 and its autograd; l_max = n_max =
  * 3, F = 64, members per atom <=
  * m3g_tb_atom_capacity()) evaluate the three-body op with one warp per centre atom out of shared memory: no
- * triplet index list is read.  fwd writes red for member bonds only and e_out for all bonds; bwd writes g_vec4 /
- * g_bas for all bonds (zeros for non-members).  The gradient w.r.t. e_in is g_e itself. */
+ * triplet index list is read.  fwd writes red for member bonds only and e_out for all bonds; bwd writes g_vec4 for
+ * all bonds (zeros for non-members) and g_bas for member bonds only (pair it with the member edge_list of
+ * m3g_tb_edge_basis_bwd).  The gradient w.r.t. e_in is g_e itself. */
 int m3g_tri_dense_check(const int32_t* src, const int32_t* edge_ptr, const int32_t* tri_ptr, const int32_t* tri_e2,
                         int64_t E, int32_t* flags, void* stream);
 int m3g_tb_atom_capacity(void);

@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(32 * AWARPS) tb_atom_fwd_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward: g_red (member bonds, internal), g_vec4 (E,4) = d/d(v, r), g_bas (E,9); zeros for non-member bonds
+// backward: g_red (member bonds, internal), g_vec4 (E,4) = d/d(v, r) (zeros for non-member bonds), g_bas (E,9) (member
+// bonds only)
 __global__ void __launch_bounds__(32 * AWARPS) tb_atom_bwd_kernel(
     const float4* __restrict__ vec4, const float* __restrict__ bas, const float* __restrict__ red,
     const float* __restrict__ g_e, const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ tri_ptr, float r3,
@@ -197,15 +198,10 @@ __global__ void __launch_bounds__(32 * AWARPS) tb_atom_bwd_kernel(
   }
   for (int64_t atom = (int64_t)blockIdx.x * AWARPS + warp; atom < N; atom += (int64_t)gridDim.x * AWARPS) {
     const int beg = __ldg(edge_ptr + atom), end = __ldg(edge_ptr + atom + 1);
-    // non-member bonds carry no three-body term: zero gradients
-    for (int e = beg + lane; e < end; e += 32) {
-      if (!(__ldg(tri_ptr + e + 1) > __ldg(tri_ptr + e))) {
-        g_vec4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        float* gb = g_bas + (int64_t)e * AD;
-#pragma unroll
-        for (int d = 0; d < AD; ++d) gb[d] = 0.0f;
-      }
-    }
+    // non-member bonds carry no three-body term: zero geometry gradient (their g_bas rows are never read: the basis
+    // adjoint runs over the member list only)
+    for (int e = beg + lane; e < end; e += 32)
+      if (!(__ldg(tri_ptr + e + 1) > __ldg(tri_ptr + e))) g_vec4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int n3 = stage_members<true>(ent, beg, end, vec4, bas, red, tri_ptr, r3, lane);  // q = red
     // ---- gated-MLP adjoint: q <- g_red ; lane owns features 2*lane, 2*lane+1 ; two register buffers of GB upstream
     //      rows: one is processed while the other is in flight ----
