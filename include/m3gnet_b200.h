@@ -98,6 +98,24 @@ int m3g_nbr_fill(const double* lattice, const double* cart, const int32_t* atom_
                  const int32_t* bin_ptr, const int32_t* bin_atoms, const int32_t* edge_ptr /* (N+1) */, int64_t E,
                  int64_t* edge_index /* (2,E) */, int32_t* edge_shift /* (E,3) */, float* edge_dist /* (E) */,
                  int32_t* member /* (E) 1 if float32(d) <= float32(r3) */, void* stream);
+
+/* Verlet (skin) list for MD / relaxation loops (the reference rebuilds the pymatgen neighbour
+ * list for every structure it sees, data/material_graph.py:168-193).  The candidate list is an ordinary neighbour
+ * list built once with cutoff + skin (m3g_nbr_count / m3g_nbr_fill): cand_ptr (N+1), cand_j (C) int32, cand_shift
+ * (C,3).  m3g_verlet_displacement writes max_i |cart_i - ref_i|^2 (f32, rounded up; +inf for NaN input) so the host
+ * rebuilds the candidates once it exceeds (skin/2)^2.  While it does not, m3g_verlet_count / m3g_verlet_fill give
+ * exactly the output of m3g_nbr_count / m3g_nbr_fill on the new coordinates (same float64 accept test on the
+ * candidates, same (j, s0, s1, s2) order).  The lattice must be the one the candidates were built with. */
+int m3g_verlet_displacement(const double* cart, const double* ref_cart, int64_t N, float* max_d2 /* (1) */,
+                            void* stream);
+int m3g_verlet_count(const double* lattice, const double* cart, const int32_t* atom_ptr, int64_t B, int64_t N,
+                     double cutoff, const int32_t* cand_ptr, const int32_t* cand_j, const int32_t* cand_shift,
+                     int32_t* edge_count /* (N) */, void* stream);
+int m3g_verlet_fill(const double* lattice, const double* cart, const int32_t* atom_ptr, int64_t B, int64_t N,
+                    double cutoff, double threebody_cutoff, const int32_t* cand_ptr, const int32_t* cand_j,
+                    const int32_t* cand_shift, const int32_t* edge_ptr, int64_t E, int64_t* edge_index /* (2,E) */,
+                    int32_t* edge_shift /* (E,3) */, float* edge_dist /* (E) */, int32_t* member /* (E) */,
+                    void* stream);
 /* per-atom member degree n3 -> num_triplet_i (N) int64 = n3(n3-1), num_triplet_ij (E) int32,
  * tri_count (E) = triplets whose first bond is e (n3-1 for member edges else 0), and member_list (E):
  * the member edges of atom i compacted (ascending) at positions edge_ptr[i].. */

@@ -183,3 +183,25 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["config"]["workload"].startswith("C2")
+
+
+def test_verlet_list_and_calculator_host_checks(monkeypatch):
+    """Argument errors of the trajectory-side callers, and no CPU fallback for them either."""
+    import torch_m3gnet_b200 as m3g
+    from torch_m3gnet_b200 import calculator
+
+    lat = np.eye(3)[None] * 4.0
+    with pytest.raises(ValueError, match="Three body cutoff"):
+        m3g.VerletList(lat, [29], [1], 4.0, 5.0)
+    with pytest.raises(ValueError, match="skin"):
+        m3g.VerletList(lat, [29], [1], 5.0, 4.0, skin=0.0)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            m3g.VerletList(lat, [29], [1], 5.0, 4.0)
+        calc = m3g.M3GNetCalculator(m3g.build_model(5.0, 4.0, 3, 3, 95, 64, 3), round_allocations=False)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            calc.compute(lat, np.zeros((1, 3)), [29])
+    # the allocator policy of the user wins
+    monkeypatch.setenv("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+    assert calculator.stabilise_allocator() is False
+    assert abs(calculator.ACC_UNIT - 1.602176634e-19 * 1e20 / (1.66053906660e-27 * 1e30)) < 1e-12

@@ -238,6 +238,80 @@ nbr_kernel(const double* __restrict__ lattice, const double* __restrict__ cart, 
   if (!FILL && lane == 0) edge_count[i] = total;
 }
 
+// ---- Verlet (skin) list: the bonds of a step out of a candidate list built once with cutoff + skin ----
+// The candidate list is an ordinary neighbour list (same kernels, larger radius): per atom ordered by (j, s0, s1, s2),
+// images relative to the unwrapped coordinates.  While no atom has moved further than skin/2 from the coordinates the
+// candidates were built on (and the lattice is unchanged), every pair inside the cutoff is among the candidates, so
+// filtering them with the builder's own float64 accept test gives the builder's edge set in the builder's order.
+
+// max over atoms of |cart - ref|^2, as the bit pattern of a non-negative float (atomicMax on int keeps the order)
+__global__ void verlet_displacement_kernel(const double* __restrict__ cart, const double* __restrict__ ref, int64_t N,
+                                           int32_t* __restrict__ max_d2_bits) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float d2 = 0.f;
+  if (i < N) {
+    double dx = cart[i * 3] - ref[i * 3], dy = cart[i * 3 + 1] - ref[i * 3 + 1], dz = cart[i * 3 + 2] - ref[i * 3 + 2];
+    d2 = __double2float_ru(dx * dx + dy * dy + dz * dz);  // rounded up: the trigger may only fire early
+    if (!(d2 >= 0.f)) d2 = __int_as_float(0x7f800000);    // NaN coordinates force a rebuild (which then fails loudly)
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(FULL, d2, o));
+  if ((threadIdx.x & 31) == 0 && d2 > 0.f) atomicMax(max_d2_bits, __float_as_int(d2));
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+verlet_kernel(const double* __restrict__ lattice, const double* __restrict__ cart, const int32_t* __restrict__ atom_ptr,
+              int B, int64_t N, double cutoff, float r3_f32, const int32_t* __restrict__ cand_ptr,
+              const int32_t* __restrict__ cand_j, const int32_t* __restrict__ cand_shift,
+              const int32_t* __restrict__ edge_ptr, int32_t* __restrict__ edge_count,
+              int64_t* __restrict__ edge_index, int64_t E, int32_t* __restrict__ edge_shift,
+              float* __restrict__ edge_dist, int32_t* __restrict__ member) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (i >= N) return;
+  int b = find_structure(atom_ptr, B, (int)i);
+  Cell c;
+  const double* Lm = lattice + (int64_t)b * 9;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) c.a[k] = Lm[k];
+  const double r2 = __dadd_rn(__dmul_rn(cutoff, cutoff), 1e-8);
+  const double pi[3] = {cart[i * 3 + 0], cart[i * 3 + 1], cart[i * 3 + 2]};
+  const int c_beg = cand_ptr[i], c_end = cand_ptr[i + 1];
+  int64_t w = FILL ? edge_ptr[i] : 0;
+  int total = 0;
+  for (int p0 = c_beg; p0 < c_end; p0 += 32) {
+    int p = p0 + lane;
+    bool ok = false;
+    int j = 0, s0 = 0, s1 = 0, s2 = 0;
+    double d = 0.0;
+    if (p < c_end) {
+      j = cand_j[p];
+      s0 = cand_shift[(int64_t)p * 3]; s1 = cand_shift[(int64_t)p * 3 + 1]; s2 = cand_shift[(int64_t)p * 3 + 2];
+      const double pj[3] = {cart[(int64_t)j * 3 + 0], cart[(int64_t)j * 3 + 1], cart[(int64_t)j * 3 + 2]};
+      double d2 = dist2_exact(c, pi, pj, s0, s1, s2);
+      ok = d2 < r2;
+      d = __dsqrt_rn(d2);
+      if (ok && j == (int)i && d <= 1e-8) ok = false;
+    }
+    unsigned mask = __ballot_sync(FULL, ok);
+    if (FILL && ok) {
+      int64_t q = w + __popc(mask & ((1u << lane) - 1));
+      edge_index[q] = i;
+      edge_index[E + q] = j;
+      edge_shift[q * 3 + 0] = s0;
+      edge_shift[q * 3 + 1] = s1;
+      edge_shift[q * 3 + 2] = s2;
+      float df = __double2float_rn(d);
+      edge_dist[q] = df;
+      member[q] = (df <= r3_f32) ? 1 : 0;
+    }
+    w += __popc(mask);
+    total += __popc(mask);
+  }
+  if (!FILL && lane == 0) edge_count[i] = total;
+}
+
 // one warp per atom: member degree, per-edge triplet counts, compacted member list (ascending edge id)
 __global__ void triplet_count_kernel(const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ member,
                                      int64_t N, int64_t* __restrict__ num_triplet_i,
@@ -353,6 +427,48 @@ int m3g_nbr_fill(const double* lattice, const double* cart, const int32_t* atom_
       lattice, cart, atom_ptr, (int)B, N, cutoff, (float)threebody_cutoff, bins, bin_base, bin_ptr, bin_atoms, edge_ptr,
       nullptr, edge_index, E, edge_shift, edge_dist, member);
   M3G_LAUNCH_CHECK("m3g_nbr_fill");
+  return M3G_OK;
+}
+
+int m3g_verlet_displacement(const double* cart, const double* ref_cart, int64_t N, float* max_d2, void* stream) {
+  M3G_REQUIRE(max_d2, "m3g_verlet_displacement: null pointer");
+  if (cudaMemsetAsync(max_d2, 0, sizeof(float), as_stream(stream)) != cudaSuccess) {
+    m3g::set_error("m3g_verlet_displacement: memset failed");
+    return M3G_ERR_CUDA;
+  }
+  if (N == 0) return M3G_OK;
+  M3G_REQUIRE(cart && ref_cart, "m3g_verlet_displacement: null pointer");
+  verlet_displacement_kernel<<<blocks_for(N, 256), 256, 0, as_stream(stream)>>>(cart, ref_cart, N,
+                                                                                reinterpret_cast<int32_t*>(max_d2));
+  M3G_LAUNCH_CHECK("m3g_verlet_displacement");
+  return M3G_OK;
+}
+
+int m3g_verlet_count(const double* lattice, const double* cart, const int32_t* atom_ptr, int64_t B, int64_t N,
+                     double cutoff, const int32_t* cand_ptr, const int32_t* cand_j, const int32_t* cand_shift,
+                     int32_t* edge_count, void* stream) {
+  if (N == 0) return M3G_OK;
+  M3G_REQUIRE(lattice && cart && atom_ptr && cand_ptr && cand_j && cand_shift && edge_count && B > 0,
+              "m3g_verlet_count: bad argument");
+  verlet_kernel<false><<<blocks_for(N * 32, 256), 256, 0, as_stream(stream)>>>(
+      lattice, cart, atom_ptr, (int)B, N, cutoff, 0.0f, cand_ptr, cand_j, cand_shift, nullptr, edge_count, nullptr, 0,
+      nullptr, nullptr, nullptr);
+  M3G_LAUNCH_CHECK("m3g_verlet_count");
+  return M3G_OK;
+}
+
+int m3g_verlet_fill(const double* lattice, const double* cart, const int32_t* atom_ptr, int64_t B, int64_t N,
+                    double cutoff, double threebody_cutoff, const int32_t* cand_ptr, const int32_t* cand_j,
+                    const int32_t* cand_shift, const int32_t* edge_ptr, int64_t E, int64_t* edge_index,
+                    int32_t* edge_shift, float* edge_dist, int32_t* member, void* stream) {
+  if (N == 0 || E == 0) return M3G_OK;
+  M3G_REQUIRE(lattice && cart && atom_ptr && cand_ptr && cand_j && cand_shift && edge_ptr && edge_index &&
+                  edge_shift && edge_dist && member && B > 0,
+              "m3g_verlet_fill: bad argument");
+  verlet_kernel<true><<<blocks_for(N * 32, 256), 256, 0, as_stream(stream)>>>(
+      lattice, cart, atom_ptr, (int)B, N, cutoff, (float)threebody_cutoff, cand_ptr, cand_j, cand_shift, edge_ptr,
+      nullptr, edge_index, E, edge_shift, edge_dist, member);
+  M3G_LAUNCH_CHECK("m3g_verlet_fill");
   return M3G_OK;
 }
 

@@ -216,17 +216,74 @@ class Batch(MaterialGraph):
         return bins, bin_base, bin_ptr, bin_atoms
 
     @classmethod
-    def from_arrays(cls, lattices: np.ndarray, cart: np.ndarray, atomic_numbers: np.ndarray, sizes: Sequence[int],
-                    cutoff: float, threebody_cutoff: float, device: Optional[torch.device] = None,
-                    want_triplet_index: bool = True) -> "Batch":
-        if threebody_cutoff > cutoff:
-            raise ValueError("Three body cutoff raidus should be smaller than two body.")
+    def _sweep(cls, lattices, lat64, cart64, atom_ptr, B, N, cutoff, threebody_cutoff, device):
+        """Neighbour sweep (count -> scan -> fill) of the atoms in ``cart64``; returns the source-CSR offsets, the
+        bond count and the bond tensors."""
+        i32 = dict(dtype=torch.int32, device=device)
+        bins, bin_base, bin_ptr, bin_atoms = cls._cell_list(lattices, B, N, float(cutoff), lat64, cart64, atom_ptr,
+                                                            device)
+        counts = torch.empty(N, **i32)
+        _lib.call("nbr_count", lat64, cart64, atom_ptr, B, N, float(cutoff), bins, bin_base, bin_ptr, bin_atoms,
+                  counts)
+        edge_ptr = torch.empty(N + 1, **i32)
+        work = torch.empty(_lib.scan_work_elems(N), **i32)
+        _lib.call("exclusive_scan_i32", counts, edge_ptr, N, work)
+        E = int(edge_ptr[-1].item())
+        edge_index = torch.empty((2, E), dtype=torch.int64, device=device)
+        shift = torch.empty((E, 3), **i32)
+        dist = torch.empty(E, dtype=torch.float32, device=device)
+        member = torch.empty(E, **i32)
+        _lib.call("nbr_fill", lat64, cart64, atom_ptr, B, N, float(cutoff), float(threebody_cutoff), bins, bin_base,
+                  bin_ptr, bin_atoms, edge_ptr, E, edge_index, shift, dist, member)
+        return edge_ptr, E, edge_index, shift, dist, member
+
+    @classmethod
+    def _assemble(cls, lat64, cart64, types, atom_ptr, batch, N, edge_ptr, E, edge_index, shift, dist, member,
+                  want_triplet_index, lat32=None):
+        """Triplets of the bond list + the Batch object with its plan seeded from the builder's CSR."""
+        device = cart64.device
+        i32 = dict(dtype=torch.int32, device=device)
+        nti = torch.empty(N, dtype=torch.int64, device=device)
+        ntij = torch.empty(E, **i32)
+        tri_count = torch.empty(E, **i32)
+        member_list = torch.empty(max(E, 1), **i32)
+        _lib.call("triplet_count", edge_ptr, member, N, E, nti, ntij, tri_count, member_list)
+        tri_ptr = torch.empty(E + 1, **i32)
+        work = torch.empty(_lib.scan_work_elems(E), **i32)
+        _lib.call("exclusive_scan_i32", tri_count, tri_ptr, E, work)
+        T = int(tri_ptr[-1].item())
+        tri_e2 = torch.empty(T, **i32)
+        tri_index = torch.empty((2, T), dtype=torch.int64, device=device) if want_triplet_index else None
+        _lib.call("triplet_fill", edge_ptr, tri_ptr, tri_count, member_list, N, T, tri_e2, tri_index)
+        g = cls(
+            pos=cart64.to(torch.float32), atom_types=types,
+            num_triplet_i=nti, edge_index=edge_index, edge_cell_shift=shift, num_triplet_ij=ntij,
+            triplet_edge_index=tri_index, lattice=lat64.to(torch.float32) if lat32 is None else lat32,
+        )
+        g._store[K.BATCH] = batch
+        g._store[K.NUM_TRIPLETS] = T
+        g._private["edge_distances_build"] = dist
+        # the builder already holds the canonical CSR: seed the plan so the model does not re-derive it
+        plan = GraphPlan.from_builder(g, atom_ptr, edge_ptr, tri_ptr, tri_e2)
+        object.__setattr__(g, "_plan", plan)
+        return g
+
+    @staticmethod
+    def _check_device(device):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
         if device is None or torch.device(device).type != "cuda":
             raise RuntimeError("graph construction runs on the GPU; no CUDA device is available "
                                "(torch_m3gnet_b200 has no CPU fallback)")
-        device = torch.device(device)
+        return torch.device(device)
+
+    @classmethod
+    def from_arrays(cls, lattices: np.ndarray, cart: np.ndarray, atomic_numbers: np.ndarray, sizes: Sequence[int],
+                    cutoff: float, threebody_cutoff: float, device: Optional[torch.device] = None,
+                    want_triplet_index: bool = True) -> "Batch":
+        if threebody_cutoff > cutoff:
+            raise ValueError("Three body cutoff raidus should be smaller than two body.")
+        device = cls._check_device(device)
         with torch.cuda.device(device):
             B = len(sizes)
             N = int(sum(sizes))
@@ -234,48 +291,12 @@ class Batch(MaterialGraph):
             cart64 = torch.as_tensor(np.ascontiguousarray(cart, dtype=np.float64).reshape(N, 3)).to(device)
             atom_ptr_h = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
             atom_ptr = torch.as_tensor(atom_ptr_h).to(device)
-            i32 = dict(dtype=torch.int32, device=device)
-            bins, bin_base, bin_ptr, bin_atoms = cls._cell_list(lattices, B, N, float(cutoff), lat64, cart64, atom_ptr,
-                                                                device)
-            counts = torch.empty(N, **i32)
-            _lib.call("nbr_count", lat64, cart64, atom_ptr, B, N, float(cutoff), bins, bin_base, bin_ptr, bin_atoms,
-                      counts)
-            edge_ptr = torch.empty(N + 1, **i32)
-            work = torch.empty(_lib.scan_work_elems(N), **i32)
-            _lib.call("exclusive_scan_i32", counts, edge_ptr, N, work)
-            E = int(edge_ptr[-1].item())
-            edge_index = torch.empty((2, E), dtype=torch.int64, device=device)
-            shift = torch.empty((E, 3), **i32)
-            dist = torch.empty(E, dtype=torch.float32, device=device)
-            member = torch.empty(E, **i32)
-            _lib.call("nbr_fill", lat64, cart64, atom_ptr, B, N, float(cutoff), float(threebody_cutoff), bins, bin_base,
-                      bin_ptr, bin_atoms, edge_ptr, E, edge_index, shift, dist, member)
-            nti = torch.empty(N, dtype=torch.int64, device=device)
-            ntij = torch.empty(E, **i32)
-            tri_count = torch.empty(E, **i32)
-            member_list = torch.empty(max(E, 1), **i32)
-            _lib.call("triplet_count", edge_ptr, member, N, E, nti, ntij, tri_count, member_list)
-            tri_ptr = torch.empty(E + 1, **i32)
-            work = torch.empty(_lib.scan_work_elems(E), **i32)
-            _lib.call("exclusive_scan_i32", tri_count, tri_ptr, E, work)
-            T = int(tri_ptr[-1].item())
-            tri_e2 = torch.empty(T, **i32)
-            tri_index = torch.empty((2, T), dtype=torch.int64, device=device) if want_triplet_index else None
-            _lib.call("triplet_fill", edge_ptr, tri_ptr, tri_count, member_list, N, T, tri_e2, tri_index)
+            edge_ptr, E, edge_index, shift, dist, member = cls._sweep(lattices, lat64, cart64, atom_ptr, B, N, cutoff,
+                                                                      threebody_cutoff, device)
             batch = torch.repeat_interleave(torch.arange(B, device=device), torch.as_tensor(list(sizes), device=device))
-            g = cls(
-                pos=cart64.to(torch.float32),
-                atom_types=torch.as_tensor(np.asarray(atomic_numbers, dtype=np.int64) - 1).to(device),
-                num_triplet_i=nti, edge_index=edge_index, edge_cell_shift=shift, num_triplet_ij=ntij,
-                triplet_edge_index=tri_index, lattice=lat64.to(torch.float32),
-            )
-            g._store[K.BATCH] = batch
-            g._store[K.NUM_TRIPLETS] = T
-            g._private["edge_distances_build"] = dist
-            # the builder already holds the canonical CSR: seed the plan so the model does not re-derive it
-            plan = GraphPlan.from_builder(g, atom_ptr, edge_ptr, tri_ptr, tri_e2)
-            object.__setattr__(g, "_plan", plan)
-            return g
+            types = torch.as_tensor(np.asarray(atomic_numbers, dtype=np.int64) - 1).to(device)
+            return cls._assemble(lat64, cart64, types, atom_ptr, batch, N, edge_ptr, E, edge_index, shift, dist,
+                                 member, want_triplet_index)
 
 
 def _sig(t: Optional[torch.Tensor]):

@@ -79,9 +79,11 @@ class GeometryFn(Function):
         vec4 = _empty((E, 4), pos)
         dist = _empty((E,), pos)
         call("geometry_fwd", pos, lattice, plan.batch, plan.src, plan.dst, plan.shift, E, vec4, dist)
-        cos = _empty((T,), pos)
-        tri_index = tri_index.contiguous()
-        call("angles_fwd", vec4, tri_index, T, cos)
+        cos = None
+        if tri_index is not None:  # builder batches made without the (2,T) API list carry no TRIPLET_ANGLES output
+            cos = _empty((T,), pos)
+            tri_index = tri_index.contiguous()
+            call("angles_fwd", vec4, tri_index, T, cos)
         ctx.plan = plan
         ctx.tri_index = tri_index
         ctx.save_for_backward(vec4)

@@ -11,7 +11,9 @@ PAIR_VEC4 = "_pair_vec4"  # private: (E,4) = (r_ij vector, |r_ij|), consumed by 
 
 class DistanceAndAngle(torch.nn.Module):
     """Bond vectors, distances and cos(theta_jik) (reference nn/invariant.py:8-59): supplies EDGE_DISTANCES and
-    TRIPLET_ANGLES (the *cosine*, clamped to [-1, 1], in the caller's triplet order)."""
+    TRIPLET_ANGLES (the *cosine*, clamped to [-1, 1], in the caller's triplet order).  TRIPLET_ANGLES is an output key
+    only (the three-body kernels take their cosines from the bond vectors); it stays None for builder batches created
+    with ``want_triplet_index=False``."""
 
     def forward(self, graph):
         plan = get_plan(graph)
