@@ -102,32 +102,47 @@ def _dummy(device):
 
 
 def _ptr(t):
+    """Device address of a tensor argument (None stays NULL)."""
     if t is None:
         return None
-    if not torch.is_tensor(t):
-        raise TypeError(f"expected a tensor or None, got {type(t)}")
-    if not t.is_cuda:
+    try:
+        ok = t.is_cuda
+    except AttributeError:
+        raise TypeError(f"expected a tensor or None, got {type(t)}") from None
+    if not ok:
         raise RuntimeError("torch_m3gnet_b200 kernels need CUDA tensors (there is no CPU fallback)")
     if not t.is_contiguous():
         raise RuntimeError("torch_m3gnet_b200 kernels need contiguous tensors")
-    if t.numel() == 0:
-        # empty tensors have a null data pointer; the ABI's null checks are about missing arguments, so hand over a
-        # valid (never dereferenced) address instead: batches without bonds or triplets are legal inputs
-        return ctypes.c_void_p(_dummy(t.device).data_ptr())
-    return ctypes.c_void_p(t.data_ptr())
+    # empty tensors have a null data pointer; the ABI's null checks are about missing arguments, so hand over a
+    # valid (never dereferenced) address instead: batches without bonds or triplets are legal inputs
+    return t.data_ptr() or _dummy(t.device).data_ptr()
+
+
+_ENTRY = {}  # name -> (function, indices of the pointer arguments, number of arguments before the stream)
+
+
+def _entry(name: str):
+    ent = _ENTRY.get(name)
+    if ent is None:
+        fn = getattr(LIB.load(), "m3g_" + name)
+        n = len(fn.argtypes) - 1
+        ent = _ENTRY[name] = (fn, tuple(k for k in range(n) if fn.argtypes[k] is ctypes.c_void_p), n)
+    return ent
 
 
 def call(name: str, *args):
-    """Call ``m3g_<name>(*args, stream)`` on the current CUDA stream; raise on a non-zero status."""
+    """Call ``m3g_<name>(*args, stream)`` on the current CUDA stream; raise on a non-zero status.
+
+    This is the per-launch host path (~70 calls per model step), so it is kept short: cached prototypes, raw stream
+    handle straight from the runtime."""
     global CALLS, LAUNCHES
-    cdll = LIB.load()
-    fn = getattr(cdll, "m3g_" + name)
-    conv = []
-    for a, ty in zip(args, fn.argtypes):
-        conv.append(_ptr(a) if ty is ctypes.c_void_p else a)
-    if len(args) != len(fn.argtypes) - 1:
-        raise TypeError(f"m3g_{name}: expected {len(fn.argtypes) - 1} arguments before the stream, got {len(args)}")
-    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    fn, ptr_idx, n = _entry(name)
+    if len(args) != n:
+        raise TypeError(f"m3g_{name}: expected {n} arguments before the stream, got {len(args)}")
+    conv = list(args)
+    for k in ptr_idx:
+        conv[k] = _ptr(conv[k])
+    stream = torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
     if PROFILE is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -139,7 +154,7 @@ def call(name: str, *args):
     CALLS += 1
     LAUNCHES += _KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
-        raise RuntimeError(f"m3g_{name} failed ({rc}): {cdll.m3g_last_error().decode()}")
+        raise RuntimeError(f"m3g_{name} failed ({rc}): {LIB.load().m3g_last_error().decode()}")
 
 
 def scan_work_elems(n: int) -> int:

@@ -23,6 +23,20 @@ class PackedWeights:
         return self._cache
 
 
+def module_params(module: torch.nn.Module) -> Callable[[], Iterable[torch.Tensor]]:
+    """``lambda: list(module.parameters())`` without walking the module tree on every call: the (submodule, name)
+    slots are listed once and read each time, so a replaced Parameter object is still seen."""
+    slots = None
+
+    def fetch():
+        nonlocal slots
+        if slots is None:
+            slots = [(m, n) for m in module.modules() for n in m._parameters]
+        return [m._parameters[n] for m, n in slots if m._parameters[n] is not None]
+
+    return fetch
+
+
 def t_(w: torch.Tensor) -> torch.Tensor:
     """(out,in) → contiguous (in,out)."""
     return w.detach().t().contiguous()

@@ -8,7 +8,7 @@ from torch_m3gnet_b200._lib import call
 from torch_m3gnet_b200.data import MaterialGraphKey as K
 from torch_m3gnet_b200.data.material_graph import get_plan
 from torch_m3gnet_b200.nn._functions import ConvFn
-from torch_m3gnet_b200.nn._packing import PackedWeights, c_, t_
+from torch_m3gnet_b200.nn._packing import PackedWeights, c_, module_params, t_
 from torch_m3gnet_b200.nn.core import GatedMLP
 
 
@@ -63,7 +63,7 @@ class M3GNetConv(torch.nn.Module):
         self.concat_node_update = GatedMLP(self.num_concat_features, [num_edge_features, num_node_features],
                                            device=device)
         self.node_linear = torch.nn.Linear(degree, num_node_features, bias=False, device=device)
-        self._packed = PackedWeights(lambda: list(self.parameters()), self._pack)
+        self._packed = PackedWeights(module_params(self), self._pack)
 
     def _pack_mlp(self, mlp: GatedMLP, lin: torch.nn.Linear):
         F = self.num_node_features

@@ -5,7 +5,7 @@ import torch
 from torch_m3gnet_b200.data import MaterialGraphKey as K
 from torch_m3gnet_b200.data.material_graph import get_plan
 from torch_m3gnet_b200.nn._functions import ReadoutFn
-from torch_m3gnet_b200.nn._packing import PackedWeights, c_, t_
+from torch_m3gnet_b200.nn._packing import PackedWeights, c_, module_params, t_
 from torch_m3gnet_b200.nn.core import GatedMLP
 
 
@@ -21,7 +21,7 @@ class AtomWiseReadout(torch.nn.Module):
         self.num_layers = num_layers
         self.scale = scale
         self.gated = GatedMLP(in_features, [in_features] * (num_layers - 1) + [1], is_output=True, device=device)
-        self._packed = PackedWeights(lambda: list(self.parameters()), self._pack)
+        self._packed = PackedWeights(module_params(self), self._pack)
 
     def _pack(self):
         d = self.gated.linears("dense")
