@@ -4,12 +4,43 @@
 
 namespace m3g {
 
+// Two shapes of the same kernel:
+//  * SW = false: 4 warps x 4 atoms, weights read through L2 for every k (any F <= M3G_MAX_F);
+//  * SW = true : persistent CTAs of 8 warps x 8 atoms with all weight matrices staged once in shared memory
+//                (F % 4 == 0 and 4 F^2 (fwd) / 8 F^2 (bwd) floats + scratch within 227 KB, i.e. F <= 64).
+// The per-atom accumulation order (k ascending) is the same in both.
 constexpr int RO_EPW = 4;
 constexpr int RO_WARPS = 4;
+constexpr int RO_EPW_SW = 8;
+constexpr int RO_WARPS_SW = 8;
 
-template <int NJ>
+template <int NJ, int EPW, bool VEC>
 __device__ __forceinline__ void ro_matvec(const float* xs, int xs_stride, int K, const float* __restrict__ Wt, int ldw,
-                                          int ncols, int lane, float (&acc)[RO_EPW][NJ]) {
+                                          int ncols, int lane, float (&acc)[EPW][NJ]) {
+  if (VEC) {  // K % 4 == 0, xs rows 16-byte aligned: four k per step, activations as float4 broadcasts
+    for (int k = 0; k < K; k += 4) {
+      float w[4][NJ];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          int col = lane + 32 * j;
+          w[kk][j] = (col < ncols) ? Wt[(k + kk) * ldw + col] : 0.0f;
+        }
+#pragma unroll
+      for (int q = 0; q < EPW; ++q) {
+        const float4 xv = *reinterpret_cast<const float4*>(xs + q * xs_stride + k);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          acc[q][j] += xv.x * w[0][j];
+          acc[q][j] += xv.y * w[1][j];
+          acc[q][j] += xv.z * w[2][j];
+          acc[q][j] += xv.w * w[3][j];
+        }
+      }
+    }
+    return;
+  }
   for (int k = 0; k < K; ++k) {
     float w[NJ];
 #pragma unroll
@@ -18,7 +49,7 @@ __device__ __forceinline__ void ro_matvec(const float* xs, int xs_stride, int K,
       w[j] = (col < ncols) ? Wt[(int64_t)k * ldw + col] : 0.0f;
     }
 #pragma unroll
-    for (int q = 0; q < RO_EPW; ++q) {
+    for (int q = 0; q < EPW; ++q) {
       float xv = xs[q * xs_stride + k];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) acc[q][j] += xv * w[j];
@@ -34,19 +65,36 @@ struct ReadoutW {
 
 // BWD = false: writes atomic[i] = elemental[i]/scale + eps_i
 // BWD = true : writes g_x
-template <int NJ, bool BWD>
-__global__ void readout_kernel(const float* __restrict__ x, ReadoutW w, const float* __restrict__ elemental,
-                               float scale, const float* __restrict__ g_atomic,
-                               const float* __restrict__ g_scaled_total, const float* __restrict__ g_total,
-                               const int32_t* __restrict__ batch, int64_t N, int F, float* __restrict__ out) {
-  extern __shared__ float smem[];
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int64_t i0 = ((int64_t)blockIdx.x * RO_WARPS + warp) * RO_EPW;
-  if (i0 >= N) return;
+template <int NJ, bool BWD, int EPW, bool SW>
+__global__ void __launch_bounds__(SW ? RO_WARPS_SW * 32 : RO_WARPS * 32)
+readout_kernel(const float* __restrict__ x, ReadoutW w, const float* __restrict__ elemental, float scale,
+               const float* __restrict__ g_atomic, const float* __restrict__ g_scaled_total,
+               const float* __restrict__ g_total, const int32_t* __restrict__ batch, int64_t N, int F,
+               float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int RO_EPW = EPW;  // shadows the namespace constant inside the kernel
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
   const int F2 = 2 * F;
+  if (SW) {  // weights -> shared memory, once per CTA
+    float* ws = smem + n_warps * (RO_EPW * 5 * F);
+    const int FF = F * F;
+    const float* srcs[8] = {w.W0dT, w.W0gT, w.W1dT, w.W1gT, w.W0d, w.W0g, w.W1d, w.W1g};
+    const int n_mat = BWD ? 8 : 4;
+    for (int m = 0; m < n_mat; ++m) {
+      const float4* g4 = reinterpret_cast<const float4*>(srcs[m]);
+      float4* s4 = reinterpret_cast<float4*>(ws + m * FF);
+      for (int t = threadIdx.x; t < FF / 4; t += blockDim.x) s4[t] = g4[t];
+    }
+    w.W0dT = ws; w.W0gT = ws + FF; w.W1dT = ws + 2 * FF; w.W1gT = ws + 3 * FF;
+    if (BWD) { w.W0d = ws + 4 * FF; w.W0g = ws + 5 * FF; w.W1d = ws + 6 * FF; w.W1g = ws + 7 * FF; }
+    __syncthreads();
+  }
   float* xs = smem + warp * (RO_EPW * 5 * F);  // [EPW][F]
   float* z0_s = xs + RO_EPW * F;               // [EPW][2F]
   float* a0_s = z0_s + RO_EPW * F2;            // [EPW][2F]
+  for (int64_t grp = (int64_t)blockIdx.x * n_warps + warp; grp * RO_EPW < N; grp += (int64_t)gridDim.x * n_warps) {
+  const int64_t i0 = grp * RO_EPW;
+  __syncwarp();  // the previous group's reads of the scratch rows are complete
   int64_t iq[RO_EPW];
 #pragma unroll
   for (int q = 0; q < RO_EPW; ++q) iq[q] = min(i0 + q, N - 1);
@@ -64,8 +112,8 @@ __global__ void readout_kernel(const float* __restrict__ x, ReadoutW w, const fl
         zd[q][j] = (col < F) ? w.b0d[col] : 0.0f;
         zg[q][j] = (col < F) ? w.b0g[col] : 0.0f;
       }
-    ro_matvec<NJ>(xs, F, F, w.W0dT, F, F, lane, zd);
-    ro_matvec<NJ>(xs, F, F, w.W0gT, F, F, lane, zg);
+    ro_matvec<NJ, RO_EPW, SW>(xs, F, F, w.W0dT, F, F, lane, zd);
+    ro_matvec<NJ, RO_EPW, SW>(xs, F, F, w.W0gT, F, F, lane, zg);
 #pragma unroll
     for (int q = 0; q < RO_EPW; ++q)
 #pragma unroll
@@ -90,8 +138,8 @@ __global__ void readout_kernel(const float* __restrict__ x, ReadoutW w, const fl
       zd1[q][j] = (col < F) ? w.b1d[col] : 0.0f;
       zg1[q][j] = (col < F) ? w.b1g[col] : 0.0f;
     }
-  ro_matvec<NJ>(a0_s, F2, F, w.W1dT, F, F, lane, zd1);
-  ro_matvec<NJ>(a0_s + F, F2, F, w.W1gT, F, F, lane, zg1);
+  ro_matvec<NJ, RO_EPW, SW>(a0_s, F2, F, w.W1dT, F, F, lane, zd1);
+  ro_matvec<NJ, RO_EPW, SW>(a0_s + F, F2, F, w.W1gT, F, F, lane, zg1);
   // layer 2 (1 output): dense branch linear, gate branch sigmoid
   float dout[RO_EPW], gout[RO_EPW];
 #pragma unroll
@@ -114,7 +162,7 @@ __global__ void readout_kernel(const float* __restrict__ x, ReadoutW w, const fl
       for (int q = 0; q < RO_EPW; ++q)
         if (i0 + q < N) out[iq[q]] = elemental[iq[q]] / scale + dout[q] * gout[q];
     }
-    return;
+    continue;
   }
   __syncwarp();  // a0_s is about to be overwritten with dz1
 #pragma unroll
@@ -142,8 +190,8 @@ __global__ void readout_kernel(const float* __restrict__ x, ReadoutW w, const fl
     for (int q = 0; q < RO_EPW; ++q)
 #pragma unroll
       for (int j = 0; j < NJ; ++j) { dd[q][j] = 0.0f; dg[q][j] = 0.0f; }
-    ro_matvec<NJ>(a0_s, F2, F, w.W1d, F, F, lane, dd);
-    ro_matvec<NJ>(a0_s + F, F2, F, w.W1g, F, F, lane, dg);
+    ro_matvec<NJ, RO_EPW, SW>(a0_s, F2, F, w.W1d, F, F, lane, dd);
+    ro_matvec<NJ, RO_EPW, SW>(a0_s + F, F2, F, w.W1g, F, F, lane, dg);
 #pragma unroll
     for (int q = 0; q < RO_EPW; ++q)
 #pragma unroll
@@ -162,8 +210,8 @@ __global__ void readout_kernel(const float* __restrict__ x, ReadoutW w, const fl
     for (int q = 0; q < RO_EPW; ++q)
 #pragma unroll
       for (int j = 0; j < NJ; ++j) gx[q][j] = 0.0f;
-    ro_matvec<NJ>(z0_s, F2, F, w.W0d, F, F, lane, gx);
-    ro_matvec<NJ>(z0_s + F, F2, F, w.W0g, F, F, lane, gx);
+    ro_matvec<NJ, RO_EPW, SW>(z0_s, F2, F, w.W0d, F, F, lane, gx);
+    ro_matvec<NJ, RO_EPW, SW>(z0_s + F, F2, F, w.W0g, F, F, lane, gx);
 #pragma unroll
     for (int q = 0; q < RO_EPW; ++q)
       if (i0 + q < N) {
@@ -174,6 +222,7 @@ __global__ void readout_kernel(const float* __restrict__ x, ReadoutW w, const fl
         }
       }
   }
+  }  // group loop
 }
 
 __global__ void structure_sum_kernel(const float* __restrict__ atomic, const int32_t* __restrict__ atom_ptr,
@@ -195,15 +244,38 @@ template <bool BWD>
 static int launch_readout(const float* x, const ReadoutW& w, const float* elemental, float scale,
                           const float* g_atomic, const float* g_st, const float* g_t, const int32_t* batch, int64_t N,
                           int F, float* out, cudaStream_t st) {
+  const int nj = (F + 31) / 32;
+  const size_t smem_sw = ((size_t)RO_WARPS_SW * RO_EPW_SW * 5 * F + (size_t)(BWD ? 8 : 4) * F * F) * sizeof(float);
+  const bool sw = (F % 4 == 0) && smem_sw <= 227 * 1024 && nj <= 2;
+  if (sw) {
+    static int n_sm = 0;
+    if (n_sm == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    }
+    unsigned grid = blocks_for(N, RO_WARPS_SW * RO_EPW_SW);
+    if (grid > (unsigned)n_sm) grid = (unsigned)n_sm;
+#define LAUNCH_SW_(NJ)                                                                                              \
+  do {                                                                                                              \
+    cudaFuncSetAttribute(readout_kernel<NJ, BWD, RO_EPW_SW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                         (int)smem_sw);                                                                             \
+    readout_kernel<NJ, BWD, RO_EPW_SW, true><<<grid, RO_WARPS_SW * 32, smem_sw, st>>>(                              \
+        x, w, elemental, scale, g_atomic, g_st, g_t, batch, N, F, out);                                             \
+  } while (0)
+    if (nj == 1) LAUNCH_SW_(1); else LAUNCH_SW_(2);
+#undef LAUNCH_SW_
+    return 0;
+  }
   size_t smem = (size_t)RO_WARPS * RO_EPW * 5 * F * sizeof(float);
   unsigned grid = blocks_for(N, RO_WARPS * RO_EPW);
-  int nj = (F + 31) / 32;
 #define LAUNCH_(NJ)                                                                                        \
   do {                                                                                                     \
     if (smem > 48 * 1024)                                                                                  \
-      cudaFuncSetAttribute(readout_kernel<NJ, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    readout_kernel<NJ, BWD><<<grid, RO_WARPS * 32, smem, st>>>(x, w, elemental, scale, g_atomic, g_st, g_t, batch, \
-                                                               N, F, out);                                  \
+      cudaFuncSetAttribute(readout_kernel<NJ, BWD, RO_EPW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                           (int)smem);                                                                     \
+    readout_kernel<NJ, BWD, RO_EPW, false><<<grid, RO_WARPS * 32, smem, st>>>(x, w, elemental, scale, g_atomic, g_st, \
+                                                                              g_t, batch, N, F, out);      \
   } while (0)
   if (nj == 1) LAUNCH_(1); else if (nj == 2) LAUNCH_(2); else if (nj == 3) LAUNCH_(3); else LAUNCH_(4);
 #undef LAUNCH_
