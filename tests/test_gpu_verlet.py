@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from torch_m3gnet_b200 import Batch, M3GNetCalculator, VelocityVerlet, VerletList, build_model, synthetic
+from torch_m3gnet_b200 import Batch, Fire, M3GNetCalculator, VelocityVerlet, VerletList, build_model, synthetic
 
 pytestmark = pytest.mark.gpu
 
@@ -162,3 +162,17 @@ def test_velocity_verlet_driver(device):
     out = model(Batch.from_arrays(lat[None], md.pos.cpu().numpy(), z, [32], 5.0, 4.0, device=device))
     assert torch.equal(out["forces"], md.forces)
     assert calc.neighbor_list.n_frames == 21 and calc.neighbor_list.n_rebuilds <= 3
+
+
+def test_fire_relaxation_lowers_energy_and_forces(device):
+    lat, cart, z = synthetic.fcc_cu_supercell(2, 0.08, 6)
+    model = _model(device)
+    calc = M3GNetCalculator(model, 5.0, 4.0, skin=0.5, device=device)
+    opt = Fire(calc, lat, cart, z)
+    e0, f0 = float(opt.energy[0]), opt.fmax()
+    opt.run(fmax=0.0, steps=60)
+    e1, f1 = float(opt.energy[0]), opt.fmax()
+    print(f"[fire] E {e0:.6f} -> {e1:.6f} eV, fmax {f0:.4f} -> {f1:.4f} eV/A, {calc.neighbor_list.n_rebuilds} rebuilds")
+    assert opt.n_steps == 60 and e1 < e0 and f1 < f0
+    out = model(Batch.from_arrays(lat[None], opt.pos.cpu().numpy(), z, [32], 5.0, 4.0, device=device))
+    assert torch.equal(out["forces"], opt.forces)

@@ -7,4 +7,4 @@ __version__ = "0.1.0"
 from torch_m3gnet_b200.data.material_graph import Batch, MaterialGraph  # noqa: E402,F401
 from torch_m3gnet_b200.model.build import build_model  # noqa: E402,F401
 from torch_m3gnet_b200.data.verlet import VerletList  # noqa: E402,F401
-from torch_m3gnet_b200.calculator import M3GNetCalculator, VelocityVerlet  # noqa: E402,F401
+from torch_m3gnet_b200.calculator import Fire, M3GNetCalculator, VelocityVerlet  # noqa: E402,F401

@@ -143,3 +143,55 @@ class VelocityVerlet:
 
     def potential_energy(self) -> float:
         return float(self.energy.reshape(-1)[0].item())
+
+
+class Fire:
+    """FIRE structure relaxation at fixed cell (Bitzek et al., PRL 97, 170201) with coordinates, velocities and forces
+    on the GPU; the usual ASE parameters.  ``run(fmax, steps)`` stops when max_i |F_i| < fmax (eV/A)."""
+
+    def __init__(self, calculator: M3GNetCalculator, lattice, cart, atomic_numbers, dt: float = 0.1,
+                 dt_max: float = 1.0, max_move: float = 0.2, n_min: int = 5, f_inc: float = 1.1, f_dec: float = 0.5,
+                 a_start: float = 0.1, f_a: float = 0.99):
+        self.calc = calculator
+        self.lattice = np.asarray(lattice, dtype=np.float64).reshape(1, 3, 3)
+        self.numbers = np.asarray(atomic_numbers, dtype=np.int64).reshape(-1)
+        dev = calculator.device if calculator.device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.pos = torch.as_tensor(np.ascontiguousarray(cart, dtype=np.float64)).to(dev).reshape(-1, 3)
+        self.vel = torch.zeros_like(self.pos)
+        self.dt, self.dt_max, self.max_move = float(dt), float(dt_max), float(max_move)
+        self.n_min, self.f_inc, self.f_dec, self.a_start, self.f_a = n_min, f_inc, f_dec, a_start, f_a
+        self.a, self.n_pos = a_start, 0
+        self.energy, self.forces, self.stress = self.calc.compute(self.lattice, self.pos, self.numbers)
+        self.n_steps = 0
+
+    def fmax(self) -> float:
+        return float(self.forces.norm(dim=1).max().item())
+
+    def step(self):
+        f = self.forces.to(torch.float64)
+        power = float((f * self.vel).sum().item())
+        if power > 0.0:
+            fn = f.norm()
+            self.vel = (1.0 - self.a) * self.vel + self.a * self.vel.norm() * f / torch.clamp(fn, min=1e-30)
+            if self.n_pos > self.n_min:
+                self.dt = min(self.dt * self.f_inc, self.dt_max)
+                self.a *= self.f_a
+            self.n_pos += 1
+        else:
+            self.vel.zero_()
+            self.a, self.dt, self.n_pos = self.a_start, self.dt * self.f_dec, 0
+        self.vel = self.vel + self.dt * f
+        dr = self.dt * self.vel
+        norm = float(dr.norm().item())
+        if norm > self.max_move:
+            dr = dr * (self.max_move / norm)
+        self.pos = self.pos + dr
+        self.energy, self.forces, self.stress = self.calc.compute(self.lattice, self.pos, self.numbers)
+        self.n_steps += 1
+
+    def run(self, fmax: float = 0.05, steps: int = 200) -> bool:
+        for _ in range(steps):
+            if self.fmax() < fmax:
+                return True
+            self.step()
+        return self.fmax() < fmax
