@@ -1,0 +1,167 @@
+"""GPU: BASELINE.json's full-size configurations through size-independent properties (the oracle cannot run them in
+seconds): additivity over structures, structure-order invariance, translation / rotation invariance, Newton's third
+law per structure, oracle spot checks on members of the full batch, cell-list == plain sweep on the 32 000-atom cell,
+and per-atom three-body kernels == generic CSR kernels on the 1e8-triplet structure."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import m3gnet_oracle as O
+from tests.util import golden, state_dict_of
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def model_x3(device):
+    from torch_m3gnet_b200 import build_model
+
+    sd = {k: (v * 3 if k.endswith("weight") else v) for k, v in state_dict_of(golden("c1_default")).items()}
+    model = build_model(5.0, 4.0, 3, 3, 95, 64, 3, device=device)
+    model.load_state_dict(sd)   # amplified weights: forces O(0.1) eV/A make the absolute tolerances meaningful
+    return model, sd
+
+
+def _batch(lat, cart, z, sizes, device, **kw):
+    from torch_m3gnet_b200 import Batch
+
+    return Batch.from_arrays(lat, cart, z, sizes, 5.0, 4.0, device=device, **kw)
+
+
+def test_c2_full_batch_properties(device, model_x3):
+    """configs[1]: 256 x 108-atom Cu cells = 27 648 atoms, ~1.19 M bonds, ~8.5 M triplets in one call."""
+    from torch_m3gnet_b200 import synthetic
+
+    model, sd = model_x3
+    lat, cart, z, sizes = synthetic.config2_batch(256)
+    b = _batch(lat, cart, z, sizes, device)
+    E, T = b["edge_index"].shape[1], b["triplet_edge_index"].shape[1]
+    assert b["pos"].shape[0] == 27648 and 1.1e6 < E < 1.3e6 and 8e6 < T < 9e6
+    # integer structure: every bond has its reverse, triplet count = sum n3(n3-1)
+    ei, sh = b["edge_index"], b["edge_cell_shift"].long()
+    key = lambda s, d, c: ((s * 27648 + d) * 7 + (c[:, 0] + 3)) * 49 + (c[:, 1] + 3) * 7 + (c[:, 2] + 3)  # noqa: E731
+    fwd, rev = key(ei[0], ei[1], sh), key(ei[1], ei[0], -sh)
+    assert torch.equal(torch.sort(fwd).values, torch.sort(rev).values)
+    assert int(b["num_triplet_i"].sum()) == T == int(b["num_triplet_ij"].sum())
+    out = model(b)
+    en, f = out["total_energy"].clone(), out["forces"].clone()
+    assert torch.isfinite(en).all() and torch.isfinite(f).all() and f.abs().max() > 1e-2
+    # Newton's third law per structure
+    fs = f.view(256, 108, 3).sum(1).abs().max().item()
+    print(f"[full C2] E={E} T={T} max|F|={f.abs().max():.3e} max|sum F per structure|={fs:.2e}")
+    assert fs < 2e-5
+    # additivity: members evaluated alone give the batch's numbers (every bond row / atom sum is independent of its
+    # neighbours in the tile, so this is bit for bit)
+    for s in (0, 100, 255):
+        a0 = 108 * s
+        o1 = model(_batch(lat[s:s + 1], cart[a0:a0 + 108], z[a0:a0 + 108], [108], device))
+        assert torch.equal(o1["total_energy"][0], en[s]) and torch.equal(o1["forces"], f[a0:a0 + 108]), s
+    # structure order: reversed batch = reversed results
+    order = np.arange(255, -1, -1)
+    cart_r = cart.reshape(256, 108, 3)[order].reshape(-1, 3)
+    o2 = model(_batch(lat[order], cart_r, z, sizes, device))
+    assert torch.equal(o2["total_energy"].flip(0), en)
+    assert torch.equal(o2["forces"].view(256, 108, 3).flip(0).reshape(-1, 3), f)
+    # oracle spot checks on two members of the full batch (north_star tolerances)
+    for s in (7, 200):
+        a0 = 108 * s
+        g = O.build_graph(lat[s], cart[a0:a0 + 108], z[a0:a0 + 108], 5.0, 4.0)
+        ref = O.forward(sd, O.HyperParams(), O.collate([g]), create_graph=False)
+        dE = abs(float(en[s].cpu()) - float(ref["total_energy"][0].detach())) / 108
+        dF = (f[a0:a0 + 108].cpu() - ref["forces"]).abs().max().item()
+        print(f"[full C2] structure {s}: |dE|/atom={dE:.2e} max|dF|={dF:.2e} max|F|={ref['forces'].abs().max():.2e}")
+        assert dE <= 1e-5 and dF <= 1e-4
+
+
+def test_c2_translation_and_rotation_invariance(device, model_x3):
+    from torch_m3gnet_b200 import synthetic
+
+    model, _ = model_x3
+    lat, cart, z, sizes = synthetic.config2_batch(256)
+    out = model(_batch(lat, cart, z, sizes, device))
+    en, f = out["total_energy"].clone(), out["forces"].clone()
+    # rigid translation out of the home cell (images are relative to the unwrapped coordinates)
+    o_t = model(_batch(lat, cart + np.array([13.7, -4.2, 0.9]), z, sizes, device))
+    dE = (o_t["total_energy"] - en).abs().max().item() / 108
+    dF = (o_t["forces"] - f).abs().max().item()
+    print(f"[full C2] translation: |dE|/atom={dE:.2e} max|dF|={dF:.2e}")
+    assert dE <= 1e-5 and dF <= 1e-4
+    # proper rotation of cell and coordinates: energies equal, forces co-rotate
+    q, _ = np.linalg.qr(np.random.default_rng(3).normal(size=(3, 3)))
+    q *= np.sign(np.linalg.det(q))
+    o_r = model(_batch(lat @ q, cart @ q, z, sizes, device))
+    dE = (o_r["total_energy"] - en).abs().max().item() / 108
+    dF = (o_r["forces"].double() - f.double() @ torch.as_tensor(q, device=device)).abs().max().item()
+    print(f"[full C2] rotation: |dE|/atom={dE:.2e} max|dF|={dF:.2e}")
+    assert dE <= 1e-5 and dF <= 1e-4
+
+
+def test_c4_cell_list_equals_plain_sweep_32000_atoms(device):
+    """configs[3]: one 32 000-atom Cu supercell; the binned candidate search must give the plain sweep's bonds."""
+    from torch_m3gnet_b200 import Batch, _lib, synthetic
+
+    lat, cart, z = synthetic.fcc_cu_supercell(20, 0.1, 4)
+    n = len(cart)
+    b = _batch(lat[None], cart, z, [n], device, want_triplet_index=False)
+    E = b["edge_index"].shape[1]
+    assert n == 32000 and 1.3e6 < E < 1.5e6
+    lat64 = torch.as_tensor(lat.reshape(1, 3, 3)).to(device)
+    cart64 = torch.as_tensor(cart).to(device)
+    atom_ptr = torch.tensor([0, n], dtype=torch.int32, device=device)
+    counts = torch.empty(n, dtype=torch.int32, device=device)
+    _lib.call("nbr_count", lat64, cart64, atom_ptr, 1, n, 5.0, None, None, None, None, counts)
+    edge_ptr = torch.empty(n + 1, dtype=torch.int32, device=device)
+    work = torch.empty(_lib.scan_work_elems(n), dtype=torch.int32, device=device)
+    _lib.call("exclusive_scan_i32", counts, edge_ptr, n, work)
+    assert int(edge_ptr[-1]) == E
+    ei = torch.empty((2, E), dtype=torch.int64, device=device)
+    sh = torch.empty((E, 3), dtype=torch.int32, device=device)
+    dist = torch.empty(E, dtype=torch.float32, device=device)
+    member = torch.empty(E, dtype=torch.int32, device=device)
+    _lib.call("nbr_fill", lat64, cart64, atom_ptr, 1, n, 5.0, 4.0, None, None, None, None, edge_ptr, E, ei, sh, dist,
+              member)
+    assert torch.equal(ei, b["edge_index"]) and torch.equal(sh, b["edge_cell_shift"])
+    assert torch.equal(dist, b._private["edge_distances_build"])
+    n3 = torch.zeros(n, dtype=torch.int64, device=device).index_add_(0, ei[0], member.long())
+    assert torch.equal(n3 * (n3 - 1), b["num_triplet_i"])
+    assert isinstance(b, Batch)
+
+
+def test_c5_three_body_atom_path_equals_generic_path_1e8_triplets(device):
+    """configs[4]: ~1e8 triplets; the per-atom kernels against the generic CSR kernels (different code, different
+    accumulation structure) on the full structure, forward and backward."""
+    from torch_m3gnet_b200 import Batch, _lib, synthetic
+    from torch_m3gnet_b200.nn import interaction
+    from torch_m3gnet_b200.nn._functions import ThreeBodyFn
+
+    lat, cart, z = synthetic.fcc_cu_supercell(23, 0.4, 5)
+    b = Batch.from_arrays(lat[None], cart, z, [len(cart)], 5.0, 5.0, device=device, want_triplet_index=False)
+    plan = b._plan
+    assert plan.T > 9e7 and plan.tri_dense
+    tb = interaction.ThreeBodyInteration(5.0, 5.0, 3, 3, 64, 64, device=device)
+    tb.nsb.factors = (torch.rand(3, 3, generator=torch.Generator().manual_seed(3)) + 0.5).to(device)
+    w = tb._packed.get()
+    vec4 = torch.empty((plan.E, 4), device=device)
+    dist = torch.empty(plan.E, device=device)
+    _lib.call("geometry_fwd", b["pos"], b["lattice"], plan.batch, plan.src, plan.dst, plan.shift, plan.E, vec4, dist)
+    torch.manual_seed(5)
+    x0 = 0.1 * torch.randn(plan.N, 64, device=device)
+    e0 = 0.05 * torch.randn(plan.E, 64, device=device)
+    go = torch.randn(plan.E, 64, device=device)
+    res = {}
+    saved = interaction.TB_PATH
+    try:
+        for path in ("atom", "generic"):
+            interaction.TB_PATH = path
+            x, e, v4 = x0.clone().requires_grad_(True), e0.clone().requires_grad_(True), vec4.clone().requires_grad_(True)
+            out = ThreeBodyFn.apply(x, e, v4, plan, w, 3, 3)
+            gx, ge, gv = torch.autograd.grad(out, [x, e, v4], grad_outputs=go)
+            res[path] = [t.detach() for t in (out, gx, ge, gv)]
+            del out, gx, ge, gv
+    finally:
+        interaction.TB_PATH = saved
+    for name, a, g in zip(("out", "g_x", "g_e", "g_vec4"), res["atom"], res["generic"]):
+        scale = g.abs().max().item()
+        d = (a - g).abs().max().item()
+        print(f"[full C5] {name}: max|ref|={scale:.3e} max|diff|={d:.3e}")
+        assert d <= 2e-5 * scale + 1e-7, name
