@@ -292,6 +292,9 @@ int m3g_debug_tc_timing(int64_t* out16, int reset, void* stream);
 /* debug: cycles to issue / to complete n_mma back-to-back tcgen05.mma kind::tf32 (M = 128, K = 8) of width N with A
  * from shared (a_tmem = 0) or tensor memory (1); cycles2 = DEVICE buffer of two int64 */
 int m3g_debug_mma_rate(int N, int a_tmem, int n_mma, int64_t* cycles2, void* stream);
+/* same for tcgen05.mma.cta_group::2 (M = 256 over a two-CTA cluster, A and B from shared memory): cycles2[0] = issue
+ * loop, cycles2[1] = until the multicast commit arrives in the leader CTA. */
+int m3g_debug_mma_rate2(int N, int n_mma, int64_t* cycles2, void* stream);
 /* UMMA plumbing self test on one 128-row tile: out (128 x rows) = A (128 x cols) · W^T, W given as its image;
  * a_tmem = 1 feeds A from tensor memory (tcgen05.st + the [a_tmem] operand form) instead of shared memory */
 int m3g_tc_selftest(const float* A, const float* img_hi, const float* img_lo, int rows, int cols, int passes,

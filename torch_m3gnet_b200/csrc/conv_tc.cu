@@ -1304,6 +1304,75 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n_rep, long long* 
   if (threadIdx.x < 32) tmem_dealloc<512>(0u);
 }
 
+
+// --------------------------------------------------------------------------------------------------------
+// debug: issue rate of tcgen05.mma.cta_group::2 kind::tf32 (M = 256 over a CTA pair, each SM computes its own 128
+// rows against the full N; each CTA holds N/2 rows of B).  Only the leader CTA issues; the commit is multicast to the
+// mbarrier at the same shared-memory offset in both CTAs.
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma_rate2_kernel(int n_rep, long long* out) {
+  extern __shared__ __align__(1024) char smem_raw[];
+  char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  for (int i = threadIdx.x; i < (64 + 64) * 1024 / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 1.0f;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  fence_proxy_async();
+  cluster_sync_all();
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  cluster_sync_all();
+  long long t0 = 0;
+  if (rank == 0 && threadIdx.x == 0) {
+    constexpr uint32_t idesc = make_idesc_tf32(256, N, 0);
+    const uint32_t a = smem_u32(smem), b = a + 64 * 1024;
+    const uint64_t da0 = make_desc(a, 16, 1024), db0 = make_desc(b, 16, 1024);
+    t0 = clock64();
+    for (int r = 0; r < n_rep; ++r) {
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const uint64_t db = db0 + (uint64_t)(((kk >> 2) * ((N / 2) * 128) + (kk & 3) * 32) >> 4);
+        const uint64_t da = da0 + (uint64_t)(((kk >> 2) * (TILE_M * 128) + (kk & 3) * 32) >> 4);
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+            "}\n" ::"r"(0u),
+            "l"(da), "l"(db), "r"(idesc), "r"(1u)
+            : "memory");
+      }
+    }
+    long long t1 = clock64();
+    out[0] = t1 - t0;
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(&bar)),
+        "h"((uint16_t)3)
+        : "memory");
+  }
+  if (threadIdx.x == 0) {
+    mbar_wait(&bar, 0);
+    if (rank == 0) out[1] = clock64() - t0;
+  }
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(0u), "n"(512) : "memory");
+}
+
 }  // namespace m3g
 
 using namespace m3g;
@@ -1327,6 +1396,21 @@ int m3g_debug_mma_rate(int N, int a_tmem, int n_mma, int64_t* cycles2, void* str
   else RATE_(256, 1);
 #undef RATE_
   M3G_LAUNCH_CHECK("m3g_debug_mma_rate");
+  return M3G_OK;
+}
+
+int m3g_debug_mma_rate2(int N, int n_mma, int64_t* cycles2, void* stream) {
+  M3G_REQUIRE(cycles2 && (N == 64 || N == 128 || N == 256) && n_mma >= 8, "m3g_debug_mma_rate2: bad arguments");
+  int smem = (64 + 64) * 1024 + 1024;
+  long long* out = (long long*)cycles2;
+#define RATE2_(N_)                                                                                       \
+  do {                                                                                                   \
+    cudaFuncSetAttribute(mma_rate2_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);       \
+    mma_rate2_kernel<N_><<<2, 128, smem, as_stream(stream)>>>(n_mma / 8, out);                           \
+  } while (0)
+  if (N == 64) RATE2_(64); else if (N == 128) RATE2_(128); else RATE2_(256);
+#undef RATE2_
+  M3G_LAUNCH_CHECK("m3g_debug_mma_rate2");
   return M3G_OK;
 }
 
