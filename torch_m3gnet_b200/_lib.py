@@ -120,6 +120,13 @@ def _ptr(t):
 
 _ENTRY = {}  # name -> (function, indices of the pointer arguments, number of arguments before the stream)
 
+if hasattr(torch._C, "_cuda_getCurrentRawStream") and hasattr(torch._C, "_cuda_getDevice"):
+    def _raw_stream() -> int:
+        return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+else:  # older / newer torch without the raw accessors
+    def _raw_stream() -> int:
+        return torch.cuda.current_stream().cuda_stream
+
 
 def _entry(name: str):
     ent = _ENTRY.get(name)
@@ -142,7 +149,7 @@ def call(name: str, *args):
     conv = list(args)
     for k in ptr_idx:
         conv[k] = _ptr(conv[k])
-    stream = torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+    stream = _raw_stream()
     if PROFILE is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
