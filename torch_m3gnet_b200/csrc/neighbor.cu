@@ -110,12 +110,12 @@ __global__ void bin_fill_kernel(const int32_t* __restrict__ atom_bin, const int3
   bin_atoms[bin_ptr[g] + atomicAdd(&bin_cursor[g], 1)] = (int)i;  // order inside a bin is irrelevant (sorted later)
 }
 
-// ascending bitonic sort of s[0..P) by one warp (P a power of two)
+// ascending bitonic sort of s[0..P) by one warp (P a power of two); j is a power of two: shifts, no divisions
 __device__ __forceinline__ void warp_sort(int* s, int P, int lane) {
   for (int k = 2; k <= P; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
+    for (int j = k >> 1, lj = 31 - __clz(k >> 1); j > 0; j >>= 1, --lj) {
       for (int t = lane; t < (P >> 1); t += 32) {
-        int i = ((t / j) * 2 * j) + (t % j);
+        int i = ((t >> lj) << (lj + 1)) + (t & (j - 1));
         int x = i + j;
         bool up = (i & k) == 0;
         int a = s[i], bv = s[x];
@@ -154,23 +154,39 @@ nbr_kernel(const double* __restrict__ lattice, const double* __restrict__ cart, 
   if (bins != nullptr && bins[b * 3] > 0) {
     const int nb[3] = {bins[b * 3], bins[b * 3 + 1], bins[b * 3 + 2]};
     const int bc[3] = {bin_coord(fi[0], nb[0]), bin_coord(fi[1], nb[1]), bin_coord(fi[2], nb[2])};
-    int n = 0;
-    bool overflow = false;
-    for (int q = 0; q < 27 && !overflow; ++q) {
-      int dx = q / 9 - 1, dy = (q / 3) % 3 - 1, dz = q % 3 - 1;
+    // lanes 0..26 look up one bin each; a warp prefix sum places the bins' atoms back to back
+    int p0 = 0, cnt = 0;
+    if (lane < 27) {
+      int dx = lane / 9 - 1, dy = (lane / 3) % 3 - 1, dz = lane % 3 - 1;
       int gx = (bc[0] + dx + nb[0]) % nb[0], gy = (bc[1] + dy + nb[1]) % nb[1], gz = (bc[2] + dz + nb[2]) % nb[2];
       int g = bin_base[b] + (gx * nb[1] + gy) * nb[2] + gz;
-      int p0 = bin_ptr[g], p1 = bin_ptr[g + 1];
-      if (n + (p1 - p0) > CAND_MAX) { overflow = true; break; }
-      for (int p = p0 + lane; p < p1; p += 32) cand[n + (p - p0)] = bin_atoms[p];
-      n += p1 - p0;
+      p0 = bin_ptr[g];
+      cnt = bin_ptr[g + 1] - p0;
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += y;
+    }
+    const int n = __shfl_sync(FULL, incl, 31);
+    const bool overflow = n > CAND_MAX;
+    if (!overflow) {
+      for (int q = 0; q < 27; ++q) {
+        const int off = __shfl_sync(FULL, incl - cnt, q), c = __shfl_sync(FULL, cnt, q), b0 = __shfl_sync(FULL, p0, q);
+        for (int p = lane; p < c; p += 32) cand[off + p] = bin_atoms[b0 + p];
+      }
     }
     if (!overflow) {
       int P = 32;
       while (P < n) P <<= 1;
-      for (int t = n + lane; t < P; t += 32) cand[t] = 0x7fffffff;
-      __syncwarp();
-      warp_sort(cand, P, lane);
+      if (FILL) {  // only the emission order needs ascending candidates; counting does not
+        for (int t = n + lane; t < P; t += 32) cand[t] = 0x7fffffff;
+        __syncwarp();
+        warp_sort(cand, P, lane);
+      } else {
+        __syncwarp();
+      }
       use_cells = true;
       n_c = n;
     }
