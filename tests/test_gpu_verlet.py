@@ -21,8 +21,9 @@ def _same_graph(a, b):
     assert a["num_edges"] == b["num_edges"] and a["num_triplets"] == b["num_triplets"]
     assert torch.equal(a._private["edge_distances_build"], b._private["edge_distances_build"])
     pa, pb = a._plan, b._plan
-    for k in ("edge_ptr", "tri_ptr", "tri_e2", "in_ptr", "in_perm", "member_edges"):
+    for k in ("edge_ptr", "tri_ptr", "tri_e2", "in_ptr", "member_edges"):
         assert torch.equal(getattr(pa, k), getattr(pb, k)), k
+    assert torch.equal(pa.in_perm[:pa.E], pb.in_perm[:pb.E])  # allocated with one spare slot when there are no bonds
     assert (pa.N, pa.E, pa.T, pa.B, pa.tri_dense, pa.max_members) == (pb.N, pb.E, pb.T, pb.B, pb.tri_dense,
                                                                       pb.max_members)
 
@@ -32,7 +33,9 @@ def _cases():
     lat6, cart6, z6 = synthetic.fcc_cu_supercell(6, 0.1, 2)                     # 864 atoms, 21.7 A: cell-list path
     tiny = (np.array([[2.6, 0, 0], [0.3, 2.7, 0], [0.1, -0.2, 2.9]]), np.array([[0.1, 0.2, 0.3]]), np.array([29]))
     rag = [synthetic.mpf_like_structure(s) for s in range(5)]                   # ragged multi-species batch
+    far = (np.eye(3) * 20.0, np.array([[1.0, 2.0, 3.0], [11.0, 12.0, 13.0]]), np.array([29, 8]))  # no bonds at all
     return {
+        "isolated": ([far[0]], far[1], far[2], [2]),
         "c1": ([lat1], cart1, z1, [len(cart1)]),
         "cells864": ([lat6], cart6, z6, [len(cart6)]),
         "self_images": ([tiny[0]], tiny[1], tiny[2], [1]),
@@ -41,7 +44,7 @@ def _cases():
     }
 
 
-@pytest.mark.parametrize("name", ["c1", "cells864", "self_images", "ragged5"])
+@pytest.mark.parametrize("name", ["c1", "cells864", "self_images", "ragged5", "isolated"])
 def test_verlet_frames_equal_fresh_builds(device, name):
     lats, cart, z, sizes = _cases()[name]
     lats = np.stack(lats)
