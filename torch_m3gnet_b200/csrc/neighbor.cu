@@ -178,17 +178,50 @@ nbr_kernel(const double* __restrict__ lattice, const double* __restrict__ cart, 
       }
     }
     if (!overflow) {
-      int P = 32;
-      while (P < n) P <<= 1;
-      if (FILL) {  // only the emission order needs ascending candidates; counting does not
-        for (int t = n + lane; t < P; t += 32) cand[t] = 0x7fffffff;
+      __syncwarp();
+      n_c = n;
+      if (FILL) {
+        // Only the emission order needs ascending candidates (counting does not), and only candidates with at least
+        // one accepted image are emitted: keep those (compacted in place, reads of a chunk precede its writes), then
+        // sort the few that remain instead of the whole 27-bin neighbourhood.
+        int kept = 0;
+        for (int j0 = 0; j0 < n; j0 += 32) {
+          const bool have = (j0 + lane) < n;
+          const int j = have ? cand[j0 + lane] : 0;
+          bool any = false;
+          if (have) {
+            const double pj[3] = {cart[(int64_t)j * 3 + 0], cart[(int64_t)j * 3 + 1], cart[(int64_t)j * 3 + 2]};
+            double fj[3];
+            frac_of(c, pj, fj);
+            int lo[3], hi[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              double df = fj[k] - fi[k];
+              lo[k] = (int)ceil(-c.reach[k] - df);
+              hi[k] = (int)floor(c.reach[k] - df);
+            }
+            for (int s0 = lo[0]; s0 <= hi[0] && !any; ++s0)
+              for (int s1 = lo[1]; s1 <= hi[1] && !any; ++s1)
+                for (int s2 = lo[2]; s2 <= hi[2] && !any; ++s2) {
+                  double d2 = dist2_exact(c, pi, pj, s0, s1, s2);
+                  bool ok = d2 < r2;
+                  if (ok && j == (int)i && __dsqrt_rn(d2) <= 1e-8) ok = false;
+                  any = ok;
+                }
+          }
+          const unsigned bal = __ballot_sync(FULL, any);
+          __syncwarp();
+          if (any) cand[kept + __popc(bal & ((1u << lane) - 1u))] = j;
+          kept += __popc(bal);
+        }
+        int Pk = 32;
+        while (Pk < kept) Pk <<= 1;
+        for (int t = kept + lane; t < Pk; t += 32) cand[t] = 0x7fffffff;
         __syncwarp();
-        warp_sort(cand, P, lane);
-      } else {
-        __syncwarp();
+        warp_sort(cand, Pk, lane);
+        n_c = kept;
       }
       use_cells = true;
-      n_c = n;
     }
   }
   int64_t base = FILL ? edge_ptr[i] : 0;
