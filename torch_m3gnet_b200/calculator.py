@@ -1,5 +1,5 @@
-"""Trajectory-side callers of the hot path: an ASE-style calculator and a velocity-Verlet
-driver that keep coordinates, neighbour candidates and results on the GPU between steps.
+"""Trajectory-side callers of the hot path: an ASE-style calculator, a velocity-Verlet
+driver and a FIRE relaxation that keep coordinates, neighbour candidates and results on the GPU between steps.
 
 The reference has no driver loop of its own (its ``scripts/relax_org.py`` uses the TensorFlow package); a user would
 call ``MaterialGraph.from_structure`` + ``model(graph)`` per frame (README usage, torch_m3gnet/data/material_graph.py:
@@ -45,6 +45,10 @@ def stabilise_allocator() -> bool:
 
 
 class M3GNetCalculator:
+    """Energy (eV), forces (eV/A) and the model's ``stresses`` row (6 components exactly as the reference's
+    ``Gradient`` module returns them, nn/gradient.py:39-62 -- same order, sign and units as the reference, not
+    re-normalised to ASE's convention) for one structure or a batch; neighbour candidates cached between calls."""
+
     implemented_properties = ("energy", "free_energy", "forces", "stress")
 
     def __init__(self, model: torch.nn.Module, cutoff: float = 5.0, threebody_cutoff: float = 4.0, skin: float = 0.5,
