@@ -168,6 +168,24 @@ def neighbor_list_bruteforce(lattice: np.ndarray, cart: np.ndarray, r: float,
             np.concatenate(dist_l))
 
 
+def verlet_filter(lattice: np.ndarray, cart: np.ndarray, cand_src: np.ndarray, cand_dst: np.ndarray,
+                  cand_img: np.ndarray, r: float, tol: float = 1e-8):
+    """Bonds of a frame out of a candidate list (a ``neighbor_list_bruteforce`` result for ``r + skin`` on earlier
+    coordinates): the candidates whose distance at the NEW coordinates passes the builder's accept test, in candidate
+    order.  Restates the product's skin list (torch_m3gnet_b200/data/verlet.py, csrc/neighbor.cu verlet_kernel); the
+    reference itself rebuilds the pymatgen list for every structure (data/material_graph.py:168-193).  Equal to
+    ``neighbor_list_bruteforce(lattice, cart, r)`` whenever no atom moved further than skin/2 since the candidates
+    were built and the lattice is unchanged."""
+    lattice = np.asarray(lattice, dtype=np.float64)
+    cart = np.asarray(cart, dtype=np.float64)
+    shift = image_vector(np.asarray(cand_img), lattice)
+    vec = (cart[cand_dst] + shift) - cart[cand_src]
+    d2 = (vec[:, 0] * vec[:, 0] + vec[:, 1] * vec[:, 1]) + vec[:, 2] * vec[:, 2]
+    d = np.sqrt(d2)
+    ok = (d2 < r * r + tol) & ~((cand_src == cand_dst) & (d <= tol))
+    return cand_src[ok], cand_dst[ok], np.asarray(cand_img)[ok], d[ok]
+
+
 def enumerate_triplets(num_nodes: int, edge_index: np.ndarray, distances_f32: np.ndarray,
                        threebody_cutoff: float) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Vectorised restatement of ``compute_threebody`` (data/material_graph.py:196-254).
