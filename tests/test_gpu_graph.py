@@ -82,6 +82,9 @@ def test_builder_plan_equals_generic_plan(device):
     assert torch.equal(p1.in_perm[:p1.E], p2.in_perm[:p2.E])
     assert torch.equal(p1.tri_e2[:p1.T], p2.tri_e2[:p2.T])
     assert p2.tri_symmetric
+    # the builder certifies the dense per-atom layout itself; the generic plan derives it with m3g_tri_dense_check
+    assert (p1.tri_dense, p1.max_members) == (p2.tri_dense, p2.max_members) and p1.tri_dense
+    assert torch.equal(p1.member_edges, p2.member_edges)
 
 
 def test_model_on_gpu_built_graph_matches_oracle(device):

@@ -264,7 +264,11 @@ class Batch(MaterialGraph):
         g._store[K.NUM_TRIPLETS] = T
         g._private["edge_distances_build"] = dist
         # the builder already holds the canonical CSR: seed the plan so the model does not re-derive it
-        plan = GraphPlan.from_builder(g, atom_ptr, edge_ptr, tri_ptr, tri_e2)
+        # the builder emits the full off-diagonal pair matrix of every atom's member bonds (the canonical dense layout),
+        # so the plan needs no layout check; the largest member count follows from max n3(n3-1)
+        m = int(nti.max().item()) if N > 0 else 0
+        max_members = 0 if m == 0 else int(round((1.0 + (1.0 + 4.0 * m) ** 0.5) / 2.0))
+        plan = GraphPlan.from_builder(g, atom_ptr, edge_ptr, tri_ptr, tri_e2, max_members=max_members)
         object.__setattr__(g, "_plan", plan)
         return g
 
@@ -318,7 +322,7 @@ class GraphPlan:
         return tuple(_sig(g._store.get(k)) for k in _STRUCTURAL)
 
     @classmethod
-    def from_builder(cls, g, atom_ptr, edge_ptr, tri_ptr, tri_e2) -> "GraphPlan":
+    def from_builder(cls, g, atom_ptr, edge_ptr, tri_ptr, tri_e2, max_members: Optional[int] = None) -> "GraphPlan":
         p = cls()
         p._common(g)
         p.atom_ptr, p.edge_ptr = atom_ptr, edge_ptr
@@ -327,7 +331,7 @@ class GraphPlan:
         p.T = int(tri_e2.numel())  # also when the (2,T) int64 API list was not materialised
         p.trt_ptr, p.trt_e1 = tri_ptr, tri_e2  # builder output is the full off-diagonal: symmetric
         p.tri_symmetric = True
-        p._pick_group()
+        p._pick_group(dense_max_members=max_members)
         p.signature = cls.signature_of(g)
         return p
 
@@ -362,7 +366,7 @@ class GraphPlan:
         work = torch.empty(self.N + 1 + _lib.scan_work_elems(self.N), **i32)
         _lib.call("csr_by_key", self.dst, self.E, self.N, self.in_ptr, self.in_perm, work)
 
-    def _pick_group(self):
+    def _pick_group(self, dense_max_members: Optional[int] = None):
         avg = self.T / max(self.E, 1)
         self.tri_group = 8 if avg <= 12 else (16 if avg <= 28 else 32)
         # bonds that are the first bond of at least one triplet ("member" bonds): the only ones whose Bessel basis
@@ -373,9 +377,12 @@ class GraphPlan:
         self.member_edges = torch.nonzero(used).flatten().to(torch.int32)
         self.n_members = int(self.member_edges.numel())
         # canonical per-atom layout (full off-diagonal of the member-bond pair matrix)?  -> per-atom kernels
-        flags = torch.empty(2, dtype=torch.int32, device=self.device)
-        _lib.call("tri_dense_check", self.src, self.edge_ptr, self.tri_ptr, self.tri_e2, self.E, flags)
-        dense, self.max_members = flags.tolist()
+        if dense_max_members is not None:  # certified by the builder
+            dense, self.max_members = True, int(dense_max_members)
+        else:
+            flags = torch.empty(2, dtype=torch.int32, device=self.device)
+            _lib.call("tri_dense_check", self.src, self.edge_ptr, self.tri_ptr, self.tri_e2, self.E, flags)
+            dense, self.max_members = flags.tolist()
         self.tri_dense = bool(dense) and self.max_members <= _lib.tb_atom_capacity()
 
     @classmethod
