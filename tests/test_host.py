@@ -205,3 +205,30 @@ def test_verlet_list_and_calculator_host_checks(monkeypatch):
     monkeypatch.setenv("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
     assert calculator.stabilise_allocator() is False
     assert abs(calculator.ACC_UNIT - 1.602176634e-19 * 1e20 / (1.66053906660e-27 * 1e30)) < 1e-12
+
+
+def test_packed_weights_follow_parameter_changes():
+    """Kernel-side weight layouts are rebuilt when a parameter is modified in place, loaded, moved or replaced."""
+    from torch_m3gnet_b200.nn._packing import PackedWeights, module_params, t_
+
+    m = torch.nn.Sequential(torch.nn.Linear(3, 4, bias=False), torch.nn.Linear(4, 2))
+    calls = []
+
+    def pack():
+        calls.append(1)
+        return {"W0t": t_(m[0].weight), "W1t": t_(m[1].weight)}
+
+    pw = PackedWeights(module_params(m), pack)
+    a = pw.get()
+    assert pw.get() is a and len(calls) == 1                       # cached
+    with torch.no_grad():
+        m[0].weight.mul_(2.0)                                      # in-place edit bumps _version
+    b = pw.get()
+    assert len(calls) == 2 and torch.equal(b["W0t"], m[0].weight.t())
+    m.load_state_dict({k: v + 1 for k, v in m.state_dict().items()})
+    c = pw.get()
+    assert len(calls) == 3 and torch.equal(c["W1t"], m[1].weight.t())
+    m[1].weight = torch.nn.Parameter(torch.zeros(2, 4))            # replaced Parameter object: the slot is re-read
+    d = pw.get()
+    assert len(calls) == 4 and torch.equal(d["W1t"], torch.zeros(4, 2))
+    assert len(module_params(m)()) == 3
