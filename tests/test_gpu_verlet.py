@@ -179,3 +179,34 @@ def test_fire_relaxation_lowers_energy_and_forces(device):
     assert opt.n_steps == 60 and e1 < e0 and f1 < f0
     out = model(Batch.from_arrays(lat[None], opt.pos.cpu().numpy(), z, [32], 5.0, 4.0, device=device))
     assert torch.equal(out["forces"], opt.forces)
+
+
+def test_graph_replay_while_bonds_are_unchanged(device):
+    """graph_replay=True: frames with an unchanged bond set are replayed from a CUDA graph and are bit-identical to
+    the eager calculator; a changed bond set falls back to the eager step and drops the graph."""
+    lat, cart, z = synthetic.fcc_cu_supercell(2, 0.02, 8)
+    model = _model(device)
+    eager = M3GNetCalculator(model, 5.0, 4.0, skin=0.5, device=device)
+    replay = M3GNetCalculator(model, 5.0, 4.0, skin=0.5, device=device, graph_replay=True, replay_after=2)
+    rng = np.random.default_rng(2)
+    kept = []
+    for frame in range(12):
+        e0, f0, s0 = eager.compute(lat, cart, z)
+        e1, f1, s1 = replay.compute(lat, cart, z)
+        assert torch.equal(e0, e1) and torch.equal(f0, f1) and torch.equal(s0, s1), frame
+        kept.append(f1)                                   # returned tensors must survive later replays
+        if frame == 8:
+            cart = cart + rng.normal(0.0, 0.05, size=cart.shape)     # bond set changes: eager step, graph dropped
+        else:
+            cart = cart + rng.normal(0.0, 1e-5, size=cart.shape)     # far from any shell boundary: same bonds
+    assert replay.n_replays >= 5, replay.n_replays
+    e0, f0, _ = eager.compute(lat, cart, z)
+    e1, f1, _ = replay.compute(lat, cart, z)
+    assert torch.equal(e0, e1) and torch.equal(f0, f1)
+    assert not torch.equal(kept[3], kept[4])              # distinct frames kept distinct values (clones, not views)
+    opt = Fire(replay, lat, cart, z, dt=0.02, dt_max=0.05, max_move=0.01)
+    ref = Fire(eager, lat, cart, z, dt=0.02, dt_max=0.05, max_move=0.01)
+    for _ in range(10):
+        opt.step()
+        ref.step()
+    assert torch.equal(opt.pos, ref.pos) and torch.equal(opt.forces, ref.forces)

@@ -42,9 +42,11 @@ def main():
     ap.add_argument("--skin", type=float, default=0.5)
     ap.add_argument("--dt", type=float, default=2.0)
     ap.add_argument("--temperature", type=float, default=600.0)
+    ap.add_argument("--jitter", type=float, default=0.05)
+    ap.add_argument("--replay", action="store_true", help="Verlet arm with graph_replay=True (cold / small systems)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
-    lat, cart, z = synthetic.fcc_cu_supercell(args.cells, 0.05, 4)
+    lat, cart, z = synthetic.fcc_cu_supercell(args.cells, args.jitter, 4)
     n = len(cart)
     torch.manual_seed(0)
     model = m3g.build_model(5.0, 4.0, 3, 3, 95, 64, 3, device=dev)
@@ -54,7 +56,8 @@ def main():
     v0 -= v0.mean(axis=0)
 
     def run_arm(force_rebuild: bool):
-        calc = m3g.M3GNetCalculator(model, 5.0, 4.0, skin=args.skin, device=dev)
+        calc = m3g.M3GNetCalculator(model, 5.0, 4.0, skin=args.skin, device=dev,
+                                    graph_replay=args.replay and not force_rebuild)
         md = m3g.VelocityVerlet(calc, lat, cart, z, mass, dt=args.dt, velocities=v0)
 
         def one():
@@ -96,9 +99,9 @@ def main():
         rebuild_every_frame=dict(value=1e3 / ms_full, ms_per_step=ms_full),
         first_pass_cold_allocator=dict(value=1e3 / ms_cold, ms_per_step=ms_cold),
         graph_ms=dict(verlet_update=ms_update, candidate_rebuild_plus_update=ms_rebuild, from_arrays_host_coords=ms_fresh),
-        candidate_rebuilds_in_timed_steps=rebuilds,
+        candidate_rebuilds_in_timed_steps=rebuilds, graph_replays=calc.n_replays, graph_captures=calc.n_captures,
         config=dict(workload=f"{args.cells}^3 FCC Cu cells ({n} atoms), T0={args.temperature} K, dt={args.dt} fs, "
-                             f"skin={args.skin} A", atoms=n, bonds=b._plan.E, triplets=b._plan.T,
+                             f"skin={args.skin} A, jitter={args.jitter} A", atoms=n, bonds=b._plan.E, triplets=b._plan.T,
                     candidates=vl.C), dtype="f32", data="synthetic")))
 
 

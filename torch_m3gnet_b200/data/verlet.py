@@ -76,8 +76,9 @@ class VerletList:
         self._ref = cart64.clone()
         self.n_rebuilds += 1
 
-    def update(self, cart) -> Batch:
-        """Graph of the frame with coordinates ``cart`` ((N,3) numpy array or float64 CUDA tensor, Cartesian, A)."""
+    def filter(self, cart):
+        """Bond tensors of the frame ``cart`` (candidates rebuilt first when the skin is exhausted): a tuple
+        (cart64, edge_ptr, E, edge_index, shift, dist, member) for ``assemble``."""
         with torch.cuda.device(self.device):
             cart64 = self._cart64(cart)
             self.n_frames += 1
@@ -104,5 +105,21 @@ class VerletList:
             member = torch.empty(E, **i32)
             _lib.call("verlet_fill", self.lat64, cart64, self.atom_ptr, B, N, self.cutoff, self.threebody_cutoff,
                       self.cand_ptr, self.cand_j, self.cand_shift, edge_ptr, E, edge_index, shift, dist, member)
-            return Batch._assemble(self.lat64, cart64, self.types, self.atom_ptr, self.batch, N, edge_ptr, E,
+            return cart64, edge_ptr, E, edge_index, shift, dist, member
+
+    def assemble(self, frame) -> Batch:
+        """Triplets + Batch (with its plan) of a ``filter`` result."""
+        cart64, edge_ptr, E, edge_index, shift, dist, member = frame
+        with torch.cuda.device(self.device):
+            return Batch._assemble(self.lat64, cart64, self.types, self.atom_ptr, self.batch, self.N, edge_ptr, E,
                                    edge_index, shift, dist, member, self.want_triplet_index, lat32=self.lat32)
+
+    def update(self, cart) -> Batch:
+        """Graph of the frame with coordinates ``cart`` ((N,3) numpy array or float64 CUDA tensor, Cartesian, A)."""
+        return self.assemble(self.filter(cart))
+
+    @staticmethod
+    def same_bonds(a, b) -> bool:
+        """Do two ``filter`` results hold the same bonds, images and three-body membership (same graph topology:
+        identical index tensors, triplets and plan; only coordinates differ)?"""
+        return (a[2] == b[2] and torch.equal(a[3], b[3]) and torch.equal(a[4], b[4]) and torch.equal(a[6], b[6]))
