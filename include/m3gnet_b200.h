@@ -225,6 +225,24 @@ int m3g_tb_atom_bwd(const float* vec4, const float* bas, const float* red, const
                     const int32_t* tri_ptr, float r3, const float* WdT, const float* WgT, int64_t N, int n_sm,
                     float* g_vec4, float* g_bas, void* stream);
 
+/* O(n3)-per-atom moment form of the same op (csrc/threebody_moment.cu; replaces nn/interaction.py:187-223, :353-382 and
+ * their autograd for l_max = n_max = 3, F = 64 and the canonical triplet layout, members per atom <=
+ * m3g_tb_mom_capacity()).  m3g_tb_radial (once per step; nn/interaction.py:226-281, :389-400): G[e][d] = chi_d(r_e) fc(r_e)
+ * and dG/dr for the listed member bonds.  m3g_tb_mom_fwd: red (member bonds) and e_out (all bonds) with bas = G *
+ * sig[dst] formed in-kernel.  m3g_tb_mom_bwd: g_vec4 (E,4) complete (cos, fc' and radial chain; zeros for
+ * non-members) and g_sig_e (E,9) (zeros for non-members), ready for m3g_tb_sigma_bwd.  The Legendre adjoint follows
+ * the reference's quirk (Q3) through second-order moments.  max_members: upper bound of member bonds per atom. */
+int m3g_tb_radial(const float* vec4, const float* tb_consts, int64_t E, int L, int R, const int32_t* edge_list,
+                  int64_t n_list, float* G, float* dG, void* stream);
+int m3g_tb_mom_capacity(void);
+int m3g_tb_mom_fwd(const float* vec4, const float* G, const float* sig, const int32_t* dst, const int32_t* edge_ptr,
+                   const int32_t* tri_ptr, float r3, const float* WdT, const float* WgT, const float* e_in, int64_t N,
+                   int max_members, int n_sm, float* red, float* e_out, void* stream);
+int m3g_tb_mom_bwd(const float* vec4, const float* G, const float* dG, const float* sig, const int32_t* dst,
+                   const float* red, const float* g_e, const int32_t* edge_ptr, const int32_t* tri_ptr, float r3,
+                   const float* WdT, const float* WgT, int64_t N, int max_members, int n_sm, float* g_vec4,
+                   float* g_sig_e, void* stream);
+
 /* Specialised variants for the default model shape l_max = n_max = 3, F = 64 (compile-time loops, gated-MLP
  * weights in shared memory, vector row I/O, persistent grid of 8 x n_sm blocks).  Same results and buffers as
  * the generic entry points above; r3 = three-body cutoff.  m3g_tb_reduce_bwd_sym requires a symmetric triplet

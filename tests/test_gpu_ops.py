@@ -116,7 +116,7 @@ def _threebody_reference_grads(g, gd):
     return out, red, gx, ge, gv
 
 
-@pytest.fixture(params=["atom", "fast", "generic"])
+@pytest.fixture(params=["moment", "atom", "fast", "generic"])
 def tb_path(request):
     from torch_m3gnet_b200.nn import interaction
 
@@ -134,7 +134,7 @@ def test_threebody_operator(device, tb_path):
     gd = graph_dict(g)
     b, plan, pos, vec4, dist, cos = _plan_and_geometry(gd, device)
     report("tb.geom.dist", dist, g["dist"], 1e-6, 1e-6)
-    assert plan.tri_dense, "compute_threebody layout must be certified dense (per-atom kernels would be skipped)"
+    assert plan.tri_dense and plan.tri_moment, "compute_threebody layout must be certified dense (per-atom kernels would be skipped)"
     tb = ThreeBodyInteration(5.0, 4.0, 3, 3, 64, 64, device=device)
     tb.load_state_dict(state_dict_of(g))
     tb.nsb.factors = torch.from_numpy(g["factors"]).to(device)

@@ -35,7 +35,7 @@ def main():
     ap.add_argument("--jitter", type=float, default=0.4)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--path", default="atom", choices=["atom", "fast", "generic"])
+    ap.add_argument("--path", default="moment", choices=["moment", "atom", "fast", "generic"])
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     interaction.TB_PATH = args.path
@@ -58,8 +58,14 @@ def main():
     v4 = vec4.clone().requires_grad_(True)
     go = torch.randn(E, 64, device=dev)
 
+    from torch_m3gnet_b200.nn.invariant import PAIR_VEC4
+
     def step():
-        out = ThreeBodyFn.apply(x, e, v4, plan, w, 3, 3)
+        # the module call: includes the per-step radial tables (m3g_tb_radial) of the moment path
+        batch._private.clear()
+        batch._private[PAIR_VEC4] = v4
+        batch["x"], batch["edge_attr"] = x, e
+        out = tb(batch)["edge_attr"]
         torch.autograd.grad(out, [x, e, v4], grad_outputs=go)
 
     for _ in range(max(args.warmup, 3)):
@@ -87,7 +93,7 @@ def main():
         unit="triplets/s", ms_per_step=ms, n_gpus=1, steps=args.steps, dtype="f32", data="synthetic",
         config=dict(workload=f"C5: {args.cells}^3 FCC Cu cells, jitter +-{args.jitter} A, r_c = r3 = 5 A",
                     atoms=N, bonds=E, triplets=T, triplets_per_bond=T / max(E, 1), max_members=plan.max_members,
-                    path=("atom" if (args.path == "atom" and plan.tri_dense) else args.path), graph_build_s=build_s,
+                    path=(args.path if (args.path in ("atom", "moment") and plan.tri_dense) else args.path), graph_build_s=build_s,
                     l2="edge features (E x 256 B read + write) exceed the 126 MB L2"),
         roofline=dict(bound="hbm", achieved=achieved, peak=hbm, unit="GB/s", frac=achieved / hbm, traffic=None,
                       algorithmic_bytes=alg_bytes, formula="8 T + 868 E + 108 N (SURVEY.md 8(d))"),

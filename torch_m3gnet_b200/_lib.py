@@ -170,3 +170,7 @@ def scan_work_elems(n: int) -> int:
 
 def tb_atom_capacity() -> int:
     return int(LIB.load().m3g_tb_atom_capacity())
+
+
+def tb_mom_capacity() -> int:
+    return int(LIB.load().m3g_tb_mom_capacity())

@@ -401,6 +401,33 @@ __global__ void tb_edge_basis_bwd_kernel(const float4* __restrict__ vec4, const 
   g_vec4[e * 4 + 3] += gr;
 }
 
+// block-invariant radial part of the three-body basis (once per step): G[e][d] = chi_d(r_e) fc(r_e) and dG/dr, for the
+// listed (member) bonds.  bas = G * sigma[dst] is then formed per block inside the per-atom moment kernels.
+template <int LC, int RC>
+__global__ void tb_radial_kernel(const float4* __restrict__ vec4, const float* __restrict__ consts, int64_t n_work,
+                                 int L, int R, const int32_t* __restrict__ edge_list, float* __restrict__ G,
+                                 float* __restrict__ dG) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_work) return;
+  if (edge_list) e = edge_list[e];
+  const int D = L * R;
+  const float r = vec4[e].w;
+  const float r3 = consts[2 * D + 1];
+  const float c = cutoff_poly(r, r3);
+  const float dc = cutoff_poly_grad(r, r3);
+  float chi[LC * RC], dchi[LC * RC];
+  if (c != 0.0f) chi_eval<LC, RC>(r, consts, L, R, chi, dchi);
+#pragma unroll
+  for (int l = 0; l < LC; ++l)
+#pragma unroll
+    for (int n = 0; n < RC; ++n)
+      if (l < L && n < R) {
+        const int d = l * R + n;
+        G[e * D + d] = (c != 0.0f) ? chi[l * RC + n] * c : 0.0f;
+        dG[e * D + d] = (c != 0.0f) ? (dchi[l * RC + n] * c + chi[l * RC + n] * dc) : 0.0f;
+      }
+}
+
 __global__ void tb_sigma_bwd_kernel(const float* __restrict__ g_sig_e, const int32_t* __restrict__ in_ptr,
                                     const int32_t* __restrict__ in_perm, const float* __restrict__ sig,
                                     const float* __restrict__ Ws, int64_t N, int F, int D, float* __restrict__ g_x) {
@@ -772,6 +799,19 @@ int m3g_tb_edge_basis_bwd(const float* vec4, const int32_t* dst, const float* si
   M3G_DISPATCH_LR(K_, (const float4*)vec4, dst, sig, g_bas, tb_consts, n_work, L, R, edge_list, g_vec4, g_sig_e);
 #undef K_
   M3G_LAUNCH_CHECK("m3g_tb_edge_basis_bwd");
+  return M3G_OK;
+}
+
+int m3g_tb_radial(const float* vec4, const float* tb_consts, int64_t E, int L, int R, const int32_t* edge_list,
+                  int64_t n_list, float* G, float* dG, void* stream) {
+  const int64_t n_work = edge_list ? n_list : E;
+  if (n_work == 0) return M3G_OK;
+  M3G_REQUIRE(vec4 && tb_consts && G && dG, "m3g_tb_radial: null pointer");
+  M3G_CHECK_LR("m3g_tb_radial");
+#define K_(LC, RC, ...) tb_radial_kernel<LC, RC><<<blocks_for(n_work, 128), 128, 0, as_stream(stream)>>>(__VA_ARGS__)
+  M3G_DISPATCH_LR(K_, (const float4*)vec4, tb_consts, n_work, L, R, edge_list, G, dG);
+#undef K_
+  M3G_LAUNCH_CHECK("m3g_tb_radial");
   return M3G_OK;
 }
 

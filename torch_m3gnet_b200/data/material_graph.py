@@ -384,6 +384,7 @@ class GraphPlan:
             _lib.call("tri_dense_check", self.src, self.edge_ptr, self.tri_ptr, self.tri_e2, self.E, flags)
             dense, self.max_members = flags.tolist()
         self.tri_dense = bool(dense) and self.max_members <= _lib.tb_atom_capacity()
+        self.tri_moment = bool(dense) and self.max_members <= _lib.tb_mom_capacity()
 
     @classmethod
     def build(cls, g: MaterialGraph) -> "GraphPlan":

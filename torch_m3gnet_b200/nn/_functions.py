@@ -145,41 +145,66 @@ class EdgeAdjustFn(Function):
 
 
 class ThreeBodyFn(Function):
-    """nn/interaction.py:187-223 (see csrc/threebody.cu for the data flow)."""
+    """nn/interaction.py:187-223 (see csrc/threebody_moment.cu / threebody_atom.cu / threebody.cu for the data flow).
+
+    ``radial`` = (G, dG) from ``m3g_tb_radial`` (block-invariant, computed once per step by the caller) selects the
+    O(n3) moment kernels; the dependence of G on the bond length is differentiated inside ``m3g_tb_mom_bwd``."""
 
     @staticmethod
-    def forward(ctx, x, e, vec4, plan, w, L: int, R: int):
+    def forward(ctx, x, e, vec4, plan, w, L: int, R: int, radial=None):
         x, e, vec4 = x.contiguous(), e.contiguous(), vec4.contiguous()
         N, F = x.shape
         E = plan.E
         D = L * R
         sig = _empty((N, D), x)
         call("tb_sigma_fwd", x, w["Ws"], w["bs"], N, F, D, sig)
-        bas = _empty((E, D), x)
-        call("tb_edge_basis_fwd", vec4, plan.dst, sig, w["consts"], E, L, R, plan.member_edges, plan.n_members, bas)
         red = _empty((E, D), x)
         e_out = torch.empty_like(e)
-        fast = (L, R, F) == (3, 3, 64) and tb_path() in ("fast", "atom")
-        atom = fast and tb_path() == "atom" and plan.tri_dense
-        if atom:
-            call("tb_atom_fwd", vec4, bas, plan.edge_ptr, plan.tri_ptr, w["r3"], w["WdT"], w["WgT"], e, plan.N,
-                 sm_count(x.device), red, e_out)
-        elif fast:
-            call("tb_reduce_fwd_fast", vec4, bas, plan.tri_ptr, plan.tri_e2, w["r3"], w["WdT"], w["WgT"], e, E,
-                 plan.tri_group, sm_count(x.device), red, e_out)
+        moment = radial is not None
+        fast = (L, R, F) == (3, 3, 64) and tb_path() in ("fast", "atom", "moment")
+        atom = fast and tb_path() in ("atom", "moment") and plan.tri_dense and not moment
+        bas = None
+        if moment:
+            G = radial[0]
+            call("tb_mom_fwd", vec4, G, sig, plan.dst, plan.edge_ptr, plan.tri_ptr, w["r3"], w["WdT"], w["WgT"], e,
+                 plan.N, plan.max_members, sm_count(x.device), red, e_out)
         else:
-            call("tb_reduce_fwd", vec4, bas, plan.tri_ptr, plan.tri_e2, w["consts"], w["WdT"], w["WgT"], e, E, L, R, F,
-                 plan.tri_group, red, e_out)
+            bas = _empty((E, D), x)
+            call("tb_edge_basis_fwd", vec4, plan.dst, sig, w["consts"], E, L, R, plan.member_edges, plan.n_members,
+                 bas)
+            if atom:
+                call("tb_atom_fwd", vec4, bas, plan.edge_ptr, plan.tri_ptr, w["r3"], w["WdT"], w["WgT"], e, plan.N,
+                     sm_count(x.device), red, e_out)
+            elif fast:
+                call("tb_reduce_fwd_fast", vec4, bas, plan.tri_ptr, plan.tri_e2, w["r3"], w["WdT"], w["WgT"], e, E,
+                     plan.tri_group, sm_count(x.device), red, e_out)
+            else:
+                call("tb_reduce_fwd", vec4, bas, plan.tri_ptr, plan.tri_e2, w["consts"], w["WdT"], w["WgT"], e, E, L,
+                     R, F, plan.tri_group, red, e_out)
         ctx.plan, ctx.w, ctx.L, ctx.R, ctx.F, ctx.fast, ctx.atom = plan, w, L, R, F, fast, atom
-        ctx.save_for_backward(vec4, sig, bas, red)
+        ctx.radial = radial
+        if moment:
+            ctx.save_for_backward(vec4, sig, red)
+        else:
+            ctx.save_for_backward(vec4, sig, bas, red)
         return e_out
 
     @staticmethod
     def backward(ctx, g_e):
-        vec4, sig, bas, red = ctx.saved_tensors
         plan, w, L, R, F = ctx.plan, ctx.w, ctx.L, ctx.R, ctx.F
         E, N, D = plan.E, plan.N, L * R
         g_e = g_e.contiguous()
+        if ctx.radial is not None:
+            vec4, sig, red = ctx.saved_tensors
+            G, dG = ctx.radial
+            g_vec4 = torch.empty_like(vec4)
+            g_sig_e = torch.empty_like(red)
+            call("tb_mom_bwd", vec4, G, dG, sig, plan.dst, red, g_e, plan.edge_ptr, plan.tri_ptr, w["r3"], w["WdT"],
+                 w["WgT"], N, plan.max_members, sm_count(vec4.device), g_vec4, g_sig_e)
+            g_x = _empty((N, F), vec4)
+            call("tb_sigma_bwd", g_sig_e, plan.in_ptr, plan.in_perm, sig, w["Ws"], N, F, D, g_x)
+            return g_x, g_e, g_vec4, None, None, None, None, None
+        vec4, sig, bas, red = ctx.saved_tensors
         g_red = torch.empty_like(red)
         g_vec4 = torch.empty_like(vec4)
         g_bas = torch.empty_like(bas)
@@ -205,7 +230,7 @@ class ThreeBodyFn(Function):
              g_vec4, g_sig_e)
         g_x = _empty((N, F), vec4)
         call("tb_sigma_bwd", g_sig_e, plan.in_ptr, plan.in_perm, sig, w["Ws"], N, F, D, g_x)
-        return g_x, g_e, g_vec4, None, None, None, None
+        return g_x, g_e, g_vec4, None, None, None, None, None
 
 
 class ConvFn(Function):

@@ -5,18 +5,21 @@ import os
 
 import torch
 
+from torch_m3gnet_b200._lib import call
 from torch_m3gnet_b200.data import MaterialGraphKey as K
 from torch_m3gnet_b200.data.material_graph import get_plan
 from torch_m3gnet_b200.nn._bessel_zeros import SPHERICAL_BESSEL_ZEROS
-from torch_m3gnet_b200.nn._functions import CutoffFn, LegendreCosFn, SphericalBesselFn, ThreeBodyFn
+from torch_m3gnet_b200.nn._functions import CutoffFn, GeometryFn, LegendreCosFn, SphericalBesselFn, ThreeBodyFn
 from torch_m3gnet_b200.nn._packing import PackedWeights, c_, t_
 from torch_m3gnet_b200.nn.core import GatedMLP
 from torch_m3gnet_b200.nn.invariant import PAIR_VEC4
 
-# "atom" (default): per-centre-atom kernels for (l_max, n_max, F) = (3, 3, 64) when the plan certifies the canonical
-# triplet layout (csrc/threebody_atom.cu), otherwise "fast"; "fast": specialised CSR kernels for (3, 3, 64);
-# "generic": the width-agnostic CSR kernels everywhere
-TB_PATH = os.environ.get("M3G_TB_PATH", "atom")
+# "moment" (default): O(n3)-per-atom moment kernels for (l_max, n_max, F) = (3, 3, 64) when the plan certifies the
+# canonical triplet layout (csrc/threebody_moment.cu), falling back like "atom"; "atom": per-centre-atom pair-matrix
+# kernels (csrc/threebody_atom.cu), otherwise "fast"; "fast": specialised CSR kernels for (3, 3, 64); "generic": the
+# width-agnostic CSR kernels everywhere
+TB_PATH = os.environ.get("M3G_TB_PATH", "moment")
+RADIAL_CACHE = "_tb_radial"
 
 __all__ = ["ThreeBodyInteration", "NormalizedSphericalBessel", "SPHERICAL_BESSEL_ZEROS", "spherical_bessel",
            "legendre_cos", "cutoff_function"]
@@ -108,13 +111,47 @@ class ThreeBodyInteration(torch.nn.Module):
             "Ws": c_(self.linear_sigmoid1.weight), "bs": c_(self.linear_sigmoid1.bias),
             "WdT": t_(self.gated_mlp.dense[0].weight), "WgT": t_(self.gated_mlp.gate[0].weight),
             "consts": torch.cat([zeros, fac, tail]).contiguous(), "r3": float(self.threebody_cutoff),
+            # host copy of the constants: key of the per-step cache of the block-invariant radial tables
+            "consts_key": tuple(torch.cat([zeros, fac, tail]).tolist()),
         }
+
+    def _radial(self, graph, plan, vec4, w):
+        """(G, dG) = m3g_tb_radial for this block's constants; shared by all blocks with equal constants."""
+        cache = graph._private.get(RADIAL_CACHE)
+        if cache is None or cache["vec4"] is not vec4 or cache["version"] != vec4._version:
+            cache = graph._private[RADIAL_CACHE] = {"vec4": vec4, "version": vec4._version, "tables": {}}
+        tab = cache["tables"].get(w["consts_key"])
+        if tab is None:
+            E, D = plan.E, self.degree
+            G = torch.empty((E, D), dtype=torch.float32, device=vec4.device)
+            dG = torch.empty((E, D), dtype=torch.float32, device=vec4.device)
+            call("tb_radial", vec4.detach(), w["consts"], E, self.l_max, self.n_max, plan.member_edges, plan.n_members,
+                 G, dG)
+            tab = cache["tables"][w["consts_key"]] = (G, dG)
+        return tab
 
     def forward(self, graph):
         plan = get_plan(graph)
         vec4 = graph._private.get(PAIR_VEC4)
         if vec4 is None:
-            raise RuntimeError("ThreeBodyInteration needs the bond vectors computed by DistanceAndAngle")
-        graph[K.EDGE_ATTR] = ThreeBodyFn.apply(graph[K.NODE_FEATURES], graph[K.EDGE_ATTR], vec4, plan,
-                                               self._packed.get(), self.l_max, self.n_max)
+            # called on its own (reference nn/interaction.py:187-192 reads EDGE_DISTANCES / TRIPLET_ANGLES): derive the
+            # bond vectors from the public position / lattice keys, as DistanceAndAngle does
+            pos = graph[K.SCALED_POS] if graph[K.SCALED_POS] is not None else graph[K.POS]
+            lat = graph[K.SCALED_LATTICE] if graph[K.SCALED_LATTICE] is not None else graph[K.LATTICE]
+            with torch.cuda.device(pos.device):
+                vec4, dist, cos = GeometryFn.apply(pos, lat if lat.dim() == 3 else lat[None], plan,
+                                                   graph[K.TRIPLET_EDGE_INDEX])
+            graph._private[PAIR_VEC4] = vec4
+            if graph[K.EDGE_DISTANCES] is None:
+                graph[K.EDGE_DISTANCES] = dist
+            if graph[K.TRIPLET_ANGLES] is None:
+                graph[K.TRIPLET_ANGLES] = cos
+        w = self._packed.get()
+        radial = None
+        if (TB_PATH == "moment" and (self.l_max, self.n_max, self.num_edge_features) == (3, 3, 64)
+                and self.num_node_features == 64 and plan.tri_moment):
+            with torch.cuda.device(vec4.device):
+                radial = self._radial(graph, plan, vec4, w)
+        graph[K.EDGE_ATTR] = ThreeBodyFn.apply(graph[K.NODE_FEATURES], graph[K.EDGE_ATTR], vec4, plan, w, self.l_max,
+                                               self.n_max, radial)
         return graph
