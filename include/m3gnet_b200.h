@@ -39,8 +39,8 @@ extern "C" {
 #define M3G_ERR_UNSUPPORTED (-3)
 
 #define M3G_MAX_F 128 /* feature width supported by the kernels */
-#define M3G_MAX_L 4   /* l_max supported by the kernels (reference allows l_max <= 9) */
-#define M3G_MAX_R 4   /* n_max supported by the three-body kernels (reference allows <= 10) */
+#define M3G_MAX_L 9   /* l_max supported by the kernels = the reference's range (nn/interaction.py:250-253) */
+#define M3G_MAX_R 10  /* n_max supported by the three-body kernels = the reference's range */
 #define M3G_MAX_RADIAL 10 /* n_max supported by the radial (edge) basis */
 
 const char* m3g_last_error(void);
@@ -262,6 +262,14 @@ int m3g_tb_reduce_bwd_sym(const float* vec4, const float* bas, const float* g_re
  * ------------------------------------------------------------------------------------------- */
 int m3g_linear_fwd(const float* in, const float* Wt, const float* bias, int64_t n, int K, int M, float* out,
                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Elementwise pieces of a GatedMLP called on its own (nn/core.py:45-62): activation kind 0 = SiLU, 1 = sigmoid;
+ * m3g_act_bwd: out = g * act'(in); m3g_mul: out = a * b.  (csrc/elementwise.cu)
+ * ------------------------------------------------------------------------------------------- */
+int m3g_act_fwd(const float* in, int64_t n, int kind, float* out, void* stream);
+int m3g_act_bwd(const float* in, const float* g, int64_t n, int kind, float* out, void* stream);
+int m3g_mul(const float* a, const float* b, int64_t n, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * M3GNetConv (nn/conv.py:63-97, nn/core.py:6-62).  One "gated MLP on edges":

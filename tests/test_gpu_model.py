@@ -223,7 +223,7 @@ def test_cuda_graph_replay_matches_eager(device):
 
 
 @pytest.mark.parametrize("l_max,n_max,dim,blocks", [(3, 4, 64, 2), (4, 4, 64, 1), (2, 2, 64, 2), (3, 3, 128, 1),
-                                                    (1, 1, 32, 3)])
+                                                    (1, 1, 32, 3), (5, 3, 64, 1), (9, 10, 64, 1)])
 def test_off_default_hyper_parameters(device, l_max, n_max, dim, blocks):
     """Other (l_max, n_max, width, depth): n_max = 4 takes the tensor-core forward with the FMA backward, l_max = 4
     and width != 64 the generic kernels; whole model against the oracle on a two-species cell with O(1) factors."""

@@ -128,12 +128,15 @@ def test_calculator_equals_fresh_graph_per_frame(device):
         cart = cart + rng.normal(0.0, 0.03, size=cart.shape)
     assert calc.neighbor_list.n_rebuilds < calc.neighbor_list.n_frames
     atoms = _Atoms(lat, cart, z)
-    res = calc.calculate(atoms, ("energy", "forces", "stress"))
+    res = calc.calculate(atoms, ("energy", "forces"))
     out = model(Batch.from_arrays(lat[None], cart, z, [len(cart)], 5.0, 4.0, device=device))
     assert res["energy"] == float(out["total_energy"][0]) == res["free_energy"]
     np.testing.assert_array_equal(res["forces"], out["forces"].double().cpu().numpy())
-    np.testing.assert_array_equal(res["stress"], out["stresses"][0].double().cpu().numpy())
-    assert calc.get_forces(atoms).shape == (32, 3) and calc.get_stress(atoms).shape == (6,)
+    np.testing.assert_array_equal(res["m3gnet_stresses"], out["stresses"][0].double().cpu().numpy())
+    assert calc.get_forces(atoms).shape == (32, 3) and calc.get_reference_stresses(atoms).shape == (6,)
+    assert calc.calculate(atoms, ("forces",)) is res  # unchanged atoms: cached results, no second evaluation
+    with pytest.raises(NotImplementedError):
+        calc.calculate(atoms, ("stress",))  # the reference's row is not ASE's stress: not advertised
     assert isinstance(calc.get_potential_energy(atoms), float)
     with pytest.raises(NotImplementedError):
         calc.calculate(atoms, ("magmoms",))

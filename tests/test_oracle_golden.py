@@ -140,3 +140,44 @@ def test_rotation_invariance_of_distance_multiset():
     d1 = np.sort(O.neighbor_list_bruteforce(lat2, pos2, 5.0)[3])
     d2 = np.sort(O.neighbor_list_bruteforce(lat2 @ rot.T, pos2 @ rot.T, 5.0)[3])
     assert d1.shape == d2.shape and np.allclose(d1, d2, atol=1e-9)
+
+
+def _model_fixture(name):
+    g = golden(name)
+    hp = O.HyperParams(l_max=int(g["l_max"]), n_max=int(g["n_max"]), embedding_dim=int(g["dim"]), num_blocks=1)
+    return g, hp
+
+
+def test_wide_and_maximal_basis_sizes():
+    """l_max = 5 / n_max = 6 and the reference's largest basis l_max = 9 / n_max = 10 (nn/interaction.py:250-253)."""
+    torch.set_num_threads(1)
+    for name in ("wide_lr", "max_lr"):
+        g, hp = _model_fixture(name)
+        out = O.forward(state_dict_of(g), hp, clone_graph(graph_dict(g)), factors=torch.from_numpy(g["factors"]))
+        for k in OUT_KEYS:
+            report(f"{name}.{k}", out[k], g["out." + k], atol=2e-8, rtol=5e-6)
+
+
+def test_gated_mlp_called_on_its_own():
+    """GatedMLP.forward (nn/core.py:61-62): three layer stacks incl. the is_output / bias-free variants."""
+    g = golden("gated_mlp")
+    for i in range(3):
+        cfg = g[f"m{i}.cfg"].tolist()
+        fin, is_out, bias, dims = cfg[0], bool(cfg[1]), bool(cfg[2]), cfg[3:]
+        sd = {"m." + k[len(f"m{i}.sd."):]: torch.from_numpy(np.array(g[k])) for k in g.files if k.startswith(f"m{i}.sd.")}
+        x = torch.from_numpy(g[f"m{i}.x"]).requires_grad_(True)
+        y = O.gated_mlp(sd, "m", x, len(dims), is_output=is_out, bias=bias)
+        (gx,) = torch.autograd.grad(y, x, grad_outputs=torch.from_numpy(g[f"m{i}.go"]))
+        report(f"gmlp{i}.y", y, g[f"m{i}.y"], 1e-8, 2e-6)
+        report(f"gmlp{i}.gx", gx, g[f"m{i}.gx"], 1e-8, 5e-6)
+
+
+def test_bonds_not_grouped_by_source():
+    """The reference accepts any bond order (scatter by index); fixture: randomly permuted bonds."""
+    torch.set_num_threads(1)
+    g = golden("unsorted_edges")
+    gd = graph_dict(g)
+    assert not bool((gd["edge_index"][0][1:] >= gd["edge_index"][0][:-1]).all())
+    out = O.forward(state_dict_of(g), O.HyperParams(), clone_graph(gd), factors=torch.from_numpy(g["factors"]))
+    for k in OUT_KEYS:
+        report(f"unsorted.{k}", out[k], g["out." + k], atol=2e-8, rtol=5e-6)

@@ -56,7 +56,7 @@ def main():
     v0 -= v0.mean(axis=0)
 
     def run_arm(force_rebuild: bool):
-        calc = m3g.M3GNetCalculator(model, 5.0, 4.0, skin=args.skin, device=dev,
+        calc = m3g.M3GNetCalculator(model, 5.0, 4.0, skin=args.skin, device=dev, round_allocations=True,
                                     graph_replay=args.replay and not force_rebuild)
         md = m3g.VelocityVerlet(calc, lat, cart, z, mass, dt=args.dt, velocities=v0)
 

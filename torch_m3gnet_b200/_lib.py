@@ -121,11 +121,15 @@ def _ptr(t):
 _ENTRY = {}  # name -> (function, indices of the pointer arguments, number of arguments before the stream)
 
 if hasattr(torch._C, "_cuda_getCurrentRawStream") and hasattr(torch._C, "_cuda_getDevice"):
-    def _raw_stream() -> int:
-        return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+    _current_device = torch._C._cuda_getDevice
+
+    def _raw_stream(index: int) -> int:
+        return torch._C._cuda_getCurrentRawStream(index)
 else:  # older / newer torch without the raw accessors
-    def _raw_stream() -> int:
-        return torch.cuda.current_stream().cuda_stream
+    _current_device = torch.cuda.current_device
+
+    def _raw_stream(index: int) -> int:
+        return torch.cuda.current_stream(index).cuda_stream
 
 
 def _entry(name: str):
@@ -142,14 +146,32 @@ def call(name: str, *args):
 
     This is the per-launch host path (~70 calls per model step), so it is kept short: cached prototypes, raw stream
     handle straight from the runtime."""
-    global CALLS, LAUNCHES
     fn, ptr_idx, n = _entry(name)
     if len(args) != n:
         raise TypeError(f"m3g_{name}: expected {n} arguments before the stream, got {len(args)}")
     conv = list(args)
+    index = -1
     for k in ptr_idx:
-        conv[k] = _ptr(conv[k])
-    stream = _raw_stream()
+        t = conv[k]
+        if index < 0:
+            dev = getattr(t, "device", None)
+            if dev is not None and dev.type == "cuda":
+                index = dev.index
+        conv[k] = _ptr(t)
+    current = _current_device()
+    if index < 0:
+        index = current
+    if index != current:
+        # the kernels run where the data lives (as torch ops do), not on the thread's current device: a batch on
+        # cuda:1 while cuda:0 is current launches on cuda:1's current stream
+        with torch.cuda.device(index):
+            return _launch(name, fn, conv, index)
+    return _launch(name, fn, conv, index)
+
+
+def _launch(name, fn, conv, index):
+    global CALLS, LAUNCHES
+    stream = _raw_stream(index)
     if PROFILE is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()

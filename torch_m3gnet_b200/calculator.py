@@ -8,7 +8,7 @@ data/verlet.py) and the unchanged model, so every frame's energy / forces / stre
 ``Batch.from_arrays`` + ``model(batch)`` call.
 
 ``M3GNetCalculator`` follows ASE's calculator protocol by duck typing (``calculate(atoms, properties,
-system_changes)``, ``results``, ``get_potential_energy / get_forces / get_stress``) without importing ase: ``atoms`` only
+system_changes)``, ``results``, ``get_potential_energy / get_forces``) without importing ase: ``atoms`` only
 needs ``get_cell()``, ``get_positions()`` and ``get_atomic_numbers()`` (``numpy`` arrays, Å).
 """
 from __future__ import annotations
@@ -49,10 +49,13 @@ class M3GNetCalculator:
     ``Gradient`` module returns them, nn/gradient.py:39-62 -- same order, sign and units as the reference, not
     re-normalised to ASE's convention) for one structure or a batch; neighbour candidates cached between calls."""
 
-    implemented_properties = ("energy", "free_energy", "forces", "stress")
+    # "stress" is deliberately NOT advertised: the model's ``stresses`` row is the reference's origin-dependent
+    # sum_i pos_i (x) F_i / V (nn/gradient.py:39-62), whose sign and meaning differ from ASE's +dE/d(strain)/V; it
+    # stays available as ``results["m3gnet_stresses"]`` / ``get_reference_stresses``
+    implemented_properties = ("energy", "free_energy", "forces")
 
     def __init__(self, model: torch.nn.Module, cutoff: float = 5.0, threebody_cutoff: float = 4.0, skin: float = 0.5,
-                 device: Optional[torch.device] = None, round_allocations: bool = True, graph_replay: bool = False,
+                 device: Optional[torch.device] = None, round_allocations: bool = False, graph_replay: bool = False,
                  replay_after: int = 2):
         """``graph_replay=True`` (small systems, relaxations / cold MD): while consecutive frames keep the same bonds,
         images and three-body membership, the step is replayed from a CUDA graph (``GraphedStep``) instead of being
@@ -65,6 +68,7 @@ class M3GNetCalculator:
         self.cutoff, self.threebody_cutoff, self.skin = float(cutoff), float(threebody_cutoff), float(skin)
         self.device = device
         self.results: Dict[str, object] = {}
+        self._ase_state = None
         self._list: Optional[VerletList] = None
         self._key = None
         self.graph_replay = bool(graph_replay)
@@ -129,10 +133,18 @@ class M3GNetCalculator:
         if unknown:
             raise NotImplementedError(f"properties not implemented: {unknown}")
         cell = np.asarray(atoms.get_cell(), dtype=np.float64).reshape(3, 3)
-        e, f, s = self.compute(cell, np.asarray(atoms.get_positions(), dtype=np.float64), atoms.get_atomic_numbers())
+        pos = np.asarray(atoms.get_positions(), dtype=np.float64)
+        numbers = np.asarray(atoms.get_atomic_numbers())
+        # unchanged atoms: hand back the cached results (ASE calculators do the same through system_changes); an
+        # optimizer asking for energy, then forces, costs one model evaluation
+        state = (cell.tobytes(), pos.tobytes(), numbers.tobytes())
+        if self.results and self._ase_state == state:
+            return self.results
+        e, f, s = self.compute(cell, pos, numbers)
         energy = float(e.reshape(-1)[0].item())
         self.results = {"energy": energy, "free_energy": energy, "forces": f.double().cpu().numpy(),
-                        "stress": s.reshape(-1).double().cpu().numpy()}
+                        "m3gnet_stresses": s.reshape(-1).double().cpu().numpy()}
+        self._ase_state = state
         return self.results
 
     def get_potential_energy(self, atoms=None, force_consistent: bool = False):
@@ -141,8 +153,9 @@ class M3GNetCalculator:
     def get_forces(self, atoms=None):
         return self.calculate(atoms, ("forces",))["forces"]
 
-    def get_stress(self, atoms=None):
-        return self.calculate(atoms, ("stress",))["stress"]
+    def get_reference_stresses(self, atoms=None):
+        """The reference model's ``stresses`` row (nn/gradient.py:39-62), NOT ASE's stress convention."""
+        return self.calculate(atoms, ("energy",))["m3gnet_stresses"]
 
 
 class VelocityVerlet:

@@ -13,8 +13,7 @@
 
 namespace m3g {
 
-__device__ __constant__ float kYpref[4] = {0.28209479177387814f, 0.4886025119029199f, 0.6307831305050401f,
-                                           0.7463526651802308f};
+__device__ __constant__ float kYpref[9] = {0.28209479177387814f, 0.48860251190291992f, 0.63078313050504009f, 0.7463526651802308f, 0.84628437532163447f, 0.9356025796273888f, 1.0171072362820548f, 1.0925484305920792f, 1.1631066229203195f};
 
 // j_l(x), l < L, by the reference's upward recurrence incl. its small-x branches (quirk Q4);
 // jl[l] and derivative dj[l] (nn/interaction.py:288-348)
@@ -208,12 +207,12 @@ __global__ void tb_reduce_fwd_kernel(const float4* __restrict__ vec4, const floa
 // in shared memory; bonds that are not the first bond of any triplet are skipped (their g_red row is never read
 // as "first bond" data; it is zero-filled so that stale memory cannot leak).
 constexpr int GATE_G = 8;
+template <int DM>
 __global__ void tb_gate_bwd_kernel(const float* __restrict__ red, const float* __restrict__ g_e,
                                    const float* __restrict__ WdT, const float* __restrict__ WgT,
                                    const int32_t* __restrict__ tri_ptr, int64_t E, int D, int F,
                                    float* __restrict__ g_red) {
   extern __shared__ float w_s[];  // [2][D][F]
-  constexpr int DM = M3G_MAX_L * M3G_MAX_R;
   for (int i = threadIdx.x; i < D * F; i += blockDim.x) {
     w_s[i] = WdT[i];
     w_s[D * F + i] = WgT[i];
@@ -428,13 +427,60 @@ __global__ void tb_radial_kernel(const float4* __restrict__ vec4, const float* _
       }
 }
 
+// the same for l_max = n_max = 3 (the shape the moment kernels serve): one reciprocal per argument instead of a
+// division per recurrence step (results within 2 ulp of the generic kernel; x <= 1e-8 keeps the reference's branch)
+__global__ void tb_radial33_kernel(const float4* __restrict__ vec4, const float* __restrict__ consts, int64_t n_work,
+                                   const int32_t* __restrict__ edge_list, float* __restrict__ G,
+                                   float* __restrict__ dG) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_work) return;
+  if (edge_list) e = edge_list[e];
+  const float r = vec4[e].w;
+  const float rc = consts[18], r3 = consts[19];
+  const float c = cutoff_poly(r, r3);
+  const float dc = cutoff_poly_grad(r, r3);
+  float g[9], dg[9];
+#pragma unroll
+  for (int d = 0; d < 9; ++d) {
+    const int l = d / 3;
+    const float z = consts[d];
+    const float x = __fdiv_rn(__fmul_rn(z, r), rc);
+    float j = 1.0f, dj = 0.0f;
+    if (x > 1e-8f) {
+      float sn, cs;
+      sincosf(x, &sn, &cs);
+      const float ix = __frcp_rn(x);
+      const float j0 = sn * ix;
+      const float j1 = (j0 - cs) * ix;
+      if (l == 0) { j = j0; dj = -j1; }
+      else if (l == 1) { j = j1; dj = j0 - 2.0f * ix * j1; }
+      else { const float j2 = 3.0f * ix * j1 - j0; j = j2; dj = j1 - 3.0f * ix * j2; }
+    } else {
+      float jl[3], djl[3];
+      sph_bessel_all<3>(x, l, jl, djl);
+      j = jl[0]; dj = djl[0];
+      if (l == 1) { j = jl[1]; dj = djl[1]; }
+      if (l == 2) { j = jl[2]; dj = djl[2]; }
+    }
+    const float ifac = __frcp_rn(consts[9 + d]);
+    const float chi = j * ifac, dchi = dj * (z / rc) * ifac;
+    g[d] = chi * c;
+    dg[d] = dchi * c + chi * dc;
+  }
+#pragma unroll
+  for (int d = 0; d < 9; ++d) {
+    G[e * 9 + d] = (c != 0.0f) ? g[d] : 0.0f;
+    dG[e * 9 + d] = (c != 0.0f) ? dg[d] : 0.0f;
+  }
+}
+
+template <int DM>
 __global__ void tb_sigma_bwd_kernel(const float* __restrict__ g_sig_e, const int32_t* __restrict__ in_ptr,
                                     const int32_t* __restrict__ in_perm, const float* __restrict__ sig,
                                     const float* __restrict__ Ws, int64_t N, int F, int D, float* __restrict__ g_x) {
   int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (k >= N) return;
-  constexpr int DM = M3G_MAX_L * M3G_MAX_R;
   float acc[DM];
 #pragma unroll
   for (int d = 0; d < DM; ++d) acc[d] = 0.0f;
@@ -706,7 +752,8 @@ using namespace m3g;
 #define M3G_DISPATCH_LR(KERNEL, ...)             \
   do {                                           \
     if (L <= 3 && R <= 3) { KERNEL(3, 3, __VA_ARGS__); } \
-    else { KERNEL(4, 4, __VA_ARGS__); }          \
+    else if (L <= 4 && R <= 4) { KERNEL(4, 4, __VA_ARGS__); } \
+    else { KERNEL(M3G_MAX_L, M3G_MAX_R, __VA_ARGS__); } \
   } while (0)
 
 extern "C" {
@@ -760,8 +807,20 @@ int m3g_tb_gate_bwd(const float* red, const float* g_e, const float* WdT, const 
   M3G_REQUIRE(red && g_e && WdT && WgT && tri_ptr && g_red, "m3g_tb_gate_bwd: null pointer");
   M3G_REQUIRE(D >= 1 && D <= M3G_MAX_L * M3G_MAX_R, "m3g_tb_gate_bwd: D=%d unsupported", D);
   size_t smem = (size_t)2 * D * F * sizeof(float);
-  tb_gate_bwd_kernel<<<blocks_for(E * GATE_G, 256), 256, smem, as_stream(stream)>>>(red, g_e, WdT, WgT, tri_ptr, E, D,
-                                                                                    F, g_red);
+  if (smem > 48 * 1024) {
+    cudaError_t err = cudaFuncSetAttribute(tb_gate_bwd_kernel<M3G_MAX_L * M3G_MAX_R>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) {
+      set_error("m3g_tb_gate_bwd: %zu bytes of shared memory for D=%d, F=%d: %s", smem, D, F, cudaGetErrorString(err));
+      return M3G_ERR_INVALID;
+    }
+  }
+  if (D <= 16)
+    tb_gate_bwd_kernel<16><<<blocks_for(E * GATE_G, 256), 256, smem, as_stream(stream)>>>(red, g_e, WdT, WgT, tri_ptr,
+                                                                                          E, D, F, g_red);
+  else
+    tb_gate_bwd_kernel<M3G_MAX_L * M3G_MAX_R><<<blocks_for(E * GATE_G, 256), 256, smem, as_stream(stream)>>>(
+        red, g_e, WdT, WgT, tri_ptr, E, D, F, g_red);
   M3G_LAUNCH_CHECK("m3g_tb_gate_bwd");
   return M3G_OK;
 }
@@ -808,9 +867,14 @@ int m3g_tb_radial(const float* vec4, const float* tb_consts, int64_t E, int L, i
   if (n_work == 0) return M3G_OK;
   M3G_REQUIRE(vec4 && tb_consts && G && dG, "m3g_tb_radial: null pointer");
   M3G_CHECK_LR("m3g_tb_radial");
+  if (L == 3 && R == 3) {
+    tb_radial33_kernel<<<blocks_for(n_work, 128), 128, 0, as_stream(stream)>>>((const float4*)vec4, tb_consts, n_work,
+                                                                              edge_list, G, dG);
+  } else {
 #define K_(LC, RC, ...) tb_radial_kernel<LC, RC><<<blocks_for(n_work, 128), 128, 0, as_stream(stream)>>>(__VA_ARGS__)
-  M3G_DISPATCH_LR(K_, (const float4*)vec4, tb_consts, n_work, L, R, edge_list, G, dG);
+    M3G_DISPATCH_LR(K_, (const float4*)vec4, tb_consts, n_work, L, R, edge_list, G, dG);
 #undef K_
+  }
   M3G_LAUNCH_CHECK("m3g_tb_radial");
   return M3G_OK;
 }
@@ -820,8 +884,12 @@ int m3g_tb_sigma_bwd(const float* g_sig_e, const int32_t* in_ptr, const int32_t*
   if (N == 0) return M3G_OK;
   M3G_REQUIRE(g_sig_e && in_ptr && in_perm && sig && Ws && g_x, "m3g_tb_sigma_bwd: null pointer");
   M3G_REQUIRE(D >= 1 && D <= M3G_MAX_L * M3G_MAX_R, "m3g_tb_sigma_bwd: D=%d unsupported", D);
-  tb_sigma_bwd_kernel<<<blocks_for(N * 32, 256), 256, 0, as_stream(stream)>>>(g_sig_e, in_ptr, in_perm, sig, Ws, N,
-                                                                              F, D, g_x);
+  if (D <= 16)
+    tb_sigma_bwd_kernel<16><<<blocks_for(N * 32, 256), 256, 0, as_stream(stream)>>>(g_sig_e, in_ptr, in_perm, sig, Ws,
+                                                                                    N, F, D, g_x);
+  else
+    tb_sigma_bwd_kernel<M3G_MAX_L * M3G_MAX_R><<<blocks_for(N * 32, 256), 256, 0, as_stream(stream)>>>(
+        g_sig_e, in_ptr, in_perm, sig, Ws, N, F, D, g_x);
   M3G_LAUNCH_CHECK("m3g_tb_sigma_bwd");
   return M3G_OK;
 }

@@ -226,7 +226,7 @@ __device__ __forceinline__ int stage(float* ent, int cap, int beg, int end, cons
 
 // ------------------------------------------------------------------------------------------------
 // forward: red (member bonds) and e_out = e_in + SiLU(red WdT) * sigmoid(red WgT) (all bonds)
-__global__ void __launch_bounds__(32 * MW) tb_mom_fwd_kernel(
+__global__ void __launch_bounds__(32 * MW, 3) tb_mom_fwd_kernel(
     const float4* __restrict__ vec4, const float* __restrict__ G, const float* __restrict__ sig,
     const int32_t* __restrict__ dst, const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ tri_ptr,
     float r3, const float* __restrict__ WdT, const float* __restrict__ WgT, const float* __restrict__ e_in, int64_t N,
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(32 * MW) tb_mom_fwd_kernel(
 // ------------------------------------------------------------------------------------------------
 // backward: g_vec4 (E,4) = d/d(v, r) (zeros for non-member bonds; includes the fc' and the radial-basis chain through
 // dG) and g_sig_e (E,9) = per-bond gradient of sigma[dst] (zeros for non-member bonds)
-__global__ void __launch_bounds__(32 * MW) tb_mom_bwd_kernel(
+__global__ void __launch_bounds__(32 * MW, 4) tb_mom_bwd_kernel(
     const float4* __restrict__ vec4, const float* __restrict__ G, const float* __restrict__ dG,
     const float* __restrict__ sig, const int32_t* __restrict__ dst, const float* __restrict__ red,
     const float* __restrict__ g_e, const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ tri_ptr, float r3,
@@ -475,12 +475,16 @@ using namespace m3g;
 static inline int pick_cap(int max_members) { return max_members <= 32 ? 32 : (max_members <= 64 ? 64 : 128); }
 
 template <typename Kernel>
-static inline int mom_launch_shape(Kernel kernel, size_t smem, int64_t N, int n_sm, unsigned* grid) {
+static inline int mom_launch_shape(Kernel kernel, size_t smem, int64_t N, int n_sm, bool max_shared, unsigned* grid) {
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) {
     set_error("three-body moment kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     return M3G_ERR_CUDA;
   }
+  // backward: all of the unified L1 / shared memory as shared memory (4 CTAs per SM; the entries hold the reused data);
+  // the forward streams the edge rows and keeps the default split (measured: 0.416 vs 0.445 ms at C5)
+  if (max_shared)
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * MW, smem) != cudaSuccess || per_sm < 1)
     per_sm = 1;
@@ -504,7 +508,7 @@ int m3g_tb_mom_fwd(const float* vec4, const float* G, const float* sig, const in
   const int cap = pick_cap(max_members);
   const size_t smem = (size_t)MW * (cap * ES + M_SIDE) * sizeof(float);
   unsigned grid;
-  int rc = mom_launch_shape(tb_mom_fwd_kernel, smem, N, n_sm, &grid);
+  int rc = mom_launch_shape(tb_mom_fwd_kernel, smem, N, n_sm, false, &grid);
   if (rc != M3G_OK) return rc;
   tb_mom_fwd_kernel<<<grid, 32 * MW, smem, as_stream(stream)>>>((const float4*)vec4, G, sig, dst, edge_ptr, tri_ptr, r3,
                                                                WdT, WgT, e_in, N, cap, red, e_out);
@@ -524,7 +528,7 @@ int m3g_tb_mom_bwd(const float* vec4, const float* G, const float* dG, const flo
   const int cap = pick_cap(max_members);
   const size_t smem = (size_t)MW * (cap * ES + 2 * M_SIDE) * sizeof(float);
   unsigned grid;
-  int rc = mom_launch_shape(tb_mom_bwd_kernel, smem, N, n_sm, &grid);
+  int rc = mom_launch_shape(tb_mom_bwd_kernel, smem, N, n_sm, true, &grid);
   if (rc != M3G_OK) return rc;
   tb_mom_bwd_kernel<<<grid, 32 * MW, smem, as_stream(stream)>>>((const float4*)vec4, G, dG, sig, dst, red, g_e, edge_ptr,
                                                                tri_ptr, r3, WdT, WgT, N, cap, (float4*)g_vec4, g_sig_e);

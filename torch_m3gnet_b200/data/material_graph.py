@@ -239,7 +239,7 @@ class Batch(MaterialGraph):
 
     @classmethod
     def _assemble(cls, lat64, cart64, types, atom_ptr, batch, N, edge_ptr, E, edge_index, shift, dist, member,
-                  want_triplet_index, lat32=None):
+                  want_triplet_index, lat32=None, type_range=None):
         """Triplets of the bond list + the Batch object with its plan seeded from the builder's CSR."""
         device = cart64.device
         i32 = dict(dtype=torch.int32, device=device)
@@ -269,6 +269,7 @@ class Batch(MaterialGraph):
         m = int(nti.max().item()) if N > 0 else 0
         max_members = 0 if m == 0 else int(round((1.0 + (1.0 + 4.0 * m) ** 0.5) / 2.0))
         plan = GraphPlan.from_builder(g, atom_ptr, edge_ptr, tri_ptr, tri_e2, max_members=max_members)
+        plan._type_range = type_range
         object.__setattr__(g, "_plan", plan)
         return g
 
@@ -298,9 +299,45 @@ class Batch(MaterialGraph):
             edge_ptr, E, edge_index, shift, dist, member = cls._sweep(lattices, lat64, cart64, atom_ptr, B, N, cutoff,
                                                                       threebody_cutoff, device)
             batch = torch.repeat_interleave(torch.arange(B, device=device), torch.as_tensor(list(sizes), device=device))
-            types = torch.as_tensor(np.asarray(atomic_numbers, dtype=np.int64) - 1).to(device)
+            types_h = np.asarray(atomic_numbers, dtype=np.int64) - 1
+            types = torch.as_tensor(types_h).to(device)
+            type_range = (int(types_h.min()), int(types_h.max())) if N > 0 else (0, 0)
             return cls._assemble(lat64, cart64, types, atom_ptr, batch, N, edge_ptr, E, edge_index, shift, dist,
-                                 member, want_triplet_index)
+                                 member, want_triplet_index, type_range=type_range)
+
+
+class EdgesNotGrouped(ValueError):
+    """edge_index[0] is not non-decreasing: the kernels need the bonds of an atom to be contiguous.  ``Gradient``
+    catches this and evaluates a regrouped copy of the graph (``regroup_by_source``)."""
+
+
+def regroup_by_source(g: "MaterialGraph"):
+    """Stable sort of the bonds by source atom (ties keep the caller's order): returns (shadow graph whose bond-level
+    tensors are regrouped and whose triplet list is renumbered accordingly, ``rank`` with rank[e] = row of the caller's
+    bond e in the shadow).  Node- and structure-level tensors are shared with ``g``."""
+    ei = g[K.EDGE_INDEX].contiguous()
+    dev = ei.device
+    E, N = int(ei.size(1)), int(g[K.POS].size(0))
+    i32 = dict(dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        src = torch.empty(E, **i32)
+        _lib.call("narrow_i64", ei[0].contiguous(), src, E)
+        ptr = torch.empty(N + 1, **i32)
+        perm = torch.empty(max(E, 1), **i32)
+        work = torch.empty(N + 1 + _lib.scan_work_elems(N), **i32)
+        _lib.call("csr_by_key", src, E, N, ptr, perm, work)  # rows ascending in the original bond id: stable
+    perm = perm[:E].long()
+    rank = torch.empty(E, dtype=torch.long, device=dev)
+    rank[perm] = torch.arange(E, device=dev)
+    tri = g[K.TRIPLET_EDGE_INDEX]
+    ntij = g[K.NUM_TRIPLET_IJ]
+    shadow = Batch(pos=g[K.POS], atom_types=g[K.ATOM_TYPES], num_triplet_i=g[K.NUM_TRIPLET_I],
+                   edge_index=ei[:, perm].contiguous(), edge_cell_shift=g[K.EDGE_CELL_SHIFT][perm].contiguous(),
+                   num_triplet_ij=None if ntij is None else ntij[perm].contiguous(),
+                   triplet_edge_index=None if tri is None else rank[tri].contiguous(), lattice=g[K.LATTICE])
+    if g._store.get(K.BATCH) is not None:
+        shadow._store[K.BATCH] = g[K.BATCH]
+    return shadow, rank
 
 
 def _sig(t: Optional[torch.Tensor]):
@@ -316,6 +353,23 @@ class GraphPlan:
         self.N = self.E = self.T = self.B = 0
         self.signature = None
         self.tri_group = 8
+        self._type_range = None
+
+    def check_types(self, limit: int, what: str):
+        """Raise unless every atom type (= Z - 1) indexes a table of ``limit`` rows.  The reference fails loudly here
+        too (nn/featurizer.py:36 one_hot: "Class values must be smaller than num_classes"); the kernels index their
+        tables unchecked.  The (min, max) pair is read back once per plan (seeded from the host arrays by the graph
+        builder)."""
+        if self._type_range is None:
+            if self.N == 0:
+                self._type_range = (0, 0)
+            else:
+                lo, hi = torch.aminmax(self.types)
+                self._type_range = (int(lo.item()), int(hi.item()))
+        lo, hi = self._type_range
+        if lo < 0 or hi >= limit:
+            raise ValueError(f"atom_types (atomic number - 1) span [{lo}, {hi}] but {what} has {limit} entries "
+                             f"(valid types are 0 .. {limit - 1})")
 
     @staticmethod
     def signature_of(g: MaterialGraph):
@@ -402,8 +456,9 @@ class GraphPlan:
         if not (f_src[1] and f_dst[1]):
             raise ValueError("edge_index contains atom indices outside [0, num_nodes)")
         if not f_src[0]:
-            raise ValueError("edge_index[0] must be non-decreasing (edges grouped by source atom, as "
-                             "MaterialGraph.from_structure produces them)")
+            raise EdgesNotGrouped("edge_index[0] must be non-decreasing (edges grouped by source atom, as "
+                                  "MaterialGraph.from_structure produces them); the full model regroups such graphs "
+                                  "itself, single layers need regroup_by_source() first")
         _lib.call("check_sorted", p.batch, p.N, p.B, flags)
         f_b = flags[:2].tolist()
         if not (f_b[0] and f_b[1]):

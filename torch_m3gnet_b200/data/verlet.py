@@ -42,7 +42,9 @@ class VerletList:
             self.atom_ptr = torch.as_tensor(np.concatenate([[0], np.cumsum(self.sizes)]).astype(np.int32)).to(dev)
             self.batch = torch.repeat_interleave(torch.arange(self.B, device=dev),
                                                  torch.as_tensor(self.sizes, device=dev))
-            self.types = torch.as_tensor(np.asarray(atomic_numbers, dtype=np.int64).reshape(-1) - 1).to(dev)
+            types_h = np.asarray(atomic_numbers, dtype=np.int64).reshape(-1) - 1
+            self.types = torch.as_tensor(types_h).to(dev)
+            self.type_range = (int(types_h.min()), int(types_h.max())) if types_h.size else (0, 0)
             if self.types.numel() != self.N:
                 raise ValueError("atomic_numbers and sizes disagree")
             self._max_d2 = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -112,7 +114,8 @@ class VerletList:
         cart64, edge_ptr, E, edge_index, shift, dist, member = frame
         with torch.cuda.device(self.device):
             return Batch._assemble(self.lat64, cart64, self.types, self.atom_ptr, self.batch, self.N, edge_ptr, E,
-                                   edge_index, shift, dist, member, self.want_triplet_index, lat32=self.lat32)
+                                   edge_index, shift, dist, member, self.want_triplet_index, lat32=self.lat32,
+                                   type_range=self.type_range)
 
     def update(self, cart) -> Batch:
         """Graph of the frame with coordinates ``cart`` ((N,3) numpy array or float64 CUDA tensor, Cartesian, A)."""

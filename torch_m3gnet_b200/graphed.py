@@ -45,9 +45,31 @@ class GraphedStep:
         with torch.cuda.graph(self.graph):
             out = model(batch)
         self.out: Dict[str, torch.Tensor] = {k: out[k] for k in _KEYS}
+        # the captured launches hold the device addresses of the packed weight images / constant tables that existed
+        # at capture time; remember what they were made from so that a later parameter edit is noticed
+        self._weights = self._weight_signature()
+
+    def _weight_signature(self):
+        sig = []
+        for m in self.model.modules():
+            packed = getattr(m, "_packed", None)
+            if packed is not None:
+                sig.append(tuple((p.data_ptr(), p._version, p.device) for p in packed._params()))
+            table = getattr(m, "elemental_energies", None)
+            if torch.is_tensor(table):
+                sig.append((table.data_ptr(), table._version, table.device))
+        return tuple(sig)
+
+    def stale(self) -> bool:
+        """True when a parameter / constant table the capture depends on was replaced or modified since
+        (``load_state_dict``, an optimizer step, an edit of ``nsb.factors`` or ``elemental_energies``)."""
+        return self._weight_signature() != self._weights
 
     @torch.no_grad()
     def __call__(self, pos: Optional[torch.Tensor] = None, lattice: Optional[torch.Tensor] = None):
+        if self.stale():
+            raise RuntimeError("the model's parameters changed after this GraphedStep was captured: build a new "
+                               "GraphedStep (the captured launches still point at the old packed weights)")
         if pos is not None:
             self._pos.copy_(pos)
         if lattice is not None:

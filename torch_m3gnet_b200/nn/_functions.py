@@ -1,13 +1,15 @@
 """torch.autograd.Functions over the C-ABI kernels (forward kernels + hand-written adjoint kernels).
 
-Only input gradients that lead back to the atomic positions are produced (forces = -dE/dpos); weight
-gradients and double backward (the reference's ``create_graph=True`` training path, nn/gradient.py:33) are
-out of scope for the inference hot path and raise if requested.
+Only input gradients that lead back to the atomic positions are produced (forces = -dE/dpos).  Weight gradients
+are not produced (the kernels read detached, re-laid-out copies of the parameters), and every ``backward`` is
+``once_differentiable``: asking for a double backward (the reference's ``create_graph=True`` training path,
+nn/gradient.py:33) raises instead of returning silently wrong gradients.
 """
 from __future__ import annotations
 
 import torch
 from torch.autograd import Function
+from torch.autograd.function import once_differentiable
 
 from torch_m3gnet_b200._lib import call
 
@@ -60,6 +62,7 @@ class ScaleFn(Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g):
         g = g.contiguous()
         out = torch.empty_like(g)
@@ -90,6 +93,7 @@ class GeometryFn(Function):
         return vec4, dist, cos
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g_vec4, g_dist, g_cos):
         (vec4,) = ctx.saved_tensors
         plan = ctx.plan
@@ -115,6 +119,7 @@ class RadialFn(Function):
         return h
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g_h):
         dist, consts = ctx.saved_tensors
         g = torch.empty_like(dist)
@@ -136,6 +141,7 @@ class EdgeAdjustFn(Function):
         return e0
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g_e0):
         h, Wt = ctx.saved_tensors
         E, R = h.shape
@@ -190,6 +196,7 @@ class ThreeBodyFn(Function):
         return e_out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g_e):
         plan, w, L, R, F = ctx.plan, ctx.w, ctx.L, ctx.R, ctx.F
         E, N, D = plan.E, plan.N, L * R
@@ -273,6 +280,7 @@ class ConvFn(Function):
         return x2, e2
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g_x2, g_e2):
         x, e, e2, h, P = ctx.saved_tensors
         plan, w = ctx.plan, ctx.w
@@ -338,6 +346,7 @@ class ReadoutFn(Function):
         return atomic, stot, tot
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g_atomic, g_stot, g_tot):
         (x,) = ctx.saved_tensors
         plan, w = ctx.plan, ctx.w
@@ -361,6 +370,7 @@ class SphericalBesselFn(Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, go):
         (dout,) = ctx.saved_tensors
         return dout * go, None
@@ -379,6 +389,7 @@ class LegendreCosFn(Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, go):
         (x,) = ctx.saved_tensors
         gx = torch.empty_like(x)
@@ -398,6 +409,76 @@ class CutoffFn(Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, go):
         (dout,) = ctx.saved_tensors
         return dout * go, None
+
+
+class LinearFn(Function):
+    """torch.nn.Linear inside a GatedMLP that is called on its own (reference nn/core.py:30-59): out = in W^T + b."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x2 = x.contiguous().reshape(-1, x.shape[-1])
+        n, K = x2.shape
+        M = weight.shape[0]
+        wt = weight.detach().t().contiguous()
+        out = _empty((n, M), x2)
+        call("linear_fwd", x2, wt, None if bias is None else bias.detach().contiguous(), n, K, M, out)
+        ctx.save_for_backward(weight.detach().contiguous())
+        ctx.shape = x.shape
+        return out.reshape(x.shape[:-1] + (M,))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (w,) = ctx.saved_tensors
+        M, K = w.shape
+        g2 = g.contiguous().reshape(-1, M)
+        out = _empty((g2.shape[0], K), g2)
+        call("linear_bwd_input", g2, w, None, g2.shape[0], K, M, out)
+        return out.reshape(ctx.shape), None, None
+
+
+class ActivationFn(Function):
+    """torch.nn.SiLU (kind 0) / torch.nn.Sigmoid (kind 1) of nn/core.py:45-59."""
+
+    @staticmethod
+    def forward(ctx, x, kind: int):
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        call("act_fwd", x, x.numel(), int(kind), out)
+        ctx.kind = int(kind)
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        out = torch.empty_like(x)
+        call("act_bwd", x, g.contiguous(), x.numel(), ctx.kind, out)
+        return out, None
+
+
+class MulFn(Function):
+    """dense(x) * gate(x) (nn/core.py:61-62)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous(), b.contiguous()
+        out = torch.empty_like(a)
+        call("mul", a, b, a.numel(), out)
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = g.contiguous()
+        ga, gb = torch.empty_like(a), torch.empty_like(b)
+        call("mul", g, b, a.numel(), ga)
+        call("mul", g, a, a.numel(), gb)
+        return ga, gb

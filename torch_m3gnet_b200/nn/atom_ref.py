@@ -23,6 +23,7 @@ class AtomRef(torch.nn.Module):
         if self._table_cache is None or self._table_cache[0] != sig:
             self._table_cache = (sig, src.detach().to(device=plan.device, dtype=torch.float32).contiguous())
         table = self._table_cache[1]
+        plan.check_types(int(table.numel()), "the elemental-energy table")
         out = torch.empty(plan.N, dtype=torch.float32, device=plan.device)
         call("atomref_fwd", table, plan.types, plan.N, out)
         graph[K.ELEMENTAL_ENERGIES] = out

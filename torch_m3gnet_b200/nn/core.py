@@ -4,9 +4,10 @@ import torch
 
 
 class GatedMLP(torch.nn.Module):
-    """Parameter container with the reference's layout (nn/core.py:6-62): ``dense`` and ``gate`` Sequentials
-    whose Linear layers sit at even indices (0, 2, 4 …) so that state_dict keys are identical.  The arithmetic
-    dense(x) * gate(x) is fused into the parent layer's CUDA kernel (csrc/conv.cu, threebody.cu, readout.cu)."""
+    """The reference's gated MLP (nn/core.py:6-62): ``dense`` and ``gate`` Sequentials whose Linear layers sit at
+    even indices (0, 2, 4 …) so that state_dict keys are identical.  Inside M3GNetConv / ThreeBodyInteration /
+    AtomWiseReadout the arithmetic dense(x) * gate(x) is fused into the parent layer's CUDA kernel (csrc/conv_tc.cu,
+    threebody_moment.cu, readout.cu); ``forward`` evaluates it on its own."""
 
     def __init__(self, in_features: int, dimensions: list[int], is_output: bool = False, use_bias: bool = True,
                  device: torch.device | None = None):
@@ -32,5 +33,24 @@ class GatedMLP(torch.nn.Module):
         seq = self.dense if branch == "dense" else self.gate
         return [m for m in seq if isinstance(m, torch.nn.Linear)]
 
-    def forward(self, input):  # pragma: no cover - the fused kernels own the arithmetic
-        raise RuntimeError("GatedMLP is evaluated inside the fused CUDA kernels of its parent layer")
+    def forward(self, input):
+        """dense(input) * gate(input) (reference nn/core.py:61-62) through the generic linear / activation kernels.
+        The parent layers never take this route (their fused kernels own the arithmetic); it serves a GatedMLP that
+        is called on its own.  Input gradients only, like every kernel-backed layer of this package."""
+        from torch_m3gnet_b200.nn._functions import ActivationFn, LinearFn, MulFn
+
+        def run(seq):
+            y = input
+            for m in seq:
+                if isinstance(m, torch.nn.Linear):
+                    y = LinearFn.apply(y, m.weight, m.bias)
+                elif isinstance(m, torch.nn.SiLU):
+                    y = ActivationFn.apply(y, 0)
+                elif isinstance(m, torch.nn.Sigmoid):
+                    y = ActivationFn.apply(y, 1)
+                else:  # pragma: no cover
+                    raise TypeError(f"unexpected layer {type(m).__name__} in a GatedMLP branch")
+            return y
+
+        with torch.cuda.device(input.device):
+            return MulFn.apply(run(self.dense), run(self.gate))

@@ -27,6 +27,7 @@ class AtomFeaturizer(torch.nn.Module):
     def forward(self, graph):
         plan = get_plan(graph)
         w = self._packed.get()["W"]
+        plan.check_types(self._num_types, "the atom embedding (num_types)")
         F = w.shape[0]
         x = torch.empty((plan.N, F), dtype=torch.float32, device=plan.device)
         call("embed_fwd", w, plan.types, plan.N, F, self._num_types, x)

@@ -4,7 +4,7 @@ import torch
 
 from torch_m3gnet_b200._lib import call
 from torch_m3gnet_b200.data import MaterialGraphKey as K
-from torch_m3gnet_b200.data.material_graph import get_plan
+from torch_m3gnet_b200.data.material_graph import EdgesNotGrouped, get_plan, regroup_by_source
 
 _OUTPUT_KEYS = (K.SCALED_POS, K.SCALED_LATTICE, K.EDGE_DISTANCES, K.TRIPLET_ANGLES, K.EDGE_WEIGHTS,
                 K.NODE_FEATURES, K.EDGE_ATTR, K.SCALED_ATOMIC_ENERGIES, K.SCALED_TOTAL_ENERGY, K.TOTAL_ENERGY)
@@ -23,8 +23,24 @@ class Gradient(torch.nn.Module):
         self.model = model
         self.keep_graph = False
 
+    def _forward_regrouped(self, graph):
+        """Bonds not grouped by source atom (hand-built graphs; the reference accepts any bond order): evaluate a
+        stably regrouped copy and hand every bond-level result back in the caller's order."""
+        shadow, rank = regroup_by_source(graph)
+        out = self.forward(shadow)
+        for k in _OUTPUT_KEYS + (K.ELEMENTAL_ENERGIES, K.FORCES, K.STRESSES):
+            v = out[k]
+            if torch.is_tensor(v) and k in (K.EDGE_DISTANCES, K.EDGE_WEIGHTS, K.EDGE_ATTR):
+                v = v.index_select(0, rank)
+            graph[k] = v
+        return graph
+
     def forward(self, graph):
         pos = graph[K.POS]
+        try:
+            get_plan(graph)
+        except EdgesNotGrouped:
+            return self._forward_regrouped(graph)
         pos.requires_grad_(True)
         graph = self.model(graph)
         energy = graph[K.TOTAL_ENERGY]
