@@ -202,9 +202,9 @@ int m3g_tb_reduce_bwd(const float* vec4, const float* bas, const float* g_red, c
 int m3g_tb_edge_basis_bwd(const float* vec4, const int32_t* dst, const float* sig, const float* g_bas,
                           const float* tb_consts, int64_t E, int L, int R, const int32_t* edge_list, int64_t n_list,
                           float* g_vec4, float* g_sig_e, void* stream);
-/* g_x (N,F) = (sum_{e in in(k)} g_sig_e[e]) * sig(1-sig) · Ws, Ws (D,F) */
+/* g_x (N,F) = base (N,F or NULL) + (sum_{e in in(k)} g_sig_e[e]) * sig(1-sig) · Ws, Ws (D,F) */
 int m3g_tb_sigma_bwd(const float* g_sig_e, const int32_t* in_ptr, const int32_t* in_perm, const float* sig,
-                     const float* Ws, int64_t N, int F, int D, float* g_x, void* stream);
+                     const float* Ws, const float* base, int64_t N, int F, int D, float* g_x, void* stream);
 
 /* Canonical triplet layout (what compute_threebody, data/material_graph.py:239-248, emits): for every atom the
  * rows of its member bonds (bonds with a non-empty triplet row) list exactly all other member bonds of that atom,
@@ -230,7 +230,8 @@ int m3g_tb_atom_bwd(const float* vec4, const float* bas, const float* red, const
  * m3g_tb_mom_capacity()).  m3g_tb_radial (once per step; nn/interaction.py:226-281, :389-400): G[e][d] = chi_d(r_e) fc(r_e)
  * and dG/dr for the listed member bonds.  m3g_tb_mom_fwd: red (member bonds) and e_out (all bonds) with bas = G *
  * sig[dst] formed in-kernel.  m3g_tb_mom_bwd: g_vec4 (E,4) complete (cos, fc' and radial chain; zeros for
- * non-members) and g_sig_e (E,9) (zeros for non-members), ready for m3g_tb_sigma_bwd.  The Legendre adjoint follows
+ * non-members; accumulate != 0 adds to the existing rows: the sum over the model's blocks) and g_sig_e (E,9) (zeros for
+ * non-members), ready for m3g_tb_sigma_bwd.  The Legendre adjoint follows
  * the reference's quirk (Q3) through second-order moments.  max_members: upper bound of member bonds per atom. */
 int m3g_tb_radial(const float* vec4, const float* tb_consts, int64_t E, int L, int R, const int32_t* edge_list,
                   int64_t n_list, float* G, float* dG, void* stream);
@@ -240,8 +241,8 @@ int m3g_tb_mom_fwd(const float* vec4, const float* G, const float* sig, const in
                    int max_members, int n_sm, float* red, float* e_out, void* stream);
 int m3g_tb_mom_bwd(const float* vec4, const float* G, const float* dG, const float* sig, const int32_t* dst,
                    const float* red, const float* g_e, const int32_t* edge_ptr, const int32_t* tri_ptr, float r3,
-                   const float* WdT, const float* WgT, int64_t N, int max_members, int n_sm, float* g_vec4,
-                   float* g_sig_e, void* stream);
+                   const float* WdT, const float* WgT, int64_t N, int max_members, int n_sm, int accumulate,
+                   float* g_vec4, float* g_sig_e, void* stream);
 
 /* Specialised variants for the default model shape l_max = n_max = 3, F = 64 (compile-time loops, gated-MLP
  * weights in shared memory, vector row I/O, persistent grid of 8 x n_sm blocks).  Same results and buffers as
@@ -270,6 +271,8 @@ int m3g_linear_fwd(const float* in, const float* Wt, const float* bias, int64_t 
 int m3g_act_fwd(const float* in, int64_t n, int kind, float* out, void* stream);
 int m3g_act_bwd(const float* in, const float* g, int64_t n, int kind, float* out, void* stream);
 int m3g_mul(const float* a, const float* b, int64_t n, float* out, void* stream);
+/* out = a + b (out may alias a or b) */
+int m3g_add(const float* a, const float* b, int64_t n, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * M3GNetConv (nn/conv.py:63-97, nn/core.py:6-62).  One "gated MLP on edges":
@@ -373,6 +376,87 @@ int m3g_forces_virial(const float* pos, const float* g_pos, const float* lattice
 /* out[r] = in[idx[r]] rows of width W floats (halo pack) ; in[idx[r]] += add[r] (reverse halo unpack) */
 int m3g_rows_gather(const float* in, const int32_t* idx, int64_t n, int W, float* out, void* stream);
 int m3g_rows_scatter_add(const float* add, const int32_t* idx, int64_t n, int W, float* inout, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Whole-step executor (csrc/step.cu): the launch sequence of  Gradient(Sequential[ScaleLength, AtomRef,
+ * DistanceAndAngle, AtomFeaturizer, EdgeFeaturizer, EdgeAdjustor, (ThreeBodyInteration, M3GNetConv) x n_blocks,
+ * AtomWiseReadout])  (model/build.py:37-83, nn/gradient.py:25-64) — forward kernels, then the hand-written adjoint
+ * kernels in reverse order, then forces + virial — issued from C with one call instead of ~70 Python round trips and
+ * an autograd pass.  Default model shape only (F = 64, l_max = n_max = 3, radial degree 3, canonical triplet layout);
+ * everything else stays on the per-operator entry points above.  All buffers are caller-owned device memory; the
+ * struct itself lives in HOST memory.  The sequence is cut into phases so that a caller can interleave its own work
+ * (the halo exchanges of a domain-decomposed cell, csrc/geometry.cu m3g_rows_*):
+ *
+ *   M3G_PHASE_PROLOGUE              scale, atom reference, geometry (+ cos), embedding, radial basis, e0, G / dG
+ *   M3G_PHASE_TB(b), M3G_PHASE_CONV(b)      b = 0 .. n_blocks-1   (x of block b+1 is blocks[b].x_out)
+ *   M3G_PHASE_READOUT(n)            energies; adjoint of the readout -> g_x
+ *   M3G_PHASE_CONV_BWD(n,b), M3G_PHASE_TB_BWD(n,b)   b = n_blocks-1 .. 0   (the adjoint w.r.t. blocks[b].x_in is
+ *                                   left in g_x[cur]; block 0 skips the dead gradient w.r.t. the embedding)
+ *   M3G_PHASE_EPILOGUE(n)           e0 / radial / geometry adjoints -> g_pos
+ *   M3G_PHASE_FORCES(n)             forces = -g_pos, virial stress
+ * ------------------------------------------------------------------------------------------- */
+#define M3G_STEP_MAX_BLOCKS 8
+#define M3G_PHASE_PROLOGUE 0
+#define M3G_PHASE_TB(b) (1 + 2 * (b))
+#define M3G_PHASE_CONV(b) (2 + 2 * (b))
+#define M3G_PHASE_READOUT(n) (1 + 2 * (n))
+#define M3G_PHASE_CONV_BWD(n, b) (2 + 2 * (n) + 2 * ((n)-1 - (b)))
+#define M3G_PHASE_TB_BWD(n, b) (3 + 2 * (n) + 2 * ((n)-1 - (b)))
+#define M3G_PHASE_EPILOGUE(n) (2 + 4 * (n))
+#define M3G_PHASE_FORCES(n) (3 + 4 * (n))
+
+typedef struct M3GStepBlock {
+  /* ThreeBodyInteration weights (nn/interaction.py:138-185): Ws (9,64), bs (9), WdT / WgT (9,64), tb_consts (20) */
+  const float *Ws, *bs, *WdT, *WgT, *tb_consts;
+  /* M3GNetConv weights (nn/conv.py:25-61): per-atom projection WpT (64,512) / bp (512) / Wp (512,64); per gated MLP
+   * the tcgen05 weight images (m3g_tc_pack_b), second-layer biases and the (3,64) radial weights */
+  const float *WpT, *bp, *Wp;
+  const float *e_wimg, *e_wimgT, *e_b2d, *e_b2g, *e_WhT;
+  const float *n_wimg, *n_wimgT, *n_b2d, *n_b2g, *n_WhT;
+  /* activations: G / dG (E,9) radial tables (blocks with equal constants share them; radial_owner = 1 computes),
+   * sig (N,9), red (E,9), x_in (N,64), e_in (E,64), e_tb (E,64), e_out (E,64), x_out (N,64), saved activations of
+   * the two gated MLPs (ceil(E/128)*128*256 floats each) */
+  float *G, *dG;
+  int radial_owner;
+  float *sig, *red;
+  const float *x_in, *e_in;
+  float *e_tb, *e_out, *x_out, *save_e, *save_n;
+} M3GStepBlock;
+
+typedef struct M3GStepDesc {
+  int64_t N, E, T, B;
+  int n_blocks, n_sm, passes, max_members;
+  int64_t n_members;
+  float length_scale, energy_scale, r3;
+  int num_types;
+  /* plan (int32 CSR views, see "Conventions") */
+  const int32_t *batch, *src, *dst, *shift, *types, *edge_ptr, *in_ptr, *in_perm, *tri_ptr, *atom_ptr, *member_edges;
+  const int64_t* tri_index; /* (2,T) caller-order list for the triplet_angles output, or NULL */
+  /* inputs */
+  const float *pos, *lattice;
+  /* layer weights outside the blocks */
+  const float *embed_W, *atomref_table, *radial_consts, *adjust_Wt;
+  const float *ro_W0dT, *ro_b0d, *ro_W1dT, *ro_b1d, *ro_w2d, *ro_b2d, *ro_W0gT, *ro_b0g, *ro_W1gT, *ro_b1g, *ro_w2g,
+      *ro_b2g, *ro_W0d, *ro_W1d, *ro_W0g, *ro_W1g;
+  const float* g_total; /* (B) upstream gradient of the structure energies (ones; owned / ghost weights for a domain) */
+  /* outputs / step-level activations */
+  float *scaled_pos, *scaled_lattice, *elemental, *vec4, *dist, *cos_t, *x0, *h, *e0;
+  float *atomic, *scaled_total, *total, *forces, *stresses;
+  /* scratch */
+  float *P, *msg;                 /* (N,512), (E,64) */
+  float *g_x[2];                  /* (N,64) ping-pong; g_x[cur] holds the running adjoint */
+  float *g_e[2], *ge2;            /* (E,64) */
+  float *gz_edge, *gz_node, *gP;  /* (E,128) x 2, (N,512) */
+  float *g_h, *g_h2, *g_sig_e, *g_vec4, *g_dist, *g_pos; /* (E,3) x 2, (E,9), (E,4), (E), (N,3) */
+  int cur_x, cur_e;               /* state carried between phases (updated by m3g_step_run) */
+  int have_g_e;                   /* 0 until the first conv adjoint has produced g_e */
+  M3GStepBlock blocks[M3G_STEP_MAX_BLOCKS];
+} M3GStepDesc;
+
+/* run phases first .. last (inclusive) on `stream`; returns the first non-zero status */
+int m3g_step_run(M3GStepDesc* desc, int first_phase, int last_phase, void* stream);
+/* sizeof(M3GStepDesc) as compiled (binding self-check) */
+int64_t m3g_step_desc_size(void);
 
 #ifdef __cplusplus
 }

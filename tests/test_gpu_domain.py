@@ -64,3 +64,52 @@ def test_distributed_domains_two_gpus():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0 and "DD-OK" in r.stdout
+
+
+def test_domain_step_single_rank_process_group(device):
+    """DomainStep (whole-step executor phases + NCCL halo exchanges) with a one-rank process group: every ghost is a
+    periodic image of an owned atom, so all halos are self-exchanges; against the undecomposed model."""
+    import torch.distributed as dist
+
+    from torch_m3gnet_b200.data.material_graph import Batch
+    from torch_m3gnet_b200.domain import DomainBatch, DomainPlan, DomainStep
+
+    created = False
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29531", world_size=1, rank=0,
+                                device_id=device)
+        created = True
+    try:
+        lat, cart, z = O.fcc_supercell(5, jitter=0.05, seed=4)  # 500 atoms, 18.1 A box
+        z = z.copy()
+        z[::3] = 13
+        model = _model(device)
+        full = model(Batch.from_arrays(lat[None], cart, z, [len(cart)], 5.0, 4.0, device=device))
+        plan = DomainPlan(lat, cart, z, (1, 1, 1), 5.0)
+        db = DomainBatch(plan, 0, 5.0, 4.0, device)
+        n = len(cart)
+        step = DomainStep(model, db, capture=False)
+        for _ in range(2):
+            res = step()
+        forces = torch.zeros((n, 3), device=device)
+        forces[res["owned"]] = res["forces"]
+        dE = (res["total_energy"] - full["total_energy"]).abs().item() / n
+        print(f"[dd-step] local={db.n_local} owned={db.n_own} |dE|/atom={dE:.3e} exchanges/step={step.exchanges_per_step}")
+        assert dE <= 1e-6
+        report("dd-step forces", forces, full["forces"], 2e-6, 1e-5)
+    finally:
+        if created:
+            torch.cuda.synchronize()
+            dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["engine", "graph"])
+def test_domain_step_one_rank_subprocess(mode):
+    """The torchrun entry with one rank: executor phases, and the whole step (NCCL exchanges included) captured in a
+    CUDA graph.  Runs in its own process: a process group that has captured collectives is left to process exit."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=1", "--master-addr",
+           "127.0.0.1", "--master-port", "29519", os.path.join(ROOT, "tests", "dd_multi_gpu.py"), "--cells", "5",
+           "--mode", mode]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0 and "DD-OK" in r.stdout

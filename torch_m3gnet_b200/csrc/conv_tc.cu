@@ -1213,20 +1213,23 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
       for (int i = 0; i < 4; ++i)
         gb[i] = __ldg(reinterpret_cast<const float4*>(p.g_e_base + min(erow[i], p.E - 1) * TC_F + k0 + 4 * cc4));
     }
-    // g_z1 rows straight from registers (overlaps GEMM4), coalesced through the staging tile
+    // g_z1 rows straight from registers (overlaps GEMM4), coalesced through the staging tile; skipped when the caller
+    // has no use for them (first block of the model: its node features do not depend on the positions)
+    if (p.g_z1 != nullptr) {
 #pragma unroll
-    for (int hb = 0; hb < 2; ++hb) {
-      const float* dz = hb ? zg : zd;
+      for (int hb = 0; hb < 2; ++hb) {
+        const float* dz = hb ? zg : zd;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        sts128(stg + stg_off(lane, c), make_float4(dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]));
-      __syncwarp();
+        for (int c = 0; c < 4; ++c)
+          sts128(stg + stg_off(lane, c), make_float4(dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]));
+        __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float4 r4 = lds128(stg + stg_off(8 * i + cr, cc4));
-        if (erow[i] < p.E) *reinterpret_cast<float4*>(p.g_z1 + erow[i] * 128 + 64 * hb + k0 + 4 * cc4) = r4;
+        for (int i = 0; i < 4; ++i) {
+          float4 r4 = lds128(stg + stg_off(8 * i + cr, cc4));
+          if (erow[i] < p.E) *reinterpret_cast<float4*>(p.g_z1 + erow[i] * 128 + 64 * hb + k0 + 4 * cc4) = r4;
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
     TCT(11);
     // ---- T7: g_e ----
@@ -1480,7 +1483,7 @@ int m3g_conv_tc_bwd_saved(const int32_t* src, const float* h, const float* wimgT
                           const float* g_up, const float* g_e_base, int64_t E, int R, int mode, int passes, int n_sm,
                           float* g_e, float* g_z1, float* g_h, void* stream) {
   if (E == 0) return M3G_OK;
-  M3G_REQUIRE(src && h && wimgT && WhT && save && g_up && g_e && g_z1 && g_h, "m3g_conv_tc_bwd_saved: null pointer");
+  M3G_REQUIRE(src && h && wimgT && WhT && save && g_up && g_e && g_h, "m3g_conv_tc_bwd_saved: null pointer");
   M3G_REQUIRE(R >= 1 && R <= TC_BWD_MAX_R, "m3g_conv_tc_bwd_saved: R=%d unsupported (max %d)", R, TC_BWD_MAX_R);
   M3G_REQUIRE(passes == 1 || passes == 3, "m3g_conv_tc_bwd_saved: passes must be 1 or 3");
   cudaError_t err =

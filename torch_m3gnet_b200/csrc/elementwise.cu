@@ -34,6 +34,11 @@ __global__ void mul_kernel(const float* __restrict__ a, const float* __restrict_
   if (i < n) out[i] = a[i] * b[i];
 }
 
+__global__ void add_kernel(const float* a, const float* b, int64_t n, float* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+
 }  // namespace m3g
 
 using namespace m3g;
@@ -61,6 +66,14 @@ int m3g_mul(const float* a, const float* b, int64_t n, float* out, void* stream)
   M3G_REQUIRE(a && b && out, "m3g_mul: null pointer");
   mul_kernel<<<blocks_for(n, 256), 256, 0, as_stream(stream)>>>(a, b, n, out);
   M3G_LAUNCH_CHECK("m3g_mul");
+  return M3G_OK;
+}
+
+int m3g_add(const float* a, const float* b, int64_t n, float* out, void* stream) {
+  if (n == 0) return M3G_OK;
+  M3G_REQUIRE(a && b && out, "m3g_add: null pointer");
+  add_kernel<<<blocks_for(n, 256), 256, 0, as_stream(stream)>>>(a, b, n, out);
+  M3G_LAUNCH_CHECK("m3g_add");
   return M3G_OK;
 }
 

@@ -477,7 +477,8 @@ __global__ void tb_radial33_kernel(const float4* __restrict__ vec4, const float*
 template <int DM>
 __global__ void tb_sigma_bwd_kernel(const float* __restrict__ g_sig_e, const int32_t* __restrict__ in_ptr,
                                     const int32_t* __restrict__ in_perm, const float* __restrict__ sig,
-                                    const float* __restrict__ Ws, int64_t N, int F, int D, float* __restrict__ g_x) {
+                                    const float* __restrict__ Ws, const float* __restrict__ base, int64_t N, int F,
+                                    int D, float* __restrict__ g_x) {
   int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (k >= N) return;
@@ -503,7 +504,7 @@ __global__ void tb_sigma_bwd_kernel(const float* __restrict__ g_sig_e, const int
 #pragma unroll
     for (int d = 0; d < DM; ++d)
       if (d < D) v += acc[d] * Ws[d * F + f];
-    g_x[k * F + f] = v;
+    g_x[k * F + f] = base ? base[k * F + f] + v : v;
   }
 }
 
@@ -880,16 +881,16 @@ int m3g_tb_radial(const float* vec4, const float* tb_consts, int64_t E, int L, i
 }
 
 int m3g_tb_sigma_bwd(const float* g_sig_e, const int32_t* in_ptr, const int32_t* in_perm, const float* sig,
-                     const float* Ws, int64_t N, int F, int D, float* g_x, void* stream) {
+                     const float* Ws, const float* base, int64_t N, int F, int D, float* g_x, void* stream) {
   if (N == 0) return M3G_OK;
   M3G_REQUIRE(g_sig_e && in_ptr && in_perm && sig && Ws && g_x, "m3g_tb_sigma_bwd: null pointer");
   M3G_REQUIRE(D >= 1 && D <= M3G_MAX_L * M3G_MAX_R, "m3g_tb_sigma_bwd: D=%d unsupported", D);
   if (D <= 16)
     tb_sigma_bwd_kernel<16><<<blocks_for(N * 32, 256), 256, 0, as_stream(stream)>>>(g_sig_e, in_ptr, in_perm, sig, Ws,
-                                                                                    N, F, D, g_x);
+                                                                                    base, N, F, D, g_x);
   else
     tb_sigma_bwd_kernel<M3G_MAX_L * M3G_MAX_R><<<blocks_for(N * 32, 256), 256, 0, as_stream(stream)>>>(
-        g_sig_e, in_ptr, in_perm, sig, Ws, N, F, D, g_x);
+        g_sig_e, in_ptr, in_perm, sig, Ws, base, N, F, D, g_x);
   M3G_LAUNCH_CHECK("m3g_tb_sigma_bwd");
   return M3G_OK;
 }

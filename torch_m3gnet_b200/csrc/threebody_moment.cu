@@ -321,8 +321,8 @@ __global__ void __launch_bounds__(32 * MW, 4) tb_mom_bwd_kernel(
     const float4* __restrict__ vec4, const float* __restrict__ G, const float* __restrict__ dG,
     const float* __restrict__ sig, const int32_t* __restrict__ dst, const float* __restrict__ red,
     const float* __restrict__ g_e, const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ tri_ptr, float r3,
-    const float* __restrict__ WdT, const float* __restrict__ WgT, int64_t N, int cap, float4* __restrict__ g_vec4,
-    float* __restrict__ g_sig_e) {
+    const float* __restrict__ WdT, const float* __restrict__ WgT, int64_t N, int cap, int accumulate,
+    float4* __restrict__ g_vec4, float* __restrict__ g_sig_e) {
   extern __shared__ __align__(16) float smem_f[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* ent = smem_f + (size_t)warp * (cap * ES + 2 * M_SIDE);
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(32 * MW, 4) tb_mom_bwd_kernel(
     // non-member bonds carry no three-body term
     for (int e = beg + lane; e < end; e += 32)
       if (!(__ldg(tri_ptr + e + 1) > __ldg(tri_ptr + e))) {
-        g_vec4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!accumulate) g_vec4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
         float* gs = g_sig_e + (int64_t)e * MD;
 #pragma unroll
         for (int d = 0; d < MD; ++d) gs[d] = 0.0f;
@@ -461,8 +461,12 @@ __global__ void __launch_bounds__(32 * MW, 4) tb_mom_bwd_kernel(
         grad_r = fmaf(gB[d] * __ldg(sg_ + d), __ldg(dg_ + d), grad_r);
       }
       const float ir = 1.0f / r;
-      g_vec4[e] = make_float4(Gv[0] * ir, Gv[1] * ir, Gv[2] * ir,
-                              (grad_r + gcq * cutoff_poly_grad(r, r3)) - X * ir);
+      float4 gout = make_float4(Gv[0] * ir, Gv[1] * ir, Gv[2] * ir, (grad_r + gcq * cutoff_poly_grad(r, r3)) - X * ir);
+      if (accumulate) {  // sum over the blocks of the model: this bond's row is owned by this lane
+        const float4 old = g_vec4[e];
+        gout.x += old.x; gout.y += old.y; gout.z += old.z; gout.w += old.w;
+      }
+      g_vec4[e] = gout;
     }
     __syncwarp();
   }
@@ -518,8 +522,8 @@ int m3g_tb_mom_fwd(const float* vec4, const float* G, const float* sig, const in
 
 int m3g_tb_mom_bwd(const float* vec4, const float* G, const float* dG, const float* sig, const int32_t* dst,
                    const float* red, const float* g_e, const int32_t* edge_ptr, const int32_t* tri_ptr, float r3,
-                   const float* WdT, const float* WgT, int64_t N, int max_members, int n_sm, float* g_vec4,
-                   float* g_sig_e, void* stream) {
+                   const float* WdT, const float* WgT, int64_t N, int max_members, int n_sm, int accumulate,
+                   float* g_vec4, float* g_sig_e, void* stream) {
   if (N == 0) return M3G_OK;
   M3G_REQUIRE(vec4 && G && dG && sig && dst && red && g_e && edge_ptr && tri_ptr && WdT && WgT && g_vec4 && g_sig_e,
               "m3g_tb_mom_bwd: null pointer");
@@ -531,7 +535,7 @@ int m3g_tb_mom_bwd(const float* vec4, const float* G, const float* dG, const flo
   int rc = mom_launch_shape(tb_mom_bwd_kernel, smem, N, n_sm, true, &grid);
   if (rc != M3G_OK) return rc;
   tb_mom_bwd_kernel<<<grid, 32 * MW, smem, as_stream(stream)>>>((const float4*)vec4, G, dG, sig, dst, red, g_e, edge_ptr,
-                                                               tri_ptr, r3, WdT, WgT, N, cap, (float4*)g_vec4, g_sig_e);
+                                                               tri_ptr, r3, WdT, WgT, N, cap, accumulate, (float4*)g_vec4, g_sig_e);
   M3G_LAUNCH_CHECK("m3g_tb_mom_bwd");
   return M3G_OK;
 }

@@ -290,3 +290,121 @@ def evaluate_emulated(model, dbatches: List[DomainBatch]) -> Dict[str, torch.Ten
         graphs[r]._private.clear()
     return {"total_energy": total.detach().reshape(1), "forces": forces}
 
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the same evaluation on the whole-step executor (engine.py): no autograd, the halo exchanges sit between the phases
+# ----------------------------------------------------------------------------------------------------------------
+class DomainStep:
+    """Energy + forces of one rank's sub-domain through ``m3g_step_run`` phases with the halo exchanges in between:
+
+        prologue, TB(0), CONV(0)  | x halo |  TB(1), CONV(1)  | x halo | ... READOUT
+        CONV_BWD(n-1), TB_BWD(n-1) | reverse x halo | CONV_BWD(n-2) ... TB_BWD(0), EPILOGUE | reverse pos halo | FORCES
+
+    Per step: (n_blocks - 1) forward halos of x (N_ghost x 64 floats), as many reverse halos of dE/dx, one reverse halo
+    of dE/dpos and one all_reduce of the energy; pack / unpack are ``m3g_rows_gather`` / ``m3g_rows_scatter_add``.
+    The buffers are allocated once, so the whole step (kernels + NCCL exchanges) can be captured in a CUDA graph
+    (``capture=True``) and replayed: one host launch per step instead of ~70, which is what a sub-domain of a few
+    thousand atoms needs.  New positions go in through ``set_positions``."""
+
+    def __init__(self, model, dbatch: DomainBatch, group=None, capture: bool = False, warmup: int = 2):
+        import torch.distributed as dist
+
+        from torch_m3gnet_b200 import engine as E
+        from torch_m3gnet_b200.data.material_graph import get_plan
+
+        self.dist, self.E, self.group = dist, E, group
+        self.model, self.dbatch = model, dbatch
+        self.engine = model.step_engine()
+        graph = dbatch.graph
+        plan = get_plan(graph)
+        if not self.engine.supports(graph, plan):
+            raise RuntimeError("DomainStep needs the default model shape (whole-step executor); use "
+                               "evaluate_distributed for other models")
+        dev = graph[K.POS].device
+        self.device = dev
+        self.n = self.engine.n_blocks
+        self.weight = torch.tensor([1.0, 0.0], device=dev)  # structure 0 = owned atoms, 1 = ghosts
+        self.desc, self.keep = self.engine.prepare(graph, plan, g_total=self.weight)
+        scratch, off = self.keep["scratch"], self.keep["off"]
+        N = plan.N
+
+        def view(name, rows, width):
+            return scratch[off[name]: off[name] + rows * width].view(rows, width)
+
+        self.x_next = [view(f"x{b + 1}", N, 64) for b in range(self.n - 1)]  # output of CONV(b), input of block b+1
+        self.g_x = [view("g_x0", N, 64), view("g_x1", N, 64)]
+        self.g_pos = view("g_pos", N, 3)
+        self.n_own = dbatch.n_own
+        self.send_idx = dbatch.send_idx.to(torch.int32).contiguous()
+        self.n_send = int(self.send_idx.numel())
+        self.send_counts, self.recv_counts = dbatch.send_counts, dbatch.recv_counts
+        self.send64 = torch.empty((max(self.n_send, 1), 64), device=dev)
+        self.send3 = torch.empty((max(self.n_send, 1), 3), device=dev)
+        self.pos = self.keep["inputs"][0]          # the (contiguous, detached) position buffer the kernels read
+        out = self.keep["out"]
+        self.energy = torch.zeros(1, device=dev)
+        self.forces_local = out[K.FORCES]
+        self.local_energy = out[K.TOTAL_ENERGY]
+        self.exchanges_per_step = 2 * (self.n - 1) + 2
+        self.graph = None
+        if capture:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(max(warmup, 1)):
+                    self._step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            # thread_local: the NCCL watchdog thread keeps polling its events while this thread captures
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._step()
+            self.graph = g
+
+    # ---- halo exchanges -------------------------------------------------------------------------------------
+    def _halo_forward(self, x):
+        from torch_m3gnet_b200._lib import call
+
+        call("rows_gather", x, self.send_idx, self.n_send, 64, self.send64)
+        self.dist.all_to_all_single(x[self.n_own:], self.send64[: self.n_send], self.recv_counts, self.send_counts,
+                                    group=self.group)
+
+    def _halo_reverse(self, g, send_buf, width):
+        from torch_m3gnet_b200._lib import call
+
+        self.dist.all_to_all_single(send_buf[: self.n_send], g[self.n_own:], self.send_counts, self.recv_counts,
+                                    group=self.group)
+        g[self.n_own:].zero_()
+        call("rows_scatter_add", send_buf, self.send_idx, self.n_send, width, g)
+
+    def _step(self):
+        E, n, d, dev = self.E, self.n, self.desc, self.device
+        run = self.engine.run_phases
+        run(d, 0, E.phase_conv(0), dev)
+        for b in range(1, n):
+            self._halo_forward(self.x_next[b - 1])
+            run(d, E.phase_tb(b), E.phase_conv(b), dev)
+        run(d, E.phase_readout(n), E.phase_readout(n), dev)
+        for b in range(n - 1, -1, -1):
+            if b < n - 1:
+                self._halo_reverse(self.g_x[d.cur_x], self.send64, 64)
+            run(d, E.phase_conv_bwd(n, b), E.phase_tb_bwd(n, b), dev)
+        run(d, E.phase_epilogue(n), E.phase_epilogue(n), dev)
+        self._halo_reverse(self.g_pos, self.send3, 3)
+        run(d, E.phase_forces(n), E.phase_forces(n), dev)
+        self.energy.copy_(self.local_energy[0:1])
+        self.dist.all_reduce(self.energy, group=self.group)
+
+    def set_positions(self, pos_local: torch.Tensor):
+        """New local coordinates (owned atoms first, then ghosts, as in ``DomainPlan.local_arrays``); the bond list of
+        the sub-domain is kept (rebuild the DomainBatch when atoms have moved further than its skin allows)."""
+        self.pos.copy_(pos_local)
+
+    def __call__(self) -> Dict[str, torch.Tensor]:
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step()
+        return {"total_energy": self.energy, "forces": self.forces_local[: self.n_own], "owned": self.dbatch.global_owned,
+                "local_energy": self.local_energy[0:1]}

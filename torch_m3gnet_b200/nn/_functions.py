@@ -207,9 +207,9 @@ class ThreeBodyFn(Function):
             g_vec4 = torch.empty_like(vec4)
             g_sig_e = torch.empty_like(red)
             call("tb_mom_bwd", vec4, G, dG, sig, plan.dst, red, g_e, plan.edge_ptr, plan.tri_ptr, w["r3"], w["WdT"],
-                 w["WgT"], N, plan.max_members, sm_count(vec4.device), g_vec4, g_sig_e)
+                 w["WgT"], N, plan.max_members, sm_count(vec4.device), 0, g_vec4, g_sig_e)
             g_x = _empty((N, F), vec4)
-            call("tb_sigma_bwd", g_sig_e, plan.in_ptr, plan.in_perm, sig, w["Ws"], N, F, D, g_x)
+            call("tb_sigma_bwd", g_sig_e, plan.in_ptr, plan.in_perm, sig, w["Ws"], None, N, F, D, g_x)
             return g_x, g_e, g_vec4, None, None, None, None, None
         vec4, sig, bas, red = ctx.saved_tensors
         g_red = torch.empty_like(red)
@@ -236,7 +236,7 @@ class ThreeBodyFn(Function):
         call("tb_edge_basis_bwd", vec4, plan.dst, sig, g_bas, w["consts"], E, L, R, plan.member_edges, plan.n_members,
              g_vec4, g_sig_e)
         g_x = _empty((N, F), vec4)
-        call("tb_sigma_bwd", g_sig_e, plan.in_ptr, plan.in_perm, sig, w["Ws"], N, F, D, g_x)
+        call("tb_sigma_bwd", g_sig_e, plan.in_ptr, plan.in_perm, sig, w["Ws"], None, N, F, D, g_x)
         return g_x, g_e, g_vec4, None, None, None, None, None
 
 

@@ -22,6 +22,15 @@ class Gradient(torch.nn.Module):
         super().__init__()
         self.model = model
         self.keep_graph = False
+        self._engine = None
+
+    def step_engine(self):
+        """The whole-step C executor bound to this model (torch_m3gnet_b200/engine.py), built on first use."""
+        if self._engine is None:
+            from torch_m3gnet_b200.engine import StepEngine
+
+            object.__setattr__(self, "_engine", StepEngine(self.model))
+        return self._engine
 
     def _forward_regrouped(self, graph):
         """Bonds not grouped by source atom (hand-built graphs; the reference accepts any bond order): evaluate a
@@ -38,9 +47,16 @@ class Gradient(torch.nn.Module):
     def forward(self, graph):
         pos = graph[K.POS]
         try:
-            get_plan(graph)
+            plan = get_plan(graph)
         except EdgesNotGrouped:
             return self._forward_regrouped(graph)
+        if not self.keep_graph:
+            engine = self.step_engine()
+            if engine.supports(graph, plan):
+                # default model shape: forward + hand-written adjoint chain launched from C in one call
+                graph = engine.run(graph, plan)
+                graph._private.clear()
+                return graph
         pos.requires_grad_(True)
         graph = self.model(graph)
         energy = graph[K.TOTAL_ENERGY]
