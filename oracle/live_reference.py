@@ -8,8 +8,9 @@ installs four tiny stand-in modules in ``sys.modules`` (SURVEY.md §8(c) "shim r
 
 It exists for two purposes only:
   * ``oracle/make_golden.py`` uses it to generate the fixtures under ``tests/golden/``;
-  * ``tests/test_oracle_pinned.py`` uses it (when /root/reference is present, i.e. in the build
-    container, never on the GPU box) to pin ``oracle/m3gnet_oracle.py`` against the real thing.
+  * ``tests/test_oracle_pinned.py`` uses it to pin ``oracle/m3gnet_oracle.py`` against the real thing;
+  * ``bench.py --impl reference`` / ``cpu_baseline`` time it on the GPU box's host cores, from the copy that
+    ``oracle/build_ref.py`` places under ``oracle/_ref/`` (git-ignored, shipped by gpurun).
 
 Nothing under ``torch_m3gnet_b200/`` may import this file.
 """
@@ -21,11 +22,26 @@ import types
 
 import torch
 
-REFERENCE_SRC = "/root/reference/src"
+# the reference where it lies in the build container, else the copy oracle/build_ref.py ships to the GPU box
+_CANDIDATES = ("/root/reference/src", os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref"))
+
+
+def _find_src():
+    for c in _CANDIDATES:
+        if os.path.isdir(os.path.join(c, "torch_m3gnet")):
+            return c
+    return None
+
+
+REFERENCE_SRC = _find_src() or _CANDIDATES[0]
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_SRC, "torch_m3gnet"))
+    return _find_src() is not None
+
+
+def location() -> str:
+    return _find_src() or "absent"
 
 
 def _scatter_sum(src, index, dim=-1, out=None, dim_size=None):
@@ -88,14 +104,16 @@ def install_shims() -> None:
     sys.modules.setdefault("torch_geometric", tg)
     sys.modules.setdefault("torch_geometric.data", tgd)
 
-    if REFERENCE_SRC not in sys.path:
-        sys.path.insert(0, REFERENCE_SRC)
+    src = _find_src()
+    if src is not None and src not in sys.path:
+        sys.path.insert(0, src)
 
 
 def import_reference():
     """Return (build_model, compute_threebody, interaction module, nn package) of the live reference."""
     if not available():
-        raise RuntimeError("/root/reference is not present (GPU box?) — live reference unavailable")
+        raise RuntimeError("neither /root/reference nor oracle/_ref is present — live reference unavailable "
+                           "(run `python -m oracle.build_ref` in the build container)")
     install_shims()
     from torch_m3gnet.data.material_graph import compute_threebody  # type: ignore
     from torch_m3gnet.model.build import build_model  # type: ignore

@@ -99,7 +99,13 @@ def main():
     os.makedirs(PROF, exist_ok=True)
     traffic = launches(tag, launch_csv)
     full(tag, reps)
+    sys.path.insert(0, ROOT)
+    import datetime
+
+    import bench  # source_hash(): ties the capture to the CUDA sources it was taken on
+
     json.dump({"source": f"{tag}_launches.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum, per launch)",
+               "source_hash": bench.source_hash(), "captured": datetime.date.today().isoformat(),
                "bytes_per_launch": {k: round(v) for k, v in traffic.items()}},
               open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
     print("wrote", sorted(os.listdir(PROF)))

@@ -283,25 +283,37 @@ class Batch(MaterialGraph):
         return torch.device(device)
 
     @classmethod
-    def from_arrays(cls, lattices: np.ndarray, cart: np.ndarray, atomic_numbers: np.ndarray, sizes: Sequence[int],
+    def from_arrays(cls, lattices: np.ndarray, cart, atomic_numbers, sizes: Sequence[int],
                     cutoff: float, threebody_cutoff: float, device: Optional[torch.device] = None,
                     want_triplet_index: bool = True) -> "Batch":
+        """Graph build on the GPU from plain arrays: ``lattices`` (B,3,3) rows = cell vectors, ``cart`` (N,3) Cartesian
+        coordinates (float64), ``atomic_numbers`` (N), ``sizes`` atoms per structure.  ``cart`` / ``atomic_numbers`` may be
+        numpy arrays or torch CPU tensors; pinned CPU tensors are uploaded asynchronously on the current stream."""
         if threebody_cutoff > cutoff:
             raise ValueError("Three body cutoff raidus should be smaller than two body.")
         device = cls._check_device(device)
         with torch.cuda.device(device):
             B = len(sizes)
             N = int(sum(sizes))
-            lat64 = torch.as_tensor(np.ascontiguousarray(lattices, dtype=np.float64).reshape(B, 3, 3)).to(device)
-            cart64 = torch.as_tensor(np.ascontiguousarray(cart, dtype=np.float64).reshape(N, 3)).to(device)
+            lattices = np.ascontiguousarray(np.asarray(lattices, dtype=np.float64)).reshape(B, 3, 3)
+            lat64 = torch.as_tensor(lattices).to(device)
+            if torch.is_tensor(cart):
+                cart64 = cart.reshape(N, 3).to(device=device, dtype=torch.float64, non_blocking=True)
+            else:
+                cart64 = torch.as_tensor(np.ascontiguousarray(cart, dtype=np.float64).reshape(N, 3)).to(device)
             atom_ptr_h = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
             atom_ptr = torch.as_tensor(atom_ptr_h).to(device)
             edge_ptr, E, edge_index, shift, dist, member = cls._sweep(lattices, lat64, cart64, atom_ptr, B, N, cutoff,
                                                                       threebody_cutoff, device)
             batch = torch.repeat_interleave(torch.arange(B, device=device), torch.as_tensor(list(sizes), device=device))
-            types_h = np.asarray(atomic_numbers, dtype=np.int64) - 1
-            types = torch.as_tensor(types_h).to(device)
-            type_range = (int(types_h.min()), int(types_h.max())) if N > 0 else (0, 0)
+            if torch.is_tensor(atomic_numbers):
+                z_h = atomic_numbers.reshape(-1)
+                types = (z_h.to(device=device, dtype=torch.int64, non_blocking=True) - 1)
+                type_range = (int(z_h.min()) - 1, int(z_h.max()) - 1) if N > 0 else (0, 0)
+            else:
+                types_h = np.asarray(atomic_numbers, dtype=np.int64) - 1
+                types = torch.as_tensor(types_h).to(device)
+                type_range = (int(types_h.min()), int(types_h.max())) if N > 0 else (0, 0)
             return cls._assemble(lat64, cart64, types, atom_ptr, batch, N, edge_ptr, E, edge_index, shift, dist,
                                  member, want_triplet_index, type_range=type_range)
 
