@@ -289,6 +289,11 @@ int m3g_conv_mlp_fwd(const float* P, int ldp, int po, const int32_t* src, const 
 /* out (N,F) = base (N,F) + sum_{e in [edge_ptr[i], edge_ptr[i+1])} msg[e] */
 int m3g_segment_sum_add(const float* base, const float* msg, const int32_t* edge_ptr, int64_t N, int F,
                         float* out, void* stream);
+/* the same sum from the partial rows of m3g_conv_tc_fwd(mode = 2): the tensor-core forward reduces the messages of every
+ * 32-row block per source atom in its epilogue and writes one partial row per (block, atom) at the block's first row of
+ * that atom (the other rows of `part` are never written nor read); out[i] = base[i] + sum_k part[max(b_i, 32 k)] */
+int m3g_segment_sum_parts(const float* base, const float* part, const int32_t* edge_ptr, int64_t N, int F,
+                          float* out, void* stream);
 /* adjoint of one gated MLP on edges (activations recomputed).  Upstream gradient of `out`:
  *   mode 0: g_u[e] rows of g_up (E,F);   mode 1: g_u[e] = g_up[src[e]] rows of g_up (N,F).
  * Outputs: g_e (E,F) = g_e_base (may be NULL = 0) + d out/d e adjoint; g_z1 (E,2F); g_h (E,R) accumulated (+=)
@@ -328,6 +333,9 @@ int m3g_debug_mma_rate2(int N, int n_mma, int64_t* cycles2, void* stream);
  * a_tmem = 1 feeds A from tensor memory (tcgen05.st + the [a_tmem] operand form) instead of shared memory */
 int m3g_tc_selftest(const float* A, const float* img_hi, const float* img_lo, int rows, int cols, int passes,
                     int a_tmem, float* out, void* stream);
+/* mode 0 / 1 as m3g_conv_mlp_fwd; mode 2 = mode 1 with the messages summed per source atom inside the epilogue: y then
+ * holds one partial row per (32-row block, source atom) at the block's first row of that atom, for
+ * m3g_segment_sum_parts (the other rows of y are not written) */
 int m3g_conv_tc_fwd(const float* P, int ldp, int po, const int32_t* src, const int32_t* dst, const float* e,
                     const float* h, const float* wimg, const float* b2d, const float* b2g, const float* WhT, int64_t E,
                     int R, int mode, int passes, int n_sm, float* y, float* save, void* stream);
@@ -426,7 +434,7 @@ typedef struct M3GStepBlock {
 typedef struct M3GStepDesc {
   int64_t N, E, T, B;
   int n_blocks, n_sm, passes, max_members;
-  int64_t n_members;
+  int64_t n_members; /* member bonds (bonds inside the three-body cutoff) */
   float length_scale, energy_scale, r3;
   int num_types;
   /* plan (int32 CSR views, see "Conventions") */
@@ -450,6 +458,7 @@ typedef struct M3GStepDesc {
   float *g_h, *g_h2, *g_sig_e, *g_vec4, *g_dist, *g_pos; /* (E,3) x 2, (E,9), (E,4), (E), (N,3) */
   int cur_x, cur_e;               /* state carried between phases (updated by m3g_step_run) */
   int have_g_e;                   /* 0 until the first conv adjoint has produced g_e */
+  int msg_reduce;                 /* 1: node MLP sums its messages per atom in-kernel (m3g_conv_tc_fwd mode 2) */
   M3GStepBlock blocks[M3G_STEP_MAX_BLOCKS];
 } M3GStepDesc;
 

@@ -246,6 +246,26 @@ __global__ void segment_sum_add_kernel(const float* __restrict__ base, const flo
   }
 }
 
+// out[i] = base[i] + sum of the per-(32-row block, atom) partial message rows that m3g_conv_tc_fwd(mode 2) left at the
+// block's first row of the atom: rows max(b, 32 k) for k = b / 32 .. (en - 1) / 32, ascending.  One warp per atom, F = 64.
+__global__ void segment_sum_parts_kernel(const float* __restrict__ base, const float* __restrict__ part,
+                                         const int32_t* __restrict__ edge_ptr, int64_t N, float* __restrict__ out) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (i >= N) return;
+  const int b = edge_ptr[i], en = edge_ptr[i + 1];
+  float2 acc = make_float2(0.f, 0.f);
+  if (en > b) {
+    for (int k = b >> 5; k <= (en - 1) >> 5; ++k) {
+      const int row = max(b, k << 5);
+      const float2 v = __ldg(reinterpret_cast<const float2*>(part + (int64_t)row * 64) + lane);
+      acc.x += v.x; acc.y += v.y;
+    }
+  }
+  const float2 x = __ldg(reinterpret_cast<const float2*>(base + i * 64) + lane);
+  reinterpret_cast<float2*>(out + i * 64)[lane] = make_float2(x.x + acc.x, x.y + acc.y);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // adjoint of one gated MLP on edges (forward recomputed)
 template <int NJ>
@@ -528,6 +548,16 @@ int m3g_segment_sum_add(const float* base, const float* msg, const int32_t* edge
   M3G_REQUIRE(base && msg && edge_ptr && out, "m3g_segment_sum_add: null pointer");
   segment_sum_add_kernel<<<blocks_for(N * 32, 256), 256, 0, as_stream(stream)>>>(base, msg, edge_ptr, N, F, out);
   M3G_LAUNCH_CHECK("m3g_segment_sum_add");
+  return M3G_OK;
+}
+
+int m3g_segment_sum_parts(const float* base, const float* part, const int32_t* edge_ptr, int64_t N, int F,
+                          float* out, void* stream) {
+  if (N == 0) return M3G_OK;
+  M3G_REQUIRE(base && part && edge_ptr && out, "m3g_segment_sum_parts: null pointer");
+  M3G_REQUIRE(F == 64, "m3g_segment_sum_parts: F=%d (the tensor-core forward that writes the partial rows is F = 64)", F);
+  segment_sum_parts_kernel<<<blocks_for(N * 32, 256), 256, 0, as_stream(stream)>>>(base, part, edge_ptr, N, out);
+  M3G_LAUNCH_CHECK("m3g_segment_sum_parts");
   return M3G_OK;
 }
 

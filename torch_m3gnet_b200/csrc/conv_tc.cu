@@ -352,7 +352,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc4_fwd_kernel(ConvTcPara
     }
     const int64_t eg = min(e0 + row, p.E - 1);
     const int d_row = __ldg(p.dst + eg);
-    const float* Pi = p.P + (int64_t)__ldg(p.src + eg) * p.ldp + p.po;
+    const int s_atom = __ldg(p.src + eg);
+    const float* Pi = p.P + (int64_t)s_atom * p.ldp + p.po;
+    // mode 2: source atom of every row of this warp's 32-row block (-1 past the end), for the segmented message sum
+    const int s_row = (e0 + row < p.E) ? s_atom : -1;
     {
       // pull this group's next tile (e rows, indices, h) into L2 while this tile computes
       const int64_t en = (tile + 2 * (int64_t)gridDim.x) * TILE_M;
@@ -508,12 +511,44 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc4_fwd_kernel(ConvTcPara
         sts128(stg + stg_off(lane, c >> 2), make_float4(o[0], o[1], o[2], o[3]));
       }
       __syncwarp();
+      if (p.mode != 2) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float4 r4 = lds128(stg + stg_off(8 * i + cr, cc4));
-        if (p.mode == 0) { r4.x += er[i].x; r4.y += er[i].y; r4.z += er[i].z; r4.w += er[i].w; }
-        int64_t er_ = e0 + 32 * q + 8 * i + cr;
-        if (er_ < p.E) *reinterpret_cast<float4*>(p.y + er_ * TC_F + col + 4 * cc4) = r4;
+        for (int i = 0; i < 4; ++i) {
+          float4 r4 = lds128(stg + stg_off(8 * i + cr, cc4));
+          if (p.mode == 0) { r4.x += er[i].x; r4.y += er[i].y; r4.z += er[i].z; r4.w += er[i].w; }
+          int64_t er_ = e0 + 32 * q + 8 * i + cr;
+          if (er_ < p.E) *reinterpret_cast<float4*>(p.y + er_ * TC_F + col + 4 * cc4) = r4;
+        }
+      } else {
+        // messages are only ever summed per source atom (nn/conv.py:82-87) and the rows of an atom are contiguous:
+        // reduce this warp's 32 rows per source atom here and write ONE partial row per (32-row block, atom) at the
+        // block's first row of that atom; m3g_segment_sum_parts adds the (ascending) partials of an atom to x.
+        // Order (stated): rows 8 i + cr for i = 0..3 in this lane, then a fixed xor tree over cr.
+        float4 r4[4];
+        int sa[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          r4[i] = lds128(stg + stg_off(8 * i + cr, cc4));
+          sa[i] = __shfl_sync(FULL, s_row, 8 * i + cr);
+        }
+        int start = 0;
+        while (start < 32) {
+          const int a = __shfl_sync(FULL, s_row, start);
+          if (a < 0) break;
+          const int n_rows = __popc(__ballot_sync(FULL, s_row == a));
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (sa[i] == a) { acc.x += r4[i].x; acc.y += r4[i].y; acc.z += r4[i].z; acc.w += r4[i].w; }
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {
+            acc.x += __shfl_xor_sync(FULL, acc.x, o); acc.y += __shfl_xor_sync(FULL, acc.y, o);
+            acc.z += __shfl_xor_sync(FULL, acc.z, o); acc.w += __shfl_xor_sync(FULL, acc.w, o);
+          }
+          if (cr == 0)
+            *reinterpret_cast<float4*>(p.y + (e0 + 32 * q + start) * TC_F + col + 4 * cc4) = acc;
+          start += n_rows;
+        }
       }
       __syncwarp();
     }

@@ -187,6 +187,16 @@ __global__ void edge_adjust_fwd_kernel(const float* __restrict__ h, const float*
   e0[idx] = silu_acc(z);
 }
 
+// exp2 / reciprocal on the special-function unit, as in the gated-MLP epilogues (csrc/conv_tc.cu): relative error of a
+// few 1e-7, an order of magnitude below the tolerances on edge_attr (the accurate expf + IEEE division cost ~3x the
+// instructions and made these two kernels issue-bound at 40 % of the HBM rate)
+__device__ __forceinline__ float sigmoid_q(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
+__device__ __forceinline__ float silu_q(float z) { return z * sigmoid_q(z); }
+__device__ __forceinline__ float silu_grad_q(float z) {
+  const float s = sigmoid_q(z);
+  return s * (1.0f + z * (1.0f - s));
+}
+
 // F % 4 == 0: one thread per 4 consecutive features (float4 stores, the h row is a broadcast inside the row's threads)
 template <int RC>
 __global__ void edge_adjust_fwd4_kernel(const float* __restrict__ h, const float* __restrict__ Wt, int64_t E, int R,
@@ -205,7 +215,7 @@ __global__ void edge_adjust_fwd4_kernel(const float* __restrict__ h, const float
       z.x += hv * w.x; z.y += hv * w.y; z.z += hv * w.z; z.w += hv * w.w;
     }
   }
-  reinterpret_cast<float4*>(e0 + e * F)[f >> 2] = make_float4(silu_acc(z.x), silu_acc(z.y), silu_acc(z.z), silu_acc(z.w));
+  reinterpret_cast<float4*>(e0 + e * F)[f >> 2] = make_float4(silu_q(z.x), silu_q(z.y), silu_q(z.z), silu_q(z.w));
 }
 
 // one warp per edge
@@ -255,7 +265,8 @@ __global__ void edge_adjust_bwd64_kernel(const float* __restrict__ h, const floa
   float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int m = 0; m < RC; ++m) { z.x += hv[m] * w[m].x; z.y += hv[m] * w[m].y; z.z += hv[m] * w[m].z; z.w += hv[m] * w[m].w; }
-  const float gx = g.x * silu_grad(z.x), gy = g.y * silu_grad(z.y), gz = g.z * silu_grad(z.z), gw = g.w * silu_grad(z.w);
+  const float gx = g.x * silu_grad_q(z.x), gy = g.y * silu_grad_q(z.y), gz = g.z * silu_grad_q(z.z),
+              gw = g.w * silu_grad_q(z.w);
 #pragma unroll
   for (int m = 0; m < RC; ++m) {
     float a = ((gx * w[m].x + gy * w[m].y) + gz * w[m].z) + gw * w[m].w;
@@ -393,7 +404,9 @@ int m3g_embed_fwd(const float* weight, const int32_t* types, int64_t N, int F, i
 int m3g_edge_adjust_fwd(const float* h, const float* Wt, int64_t E, int R, int F, float* e0, void* stream) {
   if (E == 0) return M3G_OK;
   M3G_REQUIRE(h && Wt && e0, "m3g_edge_adjust_fwd: null pointer");
-  if (F % 4 == 0 && R <= 4)
+  if (F % 4 == 0 && R == 3)
+    edge_adjust_fwd4_kernel<3><<<blocks_for(E * (F / 4), 256), 256, 0, as_stream(stream)>>>(h, Wt, E, R, F, e0);
+  else if (F % 4 == 0 && R <= 4)
     edge_adjust_fwd4_kernel<4><<<blocks_for(E * (F / 4), 256), 256, 0, as_stream(stream)>>>(h, Wt, E, R, F, e0);
   else
     edge_adjust_fwd_kernel<<<blocks_for(E * F, 256), 256, 0, as_stream(stream)>>>(h, Wt, E, R, F, e0);
@@ -406,7 +419,9 @@ int m3g_edge_adjust_bwd(const float* h, const float* Wt, const float* g_e0, int6
   if (E == 0) return M3G_OK;
   M3G_REQUIRE(h && Wt && g_e0 && g_h, "m3g_edge_adjust_bwd: null pointer");
   M3G_REQUIRE(R >= 1 && R <= M3G_MAX_RADIAL, "m3g_edge_adjust_bwd: n_max=%d outside [1,%d]", R, M3G_MAX_RADIAL);
-  if (F == 64 && R <= 4)
+  if (F == 64 && R == 3)
+    edge_adjust_bwd64_kernel<3><<<blocks_for(E * 16, 256), 256, 0, as_stream(stream)>>>(h, Wt, g_e0, E, R, g_h);
+  else if (F == 64 && R <= 4)
     edge_adjust_bwd64_kernel<4><<<blocks_for(E * 16, 256), 256, 0, as_stream(stream)>>>(h, Wt, g_e0, E, R, g_h);
   else
     edge_adjust_bwd_kernel<<<blocks_for(E * 32, 256), 256, 0, as_stream(stream)>>>(h, Wt, g_e0, E, R, F, g_h);

@@ -50,9 +50,11 @@ int conv_fwd(M3GStepDesc* d, int b, void* s) {
   M3G_TRY(m3g_linear_fwd(k.x_in, k.WpT, k.bp, d->N, F, 8 * F, d->P, s));
   M3G_TRY(m3g_conv_tc_fwd(d->P, 8 * F, 0, d->src, d->dst, k.e_tb, d->h, k.e_wimg, k.e_b2d, k.e_b2g, k.e_WhT, d->E, R, 0,
                           d->passes, d->n_sm, k.e_out, k.save_e, s));
+  // mode 2: messages reduced per source atom in the kernel's epilogue (one partial row per 32-row block and atom)
   M3G_TRY(m3g_conv_tc_fwd(d->P, 8 * F, 4 * F, d->src, d->dst, k.e_out, d->h, k.n_wimg, k.n_b2d, k.n_b2g, k.n_WhT, d->E,
-                          R, 1, d->passes, d->n_sm, d->msg, k.save_n, s));
-  M3G_TRY(m3g_segment_sum_add(k.x_in, d->msg, d->edge_ptr, d->N, F, k.x_out, s));
+                          R, d->msg_reduce ? 2 : 1, d->passes, d->n_sm, d->msg, k.save_n, s));
+  if (d->msg_reduce) M3G_TRY(m3g_segment_sum_parts(k.x_in, d->msg, d->edge_ptr, d->N, F, k.x_out, s));
+  else M3G_TRY(m3g_segment_sum_add(k.x_in, d->msg, d->edge_ptr, d->N, F, k.x_out, s));
   return M3G_OK;
 }
 

@@ -226,7 +226,7 @@ __device__ __forceinline__ int stage(float* ent, int cap, int beg, int end, cons
 
 // ------------------------------------------------------------------------------------------------
 // forward: red (member bonds) and e_out = e_in + SiLU(red WdT) * sigmoid(red WgT) (all bonds)
-__global__ void __launch_bounds__(32 * MW, 3) tb_mom_fwd_kernel(
+__global__ void __launch_bounds__(32 * MW, 4) tb_mom_fwd_kernel(
     const float4* __restrict__ vec4, const float* __restrict__ G, const float* __restrict__ sig,
     const int32_t* __restrict__ dst, const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ tri_ptr,
     float r3, const float* __restrict__ WdT, const float* __restrict__ WgT, const float* __restrict__ e_in, int64_t N,

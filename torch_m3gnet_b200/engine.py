@@ -52,7 +52,7 @@ class _Desc(ctypes.Structure):
                 + [("g_x", _fp * 2), ("g_e", _fp * 2)]
                 + [(n, _fp) for n in ("ge2", "gz_edge", "gz_node", "gP", "g_h", "g_h2", "g_sig_e", "g_vec4", "g_dist",
                                       "g_pos")]
-                + [(n, ctypes.c_int) for n in ("cur_x", "cur_e", "have_g_e")]
+                + [(n, ctypes.c_int) for n in ("cur_x", "cur_e", "have_g_e", "msg_reduce")]
                 + [("blocks", _Block * MAX_BLOCKS)])
 
 
@@ -204,6 +204,7 @@ class StepEngine:
         d.N, d.E, d.T, d.B = N, E, T, B
         d.n_blocks, d.n_sm, d.max_members = n, sm_count(dev), int(plan.max_members)
         d.passes = 3 if conv_mod.CONV_PATH == "tc3" else 1
+        d.msg_reduce = int(conv_mod.MSG_REDUCE)
         d.n_members = int(plan.n_members)
         d.length_scale, d.energy_scale = float(self.scale.length_scale), float(self.readout.scale)
         d.r3 = float(weights[0][0]["r3"])

@@ -36,6 +36,12 @@ def tc_bwd_variant() -> int:
     return conv.TC_BWD_VARIANT
 
 
+def msg_reduce() -> bool:
+    from torch_m3gnet_b200.nn import conv
+
+    return conv.MSG_REDUCE
+
+
 def conv_path() -> str:
     from torch_m3gnet_b200.nn import conv
 
@@ -256,6 +262,7 @@ class ConvFn(Function):
         ed, nd = w["edge"], w["node"]
         path = conv_path()
         save_e = save_n = None
+        parts = False
         if F == 64 and "wimg" in ed and path in ("tc3", "tc1") and R <= 4:
             passes = 3 if path == "tc3" else 1
             n_sm = sm_count(x.device)
@@ -265,15 +272,18 @@ class ConvFn(Function):
                 save_e, save_n = _empty((n_save,), x), _empty((n_save,), x)
             call("conv_tc_fwd", P, 8 * F, 0, plan.src, plan.dst, e, h, ed["wimg"], ed["b2d"], ed["b2g"], ed["WhT"], E, R,
                  0, passes, n_sm, e2, save_e)
+            # mode 2: the messages are reduced per source atom inside the kernel's epilogue; msg holds one partial
+            # row per (32-row block, atom)
             call("conv_tc_fwd", P, 8 * F, 4 * F, plan.src, plan.dst, e2, h, nd["wimg"], nd["b2d"], nd["b2g"], nd["WhT"],
-                 E, R, 1, passes, n_sm, msg, save_n)
+                 E, R, 2 if msg_reduce() else 1, passes, n_sm, msg, save_n)
+            parts = msg_reduce()
         else:
             call("conv_mlp_fwd", P, 8 * F, 0, plan.src, plan.dst, e, h, ed["W1eT"], ed["W2dT"], ed["b2d"], ed["W2gT"],
                  ed["b2g"], ed["WhT"], E, F, R, 0, e2)
             call("conv_mlp_fwd", P, 8 * F, 4 * F, plan.src, plan.dst, e2, h, nd["W1eT"], nd["W2dT"], nd["b2d"],
                  nd["W2gT"], nd["b2g"], nd["WhT"], E, F, R, 1, msg)
         x2 = torch.empty_like(x)
-        call("segment_sum_add", x, msg, plan.edge_ptr, N, F, x2)
+        call("segment_sum_parts" if parts else "segment_sum_add", x, msg, plan.edge_ptr, N, F, x2)
         ctx.plan, ctx.w = plan, w
         ctx.saved_acts = (save_e, save_n)
         ctx.save_for_backward(x, e, e2, h, P)

@@ -17,6 +17,11 @@ CONV_PATH = os.environ.get("M3G_CONV_PATH", "tc3")
 # backward of the tensor-core gated MLPs: 4 = from the activations the forward leaves behind (SiLU'(z1) and the layer-2
 # pre-activations, 1 KB per edge and MLP; default); 2 = forward recomputed inside the backward kernel (no extra memory)
 TC_BWD_VARIANT = int(os.environ.get("M3G_TC_BWD_VARIANT", "4"))
+# True (default): the tensor-core node MLP sums its messages per source atom inside its epilogue (one partial row per
+# 32-row block and atom, csrc/conv_tc.cu mode 2): 256 B / bond less HBM traffic and no E x 64 message pass.  The grouping
+# of the sum then follows the 32-row blocks of the batch's bond list, so the same structure in another batch position
+# agrees to fp32 rounding instead of bit for bit.  False: messages written row by row and summed in ascending bond order.
+MSG_REDUCE = os.environ.get("M3G_CONV_MSG_REDUCE", "1") != "0"
 
 
 def _tc_images(w1e: torch.Tensor, w2d: torch.Tensor, w2g: torch.Tensor) -> torch.Tensor:
