@@ -243,3 +243,76 @@ def test_c5_sub_box_three_body_vs_oracle(device):
     report("c5sub.out", out, out_o, 2e-6, 2e-6)
     report("c5sub.g_x", gx, gx_o, 1e-5, 3e-5)
     report("c5sub.g_pos", gp, gp_o, 5e-5, 5e-5)
+
+
+def _c3_structures():
+    """The 1 024 MPF-like structures of BASELINE configs[2] (host worker pool; `spawn`: this process holds a CUDA
+    context)."""
+    import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
+
+    from torch_m3gnet_b200 import synthetic
+
+    with ProcessPoolExecutor(max_workers=8, mp_context=mp.get_context("spawn")) as ex:
+        return list(ex.map(synthetic.mpf_like_structure, range(1024), chunksize=16))
+
+
+def test_c3_full_ragged_batch_1024_structures(device, model_x3):
+    """configs[2] at full size: 1 024 ragged multi-element structures (~1.1e5 atoms, ~3.8e6 bonds, ~3.2e7 triplets) in
+    one call: index identities, Newton's third law per structure, additivity (members evaluated alone), structure-order
+    invariance, and oracle spot checks on the largest structure, the smallest, the one with the most species and the
+    densest one."""
+    from torch_m3gnet_b200 import Batch
+
+    model, sd = model_x3
+    structs = _c3_structures()
+    sizes = [len(s[1]) for s in structs]
+    lat = np.stack([s[0] for s in structs])
+    cart = np.concatenate([s[1] for s in structs])
+    z = np.concatenate([s[2] for s in structs])
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    b = Batch.from_arrays(lat, cart, z, sizes, 5.0, 4.0, device=device)
+    N, E, T = b["pos"].shape[0], b["edge_index"].shape[1], b["triplet_edge_index"].shape[1]
+    assert len(structs) == 1024 and 1.0e5 < N < 1.3e5 and E > 3e6 and T > 2e7
+    assert int(b["num_triplet_i"].sum()) == T == int(b["num_triplet_ij"].sum())
+    # every bond has its reverse (same structure, opposite image)
+    ei, sh = b["edge_index"], b["edge_cell_shift"].long()
+    key = lambda s, d, c: ((s * N + d) * 9 + (c[:, 0] + 4)) * 81 + (c[:, 1] + 4) * 9 + (c[:, 2] + 4)  # noqa: E731
+    assert int(sh.abs().max()) <= 4
+    assert torch.equal(torch.sort(key(ei[0], ei[1], sh)).values, torch.sort(key(ei[1], ei[0], -sh)).values)
+    out = model(b)
+    en, f = out["total_energy"].clone(), out["forces"].clone()
+    assert torch.isfinite(en).all() and torch.isfinite(f).all()
+    fmax = f.abs().max().item()
+    batch_idx = b["batch"]
+    fsum = torch.zeros((1024, 3), device=device).index_add_(0, batch_idx, f).abs().max().item()
+    print(f"[full C3] N={N} E={E} T={T} max|F|={fmax:.3e} max|sum F per structure|={fsum:.2e}")
+    assert fsum < 1e-4 * max(fmax, 1.0)
+    n_species = [len(set(s[2].tolist())) for s in structs]
+    density = [len(s[1]) / abs(np.linalg.det(s[0])) for s in structs]
+    picks = sorted({int(np.argmax(sizes)), int(np.argmin(sizes)), int(np.argmax(n_species)), int(np.argmax(density)),
+                    511})
+    for s in picks:
+        a0, a1 = off[s], off[s + 1]
+        o1 = model(Batch.from_arrays(lat[s:s + 1], cart[a0:a1], z[a0:a1], [sizes[s]], 5.0, 4.0, device=device))
+        dE = (o1["total_energy"][0] - en[s]).abs().item() / sizes[s]
+        dF = (o1["forces"] - f[a0:a1]).abs().max().item()
+        g = O.build_graph(lat[s], cart[a0:a1], z[a0:a1], 5.0, 4.0)
+        ref = O.forward(sd, O.HyperParams(), O.collate([g]), create_graph=False)
+        dEo = abs(float(en[s].cpu()) - float(ref["total_energy"][0].detach())) / sizes[s]
+        dFo = (f[a0:a1].cpu() - ref["forces"]).abs().max().item()
+        fo = ref["forces"].abs().max().item()
+        print(f"[full C3] structure {s} ({sizes[s]} atoms, {n_species[s]} species): alone vs batch |dE|/atom={dE:.1e} "
+              f"|dF|={dF:.1e}; oracle |dE|/atom={dEo:.2e} max|dF|={dFo:.2e} max|F|={fo:.2e}")
+        assert dE <= 1e-6 and dF <= 2e-6 * max(fmax, 1.0)
+        assert dEo <= 1e-5 and dFo <= 1e-4 + 1e-3 * fo
+    # structure order: reversed batch = reversed results (to fp32 rounding: see test_c2_full_batch_properties)
+    order = np.arange(1023, -1, -1)
+    cart_r = np.concatenate([structs[s][1] for s in order])
+    z_r = np.concatenate([structs[s][2] for s in order])
+    o2 = model(Batch.from_arrays(lat[order], cart_r, z_r, [sizes[s] for s in order], 5.0, 4.0, device=device))
+    assert (o2["total_energy"].flip(0) - en).abs().max().item() <= 2e-6 * en.abs().max().item()
+    f_back = torch.cat([o2["forces"][int(a):int(bb)] for a, bb in
+                        zip(np.concatenate([[0], np.cumsum([sizes[s] for s in order])])[:-1][::-1],
+                            np.cumsum([sizes[s] for s in order])[::-1])])
+    assert (f_back - f).abs().max().item() <= 2e-6 * max(fmax, 1.0)
