@@ -236,6 +236,11 @@ int m3g_tb_atom_bwd(const float* vec4, const float* bas, const float* red, const
 int m3g_tb_radial(const float* vec4, const float* tb_consts, int64_t E, int L, int R, const int32_t* edge_list,
                   int64_t n_list, float* G, float* dG, void* stream);
 int m3g_tb_mom_capacity(void);
+/* m3g_tb_sigma_fwd / _bwd specialised for F = 64, D = 9 (weights in registers, one shared butterfly for the nine sums,
+ * warps striding over atoms; n_sm sizes the persistent grid) */
+int m3g_tb_sigma64_fwd(const float* x, const float* Ws, const float* bs, int64_t N, int n_sm, float* sig, void* stream);
+int m3g_tb_sigma64_bwd(const float* g_sig_e, const int32_t* in_ptr, const int32_t* in_perm, const float* sig,
+                       const float* Ws, const float* base, int64_t N, int n_sm, float* g_x, void* stream);
 int m3g_tb_mom_fwd(const float* vec4, const float* G, const float* sig, const int32_t* dst, const int32_t* edge_ptr,
                    const int32_t* tri_ptr, float r3, const float* WdT, const float* WgT, const float* e_in, int64_t N,
                    int max_members, int n_sm, float* red, float* e_out, void* stream);

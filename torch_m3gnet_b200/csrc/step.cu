@@ -39,7 +39,7 @@ int prologue(M3GStepDesc* d, void* s) {
 
 int tb_fwd(M3GStepDesc* d, int b, void* s) {
   M3GStepBlock& k = d->blocks[b];
-  M3G_TRY(m3g_tb_sigma_fwd(k.x_in, k.Ws, k.bs, d->N, F, D, k.sig, s));
+  M3G_TRY(m3g_tb_sigma64_fwd(k.x_in, k.Ws, k.bs, d->N, d->n_sm, k.sig, s));
   M3G_TRY(m3g_tb_mom_fwd(d->vec4, k.G, k.sig, d->dst, d->edge_ptr, d->tri_ptr, d->r3, k.WdT, k.WgT, k.e_in, d->N,
                          d->max_members, d->n_sm, k.red, k.e_tb, s));
   return M3G_OK;
@@ -107,8 +107,8 @@ int tb_bwd(M3GStepDesc* d, int b, void* s) {
   M3G_TRY(m3g_tb_mom_bwd(d->vec4, k.G, k.dG, k.sig, d->dst, k.red, d->g_e[d->cur_e], d->edge_ptr, d->tri_ptr, d->r3,
                          k.WdT, k.WgT, d->N, d->max_members, d->n_sm, b != d->n_blocks - 1, d->g_vec4, d->g_sig_e, s));
   if (need_x) {
-    M3G_TRY(m3g_tb_sigma_bwd(d->g_sig_e, d->in_ptr, d->in_perm, k.sig, k.Ws, d->g_x[d->cur_x], d->N, F, D,
-                             d->g_x[d->cur_x ^ 1], s));
+    M3G_TRY(m3g_tb_sigma64_bwd(d->g_sig_e, d->in_ptr, d->in_perm, k.sig, k.Ws, d->g_x[d->cur_x], d->N, d->n_sm,
+                               d->g_x[d->cur_x ^ 1], s));
     d->cur_x ^= 1;
   }
   return M3G_OK;

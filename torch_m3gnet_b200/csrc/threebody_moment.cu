@@ -472,6 +472,93 @@ __global__ void __launch_bounds__(32 * MW, 4) tb_mom_bwd_kernel(
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// sigma = sigmoid(x Ws^T + bs) for F = 64, D = 9 (nn/interaction.py:204-206) and its adjoint.  The generic kernels
+// (threebody.cu) walk the 9 outputs one by one with a full warp reduction each and re-read Ws from global memory; here a
+// lane keeps its two columns of all nine weight rows in registers, the nine sums share one value-halving butterfly, and
+// a warp strides over atoms.
+__device__ __forceinline__ float reduce9_lanes(const float* v, int lane) {
+  const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+  float a[5];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float keep = h4 ? v[5 + i] : v[i], send = h4 ? v[i] : v[5 + i];
+    a[i] = keep + __shfl_xor_sync(FULL, send, 16);
+  }
+  a[4] = (h4 ? 0.0f : v[4]) + __shfl_xor_sync(FULL, h4 ? v[4] : 0.0f, 16);
+  float c[3];
+  c[0] = (h3 ? a[3] : a[0]) + __shfl_xor_sync(FULL, h3 ? a[0] : a[3], 8);
+  c[1] = (h3 ? a[4] : a[1]) + __shfl_xor_sync(FULL, h3 ? a[1] : a[4], 8);
+  c[2] = (h3 ? 0.0f : a[2]) + __shfl_xor_sync(FULL, h3 ? a[2] : 0.0f, 8);
+  float d[2];
+  d[0] = (h2 ? c[2] : c[0]) + __shfl_xor_sync(FULL, h2 ? c[0] : c[2], 4);
+  d[1] = (h2 ? 0.0f : c[1]) + __shfl_xor_sync(FULL, h2 ? c[1] : 0.0f, 4);
+  const float e = (h1 ? d[1] : d[0]) + __shfl_xor_sync(FULL, h1 ? d[0] : d[1], 2);
+  return e + __shfl_xor_sync(FULL, e, 1);  // lane l: total of component 5 b4 + 3 b3 + 2 b2 + b1 (bits of l)
+}
+
+__global__ void __launch_bounds__(256) tb_sigma64_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Ws,
+                                                             const float* __restrict__ bs, int64_t N,
+                                                             float* __restrict__ sig) {
+  const int lane = threadIdx.x & 31;
+  float2 w[MD];
+#pragma unroll
+  for (int d = 0; d < MD; ++d) w[d] = __ldg(reinterpret_cast<const float2*>(Ws + d * MF) + lane);
+  const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1;
+  const int dsel = 5 * b4 + 3 * b3 + 2 * b2 + b1;
+  const bool writer = !(lane & 1) && !(b3 & b2) && !(b2 & b1) && dsel < MD;
+  const float bias = writer ? __ldg(bs + dsel) : 0.0f;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < N; k += warps) {
+    const float2 xv = __ldg(reinterpret_cast<const float2*>(x + k * MF) + lane);
+    float part[MD];
+#pragma unroll
+    for (int d = 0; d < MD; ++d) part[d] = fmaf(xv.y, w[d].y, xv.x * w[d].x);
+    const float tot = reduce9_lanes(part, lane);
+    if (writer) sig[k * MD + dsel] = sigmoid_acc(tot + bias);
+  }
+}
+
+// g_x (N,64) = base + (sum_{e in in(k)} g_sig_e[e]) * sig (1 - sig) . Ws
+__global__ void __launch_bounds__(256) tb_sigma64_bwd_kernel(const float* __restrict__ g_sig_e,
+                                                             const int32_t* __restrict__ in_ptr,
+                                                             const int32_t* __restrict__ in_perm,
+                                                             const float* __restrict__ sig, const float* __restrict__ Ws,
+                                                             const float* __restrict__ base, int64_t N,
+                                                             float* __restrict__ g_x) {
+  const int lane = threadIdx.x & 31;
+  float2 w[MD];
+#pragma unroll
+  for (int d = 0; d < MD; ++d) w[d] = __ldg(reinterpret_cast<const float2*>(Ws + d * MF) + lane);
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < N; k += warps) {
+    const int pb = __ldg(in_ptr + k), pe = __ldg(in_ptr + k + 1);
+    float acc[MD];
+#pragma unroll
+    for (int d = 0; d < MD; ++d) acc[d] = 0.0f;
+    for (int p = pb + lane; p < pe; p += 32) {  // incoming bonds: ascending edge id per lane, then the fixed tree
+      const float* row = g_sig_e + (int64_t)__ldg(in_perm + p) * MD;
+#pragma unroll
+      for (int d = 0; d < MD; ++d) acc[d] += __ldg(row + d);
+    }
+    const float tot = reduce9_lanes(acc, lane);
+    // component d sits in lane 16 b4 + 8 b3 + 4 b2 + 2 b1 with d = 5 b4 + 3 b3 + 2 b2 + b1
+    float t[MD];
+    const int src_lane[MD] = {0, 2, 4, 8, 10, 16, 18, 20, 24};
+#pragma unroll
+    for (int d = 0; d < MD; ++d) {
+      const float s = __shfl_sync(FULL, tot, src_lane[d]);
+      const float sg = __ldg(sig + k * MD + d);
+      t[d] = s * sg * (1.0f - sg);
+    }
+    float2 v = base ? __ldg(reinterpret_cast<const float2*>(base + k * MF) + lane) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int d = 0; d < MD; ++d) { v.x = fmaf(t[d], w[d].x, v.x); v.y = fmaf(t[d], w[d].y, v.y); }
+    reinterpret_cast<float2*>(g_x + k * MF)[lane] = v;
+  }
+}
+
 }  // namespace m3g
 
 using namespace m3g;
@@ -498,6 +585,26 @@ static inline int mom_launch_shape(Kernel kernel, size_t smem, int64_t N, int n_
 }
 
 extern "C" {
+
+int m3g_tb_sigma64_fwd(const float* x, const float* Ws, const float* bs, int64_t N, int n_sm, float* sig, void* stream) {
+  if (N == 0) return M3G_OK;
+  M3G_REQUIRE(x && Ws && bs && sig, "m3g_tb_sigma64_fwd: null pointer");
+  const int64_t need = (N + 7) / 8, cap = (int64_t)n_sm * 8;
+  tb_sigma64_fwd_kernel<<<(unsigned)(need < cap ? need : cap), 256, 0, as_stream(stream)>>>(x, Ws, bs, N, sig);
+  M3G_LAUNCH_CHECK("m3g_tb_sigma64_fwd");
+  return M3G_OK;
+}
+
+int m3g_tb_sigma64_bwd(const float* g_sig_e, const int32_t* in_ptr, const int32_t* in_perm, const float* sig,
+                       const float* Ws, const float* base, int64_t N, int n_sm, float* g_x, void* stream) {
+  if (N == 0) return M3G_OK;
+  M3G_REQUIRE(g_sig_e && in_ptr && in_perm && sig && Ws && g_x, "m3g_tb_sigma64_bwd: null pointer");
+  const int64_t need = (N + 7) / 8, cap = (int64_t)n_sm * 8;
+  tb_sigma64_bwd_kernel<<<(unsigned)(need < cap ? need : cap), 256, 0, as_stream(stream)>>>(g_sig_e, in_ptr, in_perm, sig,
+                                                                                          Ws, base, N, g_x);
+  M3G_LAUNCH_CHECK("m3g_tb_sigma64_bwd");
+  return M3G_OK;
+}
 
 int m3g_tb_mom_capacity(void) { return 128; }
 

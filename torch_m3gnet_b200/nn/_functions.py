@@ -169,7 +169,10 @@ class ThreeBodyFn(Function):
         E = plan.E
         D = L * R
         sig = _empty((N, D), x)
-        call("tb_sigma_fwd", x, w["Ws"], w["bs"], N, F, D, sig)
+        if (F, D) == (64, 9):
+            call("tb_sigma64_fwd", x, w["Ws"], w["bs"], N, sm_count(x.device), sig)
+        else:
+            call("tb_sigma_fwd", x, w["Ws"], w["bs"], N, F, D, sig)
         red = _empty((E, D), x)
         e_out = torch.empty_like(e)
         moment = radial is not None
@@ -215,7 +218,7 @@ class ThreeBodyFn(Function):
             call("tb_mom_bwd", vec4, G, dG, sig, plan.dst, red, g_e, plan.edge_ptr, plan.tri_ptr, w["r3"], w["WdT"],
                  w["WgT"], N, plan.max_members, sm_count(vec4.device), 0, g_vec4, g_sig_e)
             g_x = _empty((N, F), vec4)
-            call("tb_sigma_bwd", g_sig_e, plan.in_ptr, plan.in_perm, sig, w["Ws"], None, N, F, D, g_x)
+            call("tb_sigma64_bwd", g_sig_e, plan.in_ptr, plan.in_perm, sig, w["Ws"], None, N, sm_count(vec4.device), g_x)
             return g_x, g_e, g_vec4, None, None, None, None, None
         vec4, sig, bas, red = ctx.saved_tensors
         g_red = torch.empty_like(red)
