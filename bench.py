@@ -633,13 +633,34 @@ def run_dd(model, device, D, steps, warmup):
     energy = out["total_energy"].clone()
     captured = False
     ms_graph = None
-    if os.environ.get("M3G_BENCH_DD_GRAPH", "1") != "0":
+    variants = {"nccl_eager_phases": ms_eager}
+    # halos as one pack-and-store kernel each into the peers' landing buffers (NVLink peer memory) + device barrier:
+    # eager phases, then the whole step as one CUDA graph (kernels only: no collective call is left in the step)
+    p2p_parity = None
+    try:
+        p2p = DomainStep(model, db, capture=False, exchange="p2p")
+        variants["p2p_eager_phases"], out_p = timed(p2p)
+        f_p = torch.zeros((n, 3), device=device)
+        f_p[out_p["owned"]] = out_p["forces"]
+        D.dist.all_reduce(f_p)
+        p2p_parity = (float((out_p["total_energy"] - energy).abs().item() / n), float((f_p - forces).abs().max().item()))
+        if os.environ.get("M3G_BENCH_DD_GRAPH", "1") != "0":
+            p2p_graph = DomainStep(model, db, capture=True, exchange="p2p")
+            variants["p2p_cuda_graph"], _ = timed(p2p_graph)
+    except Exception as exc:  # peer access / symmetric memory unavailable: the NCCL path stands
+        res["p2p_error"] = repr(exc)[:300]
+    if os.environ.get("M3G_BENCH_DD_NCCL_GRAPH", "0") == "1":
         try:
             graphed = DomainStep(model, db, capture=True)
-            ms_graph, _ = timed(graphed)
+            variants["nccl_cuda_graph"], _ = timed(graphed)
             captured = True
-        except Exception as exc:  # capture is an optimisation: report why it was not available
+        except Exception as exc:
             res["graph_capture_error"] = repr(exc)[:200]
+    ms_graph = variants.get("p2p_cuda_graph", variants.get("nccl_cuda_graph"))
+    ms_eager = min(v for k, v in variants.items() if k.endswith("eager_phases"))
+    res["variants_ms_per_step"] = variants
+    if p2p_parity is not None:
+        res["p2p_vs_nccl_abs_dE_per_atom"], res["p2p_vs_nccl_max_abs_dF"] = p2p_parity
     best = min(ms_eager, ms_graph) if ms_graph is not None else ms_eager
     res.update(ms_per_step=best, value=n / (best * 1e-3), ms_per_step_eager_phases=ms_eager,
                ms_per_step_cuda_graph=ms_graph, single_gpu_ms_per_step=single,
@@ -649,8 +670,9 @@ def run_dd(model, device, D, steps, warmup):
                owned_atoms_per_rank=[int(v) for v in D.gather(db.n_own)],
                ghosts_held=int(D.sum(db.n_local - db.n_own)), exchanges_per_step=eager.exchanges_per_step,
                halo_bytes_per_rank_per_exchange=int((db.n_local - db.n_own) * 64 * 4),
-               parallelism="scheme B: one r_c ghost shell, bonds / triplets owned by their source atom, per-block "
-                           "all_to_all_single of ghost node features over NCCL")
+               parallelism="scheme B: one r_c ghost shell, bonds / triplets owned by their source atom, per-block halo "
+                           "of ghost node features: NCCL all_to_all_single, or one pack-and-store kernel into the "
+                           "peers' landing buffers over NVLink (symmetric memory) + device barrier")
     if D.rank == 0:
         res["abs_dE_per_atom"] = float((energy - full["total_energy"]).abs().item() / n)
         res["max_abs_dF"] = float((forces - full["forces"]).abs().max().item())

@@ -389,6 +389,11 @@ int m3g_forces_virial(const float* pos, const float* g_pos, const float* lattice
 /* out[r] = in[idx[r]] rows of width W floats (halo pack) ; in[idx[r]] += add[r] (reverse halo unpack) */
 int m3g_rows_gather(const float* in, const int32_t* idx, int64_t n, int W, float* out, void* stream);
 int m3g_rows_scatter_add(const float* add, const int32_t* idx, int64_t n, int W, float* inout, void* stream);
+/* halo push over NVLink / NVSwitch peer memory: row idx[r] (or r when idx == NULL) of `in` (rows of W floats; 16-byte
+ * aligned rows when W % 4 == 0) is stored at the absolute device address dst_addr[r], typically a slot of a PEER
+ * GPU's landing buffer (peer-mapped symmetric memory).  Pack + transfer in one kernel, no collective call; the caller
+ * orders it against the consumer with a device-side barrier (domain.py::DomainStep, exchange = "p2p"). */
+int m3g_rows_put(const float* in, const int32_t* idx, const int64_t* dst_addr, int64_t n, int W, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Whole-step executor (csrc/step.cu): the launch sequence of  Gradient(Sequential[ScaleLength, AtomRef,

@@ -25,7 +25,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cells", type=int, default=6)
     ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--mode", default="engine", choices=["autograd", "engine", "graph"],
+    ap.add_argument("--mode", default="engine", choices=["autograd", "engine", "graph", "p2p", "p2p-graph"],
                     help="autograd: per-operator Functions + DistHaloFn; engine: m3g_step_run phases + exchanges; "
                          "graph: the engine step captured in a CUDA graph (NCCL inside)")
     args = ap.parse_args()
@@ -47,7 +47,8 @@ def main():
     if args.mode == "autograd":
         step = lambda: evaluate_distributed(model, db)  # noqa: E731
     else:
-        step = DomainStep(model, db, capture=(args.mode == "graph"))
+        step = DomainStep(model, db, capture=args.mode.endswith("graph"),
+                          exchange="p2p" if args.mode.startswith("p2p") else "nccl")
     res = step()
     torch.cuda.synchronize()
     dist.barrier()

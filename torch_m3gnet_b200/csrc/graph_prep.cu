@@ -220,6 +220,28 @@ __global__ void rows_scatter_add_kernel(const float* __restrict__ add, const int
   atomicAdd(&inout[(int64_t)idx[r] * W + c], add[i]);
 }
 
+// halo push over NVLink: row r of the selection goes to the absolute device address dst_addr[r] — a slot of a PEER
+// GPU's landing buffer (symmetric memory, peer-mapped pointer).  The pack and the transfer are one kernel: coalesced
+// 16-byte stores straight into the peer's HBM through NVSwitch, no staging buffer and no collective call.
+__global__ void rows_put_kernel(const float* __restrict__ in, const int32_t* __restrict__ idx,
+                                const int64_t* __restrict__ dst_addr, int64_t n, int W) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((W & 3) == 0) {
+    const int W4 = W >> 2;
+    if (i >= n * W4) return;
+    const int64_t r = i / W4;
+    const int c = (int)(i - r * W4);
+    const int64_t row = idx ? idx[r] : r;
+    reinterpret_cast<float4*>(dst_addr[r])[c] = __ldg(reinterpret_cast<const float4*>(in + row * W) + c);
+  } else {
+    if (i >= n * W) return;
+    const int64_t r = i / W;
+    const int c = (int)(i - r * W);
+    const int64_t row = idx ? idx[r] : r;
+    reinterpret_cast<float*>(dst_addr[r])[c] = in[row * W + c];
+  }
+}
+
 }  // namespace m3g
 
 using namespace m3g;
@@ -327,6 +349,15 @@ int m3g_rows_gather(const float* in, const int32_t* idx, int64_t n, int W, float
   M3G_REQUIRE(in && idx && out && W > 0, "m3g_rows_gather: bad argument");
   rows_gather_kernel<<<blocks_for(n * W, 256), 256, 0, as_stream(stream)>>>(in, idx, n, W, out);
   M3G_LAUNCH_CHECK("m3g_rows_gather");
+  return M3G_OK;
+}
+
+int m3g_rows_put(const float* in, const int32_t* idx, const int64_t* dst_addr, int64_t n, int W, void* stream) {
+  if (n == 0) return M3G_OK;
+  M3G_REQUIRE(in && dst_addr && W > 0, "m3g_rows_put: bad argument");
+  const int64_t work = (W & 3) == 0 ? n * (W >> 2) : n * W;
+  rows_put_kernel<<<blocks_for(work, 256), 256, 0, as_stream(stream)>>>(in, idx, dst_addr, n, W);
+  M3G_LAUNCH_CHECK("m3g_rows_put");
   return M3G_OK;
 }
 

@@ -307,7 +307,12 @@ class DomainStep:
     (``capture=True``) and replayed: one host launch per step instead of ~70, which is what a sub-domain of a few
     thousand atoms needs.  New positions go in through ``set_positions``."""
 
-    def __init__(self, model, dbatch: DomainBatch, group=None, capture: bool = False, warmup: int = 2):
+    def __init__(self, model, dbatch: DomainBatch, group=None, capture: bool = False, warmup: int = 2,
+                 exchange: str = "nccl"):
+        """exchange = "nccl": all_to_all_single per halo.  exchange = "p2p": every halo is ONE kernel that packs the rows
+        and stores them straight into the peers' landing buffers over NVLink / NVSwitch (peer-mapped symmetric memory,
+        ``m3g_rows_put``), ordered by a device-side barrier; no collective call is left in the step (the energy sum
+        goes the same way), so a captured step holds kernels only."""
         import torch.distributed as dist
 
         from torch_m3gnet_b200 import engine as E
@@ -347,6 +352,11 @@ class DomainStep:
         self.forces_local = out[K.FORCES]
         self.local_energy = out[K.TOTAL_ENERGY]
         self.exchanges_per_step = 2 * (self.n - 1) + 2
+        self.exchange = exchange
+        if exchange == "p2p":
+            self._setup_p2p()
+        elif exchange != "nccl":
+            raise ValueError("exchange must be 'nccl' or 'p2p'")
         self.graph = None
         if capture:
             side = torch.cuda.Stream(device=dev)
@@ -362,16 +372,81 @@ class DomainStep:
                 self._step()
             self.graph = g
 
+    # ---- peer-memory exchange ---------------------------------------------------------------------------------
+    def _setup_p2p(self):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        dist, dev, plan, me = self.dist, self.device, self.dbatch.plan, self.dbatch.rank
+        world = plan.world
+        rc = plan.recv_counts  # [r][q]: r receives from q  (= q sends to r)
+        n_ghost = [int(rc[r].sum()) for r in range(world)]
+        n_send = [int(rc[:, q].sum()) for q in range(world)]
+        G, S, nx = max(max(n_ghost), 1), max(max(n_send), 1), self.n - 1
+        # landing zones (floats), the same layout on every rank: one zone per exchange of the step, so that a zone is
+        # only rewritten after every rank has passed the barriers of all later exchanges
+        self.z_fwd = [k * G * 64 for k in range(nx)]
+        self.z_rev = [nx * G * 64 + k * S * 64 for k in range(nx)]
+        self.z_pos = nx * (G + S) * 64
+        self.z_en = self.z_pos + ((3 * S + 3) // 4) * 4
+        total = self.z_en + ((world + 3) // 4) * 4
+        self.land = symm_mem.empty(total, dtype=torch.float32, device=dev)
+        self.land.zero_()
+        group = self.group if self.group is not None else dist.group.WORLD
+        self.hdl = symm_mem.rendezvous(self.land, group)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        i64 = dict(dtype=torch.int64, device=dev)
+        # forward: my send rows are ordered by destination rank r; on r they land behind the rows of the owners q < me
+        dest = np.repeat(np.arange(world), self.send_counts)
+        pos_in_chunk = np.concatenate([np.arange(c) for c in self.send_counts]) if self.n_send else np.zeros(0, np.int64)
+        land_row = np.array([int(rc[r, :me].sum()) for r in range(world)])[dest] + pos_in_chunk if self.n_send else dest
+        base = np.array(ptrs, dtype=np.int64)[dest] if self.n_send else np.zeros(0, np.int64)
+        self.addr_fwd = [torch.as_tensor(base + 4 * (z + land_row * 64), **i64) for z in self.z_fwd]
+        # reverse: my ghost rows are ordered by owner rank q; on q they land behind the rows q sent to ranks r < me
+        n_g = self.dbatch.n_local - self.n_own
+        owner = np.repeat(np.arange(world), self.recv_counts)
+        pos_g = np.concatenate([np.arange(c) for c in self.recv_counts]) if n_g else np.zeros(0, np.int64)
+        back_row = np.array([int(rc[:me, q].sum()) for q in range(world)])[owner] + pos_g if n_g else owner
+        gbase = np.array(ptrs, dtype=np.int64)[owner] if n_g else np.zeros(0, np.int64)
+        self.addr_rev = [torch.as_tensor(gbase + 4 * (z + back_row * 64), **i64) for z in self.z_rev]
+        self.addr_pos = torch.as_tensor(gbase + 4 * (self.z_pos + back_row * 3), **i64)
+        self.addr_en = torch.as_tensor(np.array(ptrs, dtype=np.int64) + 4 * (self.z_en + me), **i64)
+        self.zero_idx = torch.zeros(world, dtype=torch.int32, device=dev)
+        self.n_ghost = n_g
+        self._chan = 0
+        dist.barrier(group=self.group)
+        torch.cuda.synchronize(dev)
+
+    def _barrier(self):
+        # device-side barrier of the symmetric-memory handle (a kernel on this stream): the peers' stores issued
+        # before their barrier are visible after ours
+        self.hdl.barrier(channel=self._chan)
+        self._chan = (self._chan + 1) % 8
+
     # ---- halo exchanges -------------------------------------------------------------------------------------
-    def _halo_forward(self, x):
+    def _halo_forward(self, x, k=0):
         from torch_m3gnet_b200._lib import call
+
+        if self.exchange == "p2p":
+            call("rows_put", x, self.send_idx, self.addr_fwd[k], self.n_send, 64)
+            self._barrier()
+            z = self.z_fwd[k]
+            x[self.n_own:].copy_(self.land[z: z + self.n_ghost * 64].view(self.n_ghost, 64))
+            return
 
         call("rows_gather", x, self.send_idx, self.n_send, 64, self.send64)
         self.dist.all_to_all_single(x[self.n_own:], self.send64[: self.n_send], self.recv_counts, self.send_counts,
                                     group=self.group)
 
-    def _halo_reverse(self, g, send_buf, width):
+    def _halo_reverse(self, g, send_buf, width, k=0):
         from torch_m3gnet_b200._lib import call
+
+        if self.exchange == "p2p":
+            addr, z = (self.addr_rev[k], self.z_rev[k]) if width == 64 else (self.addr_pos, self.z_pos)
+            call("rows_put", g[self.n_own:], None, addr, self.n_ghost, width)
+            self._barrier()
+            g[self.n_own:].zero_()
+            call("rows_scatter_add", self.land[z: z + self.n_send * width], self.send_idx, self.n_send, width, g)
+            return
 
         self.dist.all_to_all_single(send_buf[: self.n_send], g[self.n_own:], self.send_counts, self.recv_counts,
                                     group=self.group)
@@ -383,18 +458,26 @@ class DomainStep:
         run = self.engine.run_phases
         run(d, 0, E.phase_conv(0), dev)
         for b in range(1, n):
-            self._halo_forward(self.x_next[b - 1])
+            self._halo_forward(self.x_next[b - 1], b - 1)
             run(d, E.phase_tb(b), E.phase_conv(b), dev)
         run(d, E.phase_readout(n), E.phase_readout(n), dev)
         for b in range(n - 1, -1, -1):
             if b < n - 1:
-                self._halo_reverse(self.g_x[d.cur_x], self.send64, 64)
+                self._halo_reverse(self.g_x[d.cur_x], self.send64, 64, b)
             run(d, E.phase_conv_bwd(n, b), E.phase_tb_bwd(n, b), dev)
         run(d, E.phase_epilogue(n), E.phase_epilogue(n), dev)
         self._halo_reverse(self.g_pos, self.send3, 3)
         run(d, E.phase_forces(n), E.phase_forces(n), dev)
-        self.energy.copy_(self.local_energy[0:1])
-        self.dist.all_reduce(self.energy, group=self.group)
+        if self.exchange == "p2p":
+            from torch_m3gnet_b200._lib import call
+
+            world = len(self.send_counts)
+            call("rows_put", self.local_energy, self.zero_idx, self.addr_en, world, 1)
+            self._barrier()
+            torch.sum(self.land[self.z_en: self.z_en + world], dim=0, keepdim=True, out=self.energy)
+        else:
+            self.energy.copy_(self.local_energy[0:1])
+            self.dist.all_reduce(self.energy, group=self.group)
 
     def set_positions(self, pos_local: torch.Tensor):
         """New local coordinates (owned atoms first, then ghosts, as in ``DomainPlan.local_arrays``); the bond list of
