@@ -56,6 +56,23 @@ UNIT = "atom-steps/s"
 GRIDS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 
 
+def dd_grid(world):
+    """Near-cubic factorisation of the rank count (2 x 2 x 2 for 8, 3 x 2 x 1 for 6, ...)."""
+    if world in GRIDS:
+        return GRIDS[world]
+    best = (world, 1, 1)
+    for a in range(1, world + 1):
+        if world % a:
+            continue
+        for b in range(1, world // a + 1):
+            if (world // a) % b:
+                continue
+            g = tuple(sorted((a, b, world // a // b), reverse=True))
+            if max(g) - min(g) < max(best) - min(best):
+                best = g
+    return best
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -610,7 +627,7 @@ def run_dd(model, device, D, steps, warmup):
     from torch_m3gnet_b200.domain import DomainBatch, DomainPlan, DomainStep
 
     single = D.max(res.get("single_gpu_ms_per_step", 0.0))
-    plan = DomainPlan(lat, cart, z, GRIDS[D.world], 5.0)
+    plan = DomainPlan(lat, cart, z, dd_grid(D.world), 5.0)
     db = DomainBatch(plan, D.rank, 5.0, 4.0, device)
 
     def timed(step):
@@ -665,7 +682,7 @@ def run_dd(model, device, D, steps, warmup):
     res.update(ms_per_step=best, value=n / (best * 1e-3), ms_per_step_eager_phases=ms_eager,
                ms_per_step_cuda_graph=ms_graph, single_gpu_ms_per_step=single,
                speedup_vs_single_gpu=(single / best if single else None),
-               efficiency=(single / best / D.world if single else None), grid=list(GRIDS[D.world]),
+               efficiency=(single / best / D.world if single else None), grid=list(dd_grid(D.world)),
                local_atoms_per_rank=[int(v) for v in D.gather(db.n_local)],
                owned_atoms_per_rank=[int(v) for v in D.gather(db.n_own)],
                ghosts_held=int(D.sum(db.n_local - db.n_own)), exchanges_per_step=eager.exchanges_per_step,

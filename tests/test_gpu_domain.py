@@ -103,10 +103,12 @@ def test_domain_step_single_rank_process_group(device):
             dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["engine", "graph"])
+@pytest.mark.parametrize("mode", ["engine", "graph", "p2p", "p2p-graph"])
 def test_domain_step_one_rank_subprocess(mode):
-    """The torchrun entry with one rank: executor phases, and the whole step (NCCL exchanges included) captured in a
-    CUDA graph.  Runs in its own process: a process group that has captured collectives is left to process exit."""
+    """The torchrun entry with one rank: executor phases with NCCL halos, the whole step (NCCL exchanges included)
+    captured in a CUDA graph, and the same two with the halos as pack-and-store kernels into symmetric-memory landing
+    buffers + device barriers.  Runs in its own process: a process group that has captured collectives is left to
+    process exit."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=1", "--master-addr",
            "127.0.0.1", "--master-port", "29519", os.path.join(ROOT, "tests", "dd_multi_gpu.py"), "--cells", "5",
            "--mode", mode]
