@@ -244,6 +244,13 @@ int m3g_tb_sigma64_bwd(const float* g_sig_e, const int32_t* in_ptr, const int32_
 int m3g_tb_mom_fwd(const float* vec4, const float* G, const float* sig, const int32_t* dst, const int32_t* edge_ptr,
                    const int32_t* tri_ptr, float r3, const float* WdT, const float* WgT, const float* e_in, int64_t N,
                    int max_members, int n_sm, float* red, float* e_out, void* stream);
+/* the forward in two launches (default): m3g_tb_mom_red = the per-atom moment part only (red for member bonds), then
+ * m3g_tb_edge_update = e_out = e_in + SiLU(red WdT) * sigmoid(red WgT) streamed over all bond rows (members by
+ * tri_ptr), independent of the atom structure and bound by the 512 B per bond it moves */
+int m3g_tb_mom_red(const float* vec4, const float* G, const float* sig, const int32_t* dst, const int32_t* edge_ptr,
+                   const int32_t* tri_ptr, float r3, int64_t N, int max_members, int n_sm, float* red, void* stream);
+int m3g_tb_edge_update(const float* red, const int32_t* tri_ptr, const float* WdT, const float* WgT, const float* e_in,
+                       int64_t E, int n_sm, float* e_out, void* stream);
 int m3g_tb_mom_bwd(const float* vec4, const float* G, const float* dG, const float* sig, const int32_t* dst,
                    const float* red, const float* g_e, const int32_t* edge_ptr, const int32_t* tri_ptr, float r3,
                    const float* WdT, const float* WgT, int64_t N, int max_members, int n_sm, int accumulate,
@@ -469,6 +476,7 @@ typedef struct M3GStepDesc {
   int cur_x, cur_e;               /* state carried between phases (updated by m3g_step_run) */
   int have_g_e;                   /* 0 until the first conv adjoint has produced g_e */
   int msg_reduce;                 /* 1: node MLP sums its messages per atom in-kernel (m3g_conv_tc_fwd mode 2) */
+  int tb_split;                   /* 1: three-body forward as m3g_tb_mom_red + m3g_tb_edge_update */
   M3GStepBlock blocks[M3G_STEP_MAX_BLOCKS];
 } M3GStepDesc;
 

@@ -40,8 +40,14 @@ int prologue(M3GStepDesc* d, void* s) {
 int tb_fwd(M3GStepDesc* d, int b, void* s) {
   M3GStepBlock& k = d->blocks[b];
   M3G_TRY(m3g_tb_sigma64_fwd(k.x_in, k.Ws, k.bs, d->N, d->n_sm, k.sig, s));
-  M3G_TRY(m3g_tb_mom_fwd(d->vec4, k.G, k.sig, d->dst, d->edge_ptr, d->tri_ptr, d->r3, k.WdT, k.WgT, k.e_in, d->N,
-                         d->max_members, d->n_sm, k.red, k.e_tb, s));
+  if (d->tb_split) {
+    M3G_TRY(m3g_tb_mom_red(d->vec4, k.G, k.sig, d->dst, d->edge_ptr, d->tri_ptr, d->r3, d->N, d->max_members, d->n_sm,
+                           k.red, s));
+    M3G_TRY(m3g_tb_edge_update(k.red, d->tri_ptr, k.WdT, k.WgT, k.e_in, d->E, d->n_sm, k.e_tb, s));
+  } else {
+    M3G_TRY(m3g_tb_mom_fwd(d->vec4, k.G, k.sig, d->dst, d->edge_ptr, d->tri_ptr, d->r3, k.WdT, k.WgT, k.e_in, d->N,
+                           d->max_members, d->n_sm, k.red, k.e_tb, s));
+  }
   return M3G_OK;
 }
 

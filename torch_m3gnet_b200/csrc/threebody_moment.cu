@@ -315,6 +315,117 @@ __global__ void __launch_bounds__(32 * MW, 4) tb_mom_fwd_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
+// The forward split in two (default): the per-atom part only produces red (no weights, no edge rows: few registers,
+// many warps per SM to hide the staging latency) ...
+__global__ void __launch_bounds__(32 * MW, 8) tb_mom_red_kernel(
+    const float4* __restrict__ vec4, const float* __restrict__ G, const float* __restrict__ sig,
+    const int32_t* __restrict__ dst, const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ tri_ptr,
+    float r3, int64_t N, int cap, float* __restrict__ red) {
+  extern __shared__ __align__(16) float smem_f[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* ent = smem_f + (size_t)warp * (cap * ES + M_SIDE);
+  float* mom = ent + cap * ES;
+  const LaneRole role = lane_role(lane);
+  for (int64_t atom = (int64_t)blockIdx.x * MW + warp; atom < N; atom += (int64_t)gridDim.x * MW) {
+    const int beg = __ldg(edge_ptr + atom), end = __ldg(edge_ptr + atom + 1);
+    const int n3 = stage<false>(ent, cap, beg, end, vec4, G, sig, dst, nullptr, tri_ptr, r3, lane);
+    accumulate_side<false, false>(ent, n3, O_B, role, mom);
+    __syncwarp();
+    for (int j = lane; j < n3; j += 32) {
+      const float* en = ent + j * ES;
+      const float4 u4 = *reinterpret_cast<const float4*>(en + O_U);
+      const float4 oa = *reinterpret_cast<const float4*>(en + O_O6), ob = *reinterpret_cast<const float4*>(en + 8);
+      const float4 b0 = *reinterpret_cast<const float4*>(en + O_B), b1 = *reinterpret_cast<const float4*>(en + O_B + 4),
+                   b2 = *reinterpret_cast<const float4*>(en + O_B + 8);
+      const float u[3] = {u4.x, u4.y, u4.z};
+      const float o6[6] = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y};
+      const float own[MD] = {b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, b2.x, b2.y, b2.z};
+      float acc[MD];
+      eval_rows(mom, u, o6, own, acc);
+      float* ro = red + (int64_t)__float_as_int(b0.w) * MD;
+#pragma unroll
+      for (int d = 0; d < MD; ++d) ro[d] = ob.z * acc[d];
+    }
+    __syncwarp();
+  }
+}
+
+// ... and the edge update e_out = e_in + SiLU(red WdT) * sigmoid(red WgT) streams ALL bond rows, independent of the
+// atom structure: a warp takes 32 consecutive rows at a time (member flags by ballot, the chunk's red rows staged in
+// shared memory for broadcast reads, 2 x 8 rows of e in flight per warp), lane = two feature columns (FFMA2).  This half
+// is bound by the 512 B per bond it has to move.
+constexpr int UW = 8;  // warps per CTA
+__global__ void __launch_bounds__(32 * UW, 2) tb_edge_update_kernel(
+    const float* __restrict__ red, const int32_t* __restrict__ tri_ptr, const float* __restrict__ WdT,
+    const float* __restrict__ WgT, const float* __restrict__ e_in, int64_t E, float* __restrict__ e_out) {
+  __shared__ __align__(16) float red_s[UW][32][12];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2 wd[MD], wg[MD];
+#pragma unroll
+  for (int d = 0; d < MD; ++d) {
+    wd[d] = __ldg(reinterpret_cast<const float2*>(WdT + d * MF) + lane);
+    wg[d] = __ldg(reinterpret_cast<const float2*>(WgT + d * MF) + lane);
+  }
+  const int64_t n_chunks = (E + 31) >> 5;
+  const int64_t stride = (int64_t)gridDim.x * UW;
+  constexpr int RB = 8;
+  for (int64_t chunk = (int64_t)blockIdx.x * UW + warp; chunk < n_chunks; chunk += stride) {
+    const int64_t e0 = chunk << 5;
+    const int rows = (int)min((int64_t)32, E - e0);
+    float2 ra[RB], rb[RB];
+    auto load_rows = [&](float2* row, int r0) {
+#pragma unroll
+      for (int i = 0; i < RB; ++i)
+        if (r0 + i < rows) row[i] = __ldg(reinterpret_cast<const float2*>(e_in + (e0 + r0 + i) * MF) + lane);
+    };
+    load_rows(ra, 0);
+    load_rows(rb, RB);
+    bool member = false;
+    if (lane < rows) member = __ldg(tri_ptr + e0 + lane + 1) > __ldg(tri_ptr + e0 + lane);
+    const unsigned mask = __ballot_sync(FULL, member);
+    if (member) {
+      const float* q = red + (e0 + lane) * MD;
+      float qq[MD];
+#pragma unroll
+      for (int d = 0; d < MD; ++d) qq[d] = __ldg(q + d);
+      float4* o = reinterpret_cast<float4*>(&red_s[warp][lane][0]);
+      o[0] = make_float4(qq[0], qq[1], qq[2], qq[3]);
+      o[1] = make_float4(qq[4], qq[5], qq[6], qq[7]);
+      o[2] = make_float4(qq[8], 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+    auto process_rows = [&](float2* row, int r0) {
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const int r = r0 + i;
+        if (r >= rows) break;
+        if (mask & (1u << r)) {
+          const float4* rs = reinterpret_cast<const float4*>(&red_s[warp][r][0]);
+          const float4 q0 = rs[0], q1 = rs[1], q2 = rs[2];
+          const float rd[MD] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
+          float2 u2 = make_float2(0.f, 0.f), g2 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int d = 0; d < MD; ++d) {
+            u2 = fma2s(rd[d], wd[d], u2);
+            g2 = fma2s(rd[d], wg[d], g2);
+          }
+          row[i].x += silu_m(u2.x) * sigmoid_m(g2.x);
+          row[i].y += silu_m(u2.y) * sigmoid_m(g2.y);
+        }
+        reinterpret_cast<float2*>(e_out + (e0 + r) * MF)[lane] = row[i];
+      }
+    };
+    process_rows(ra, 0);
+    load_rows(ra, 2 * RB);
+    process_rows(rb, RB);
+    load_rows(rb, 3 * RB);
+    process_rows(ra, 2 * RB);
+    process_rows(rb, 3 * RB);
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // backward: g_vec4 (E,4) = d/d(v, r) (zeros for non-member bonds; includes the fc' and the radial-basis chain through
 // dG) and g_sig_e (E,9) = per-bond gradient of sigma[dst] (zeros for non-member bonds)
 __global__ void __launch_bounds__(32 * MW, 4) tb_mom_bwd_kernel(
@@ -624,6 +735,34 @@ int m3g_tb_mom_fwd(const float* vec4, const float* G, const float* sig, const in
   tb_mom_fwd_kernel<<<grid, 32 * MW, smem, as_stream(stream)>>>((const float4*)vec4, G, sig, dst, edge_ptr, tri_ptr, r3,
                                                                WdT, WgT, e_in, N, cap, red, e_out);
   M3G_LAUNCH_CHECK("m3g_tb_mom_fwd");
+  return M3G_OK;
+}
+
+int m3g_tb_mom_red(const float* vec4, const float* G, const float* sig, const int32_t* dst, const int32_t* edge_ptr,
+                   const int32_t* tri_ptr, float r3, int64_t N, int max_members, int n_sm, float* red, void* stream) {
+  if (N == 0) return M3G_OK;
+  M3G_REQUIRE(vec4 && G && sig && dst && edge_ptr && tri_ptr && red, "m3g_tb_mom_red: null pointer");
+  M3G_REQUIRE(max_members >= 0 && max_members <= 128, "m3g_tb_mom_red: %d member bonds per atom exceed the capacity 128",
+              max_members);
+  const int cap = pick_cap(max_members);
+  const size_t smem = (size_t)MW * (cap * ES + M_SIDE) * sizeof(float);
+  unsigned grid;
+  int rc = mom_launch_shape(tb_mom_red_kernel, smem, N, n_sm, true, &grid);
+  if (rc != M3G_OK) return rc;
+  tb_mom_red_kernel<<<grid, 32 * MW, smem, as_stream(stream)>>>((const float4*)vec4, G, sig, dst, edge_ptr, tri_ptr, r3, N,
+                                                               cap, red);
+  M3G_LAUNCH_CHECK("m3g_tb_mom_red");
+  return M3G_OK;
+}
+
+int m3g_tb_edge_update(const float* red, const int32_t* tri_ptr, const float* WdT, const float* WgT, const float* e_in,
+                       int64_t E, int n_sm, float* e_out, void* stream) {
+  if (E == 0) return M3G_OK;
+  M3G_REQUIRE(red && tri_ptr && WdT && WgT && e_in && e_out, "m3g_tb_edge_update: null pointer");
+  const int64_t need = ((E + 31) / 32 + UW - 1) / UW, capb = (int64_t)n_sm * 2;
+  tb_edge_update_kernel<<<(unsigned)(need < capb ? need : capb), 32 * UW, 0, as_stream(stream)>>>(red, tri_ptr, WdT, WgT,
+                                                                                               e_in, E, e_out);
+  M3G_LAUNCH_CHECK("m3g_tb_edge_update");
   return M3G_OK;
 }
 

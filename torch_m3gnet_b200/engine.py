@@ -52,7 +52,7 @@ class _Desc(ctypes.Structure):
                 + [("g_x", _fp * 2), ("g_e", _fp * 2)]
                 + [(n, _fp) for n in ("ge2", "gz_edge", "gz_node", "gP", "g_h", "g_h2", "g_sig_e", "g_vec4", "g_dist",
                                       "g_pos")]
-                + [(n, ctypes.c_int) for n in ("cur_x", "cur_e", "have_g_e", "msg_reduce")]
+                + [(n, ctypes.c_int) for n in ("cur_x", "cur_e", "have_g_e", "msg_reduce", "tb_split")]
                 + [("blocks", _Block * MAX_BLOCKS)])
 
 
@@ -154,6 +154,7 @@ class StepEngine:
         """Allocate outputs + scratch and fill the descriptor.  Returns (desc, keep) where ``keep`` holds every tensor the
         descriptor points to (outputs by name under keep["out"])."""
         from torch_m3gnet_b200.nn import conv as conv_mod
+        from torch_m3gnet_b200.nn import interaction
         from torch_m3gnet_b200.nn._functions import sm_count
 
         pos = graph[K.POS].detach().contiguous()
@@ -205,6 +206,7 @@ class StepEngine:
         d.n_blocks, d.n_sm, d.max_members = n, sm_count(dev), int(plan.max_members)
         d.passes = 3 if conv_mod.CONV_PATH == "tc3" else 1
         d.msg_reduce = int(conv_mod.MSG_REDUCE)
+        d.tb_split = int(interaction.TB_SPLIT)
         d.n_members = int(plan.n_members)
         d.length_scale, d.energy_scale = float(self.scale.length_scale), float(self.readout.scale)
         d.r3 = float(weights[0][0]["r3"])
@@ -283,7 +285,9 @@ class StepEngine:
         backward (3 for block 0, whose node-feature gradient is dead), 4 in the epilogue, 2 for forces + virial."""
         n = self.n_blocks
         tables = len({t._packed.get()["consts_key"] for t in self.tbs})
-        return 8 + int(with_angles) + tables + 6 * n + 3 + (7 * n - 4) + 4 + 2
+        from torch_m3gnet_b200.nn import interaction
+
+        return 8 + int(with_angles) + tables + (6 + int(interaction.TB_SPLIT)) * n + 3 + (7 * n - 4) + 4 + 2
 
     def run(self, graph, plan):
         desc, keep = self.prepare(graph, plan)

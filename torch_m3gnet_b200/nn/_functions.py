@@ -181,8 +181,15 @@ class ThreeBodyFn(Function):
         bas = None
         if moment:
             G = radial[0]
-            call("tb_mom_fwd", vec4, G, sig, plan.dst, plan.edge_ptr, plan.tri_ptr, w["r3"], w["WdT"], w["WgT"], e,
-                 plan.N, plan.max_members, sm_count(x.device), red, e_out)
+            from torch_m3gnet_b200.nn import interaction
+
+            if interaction.TB_SPLIT:
+                call("tb_mom_red", vec4, G, sig, plan.dst, plan.edge_ptr, plan.tri_ptr, w["r3"], plan.N,
+                     plan.max_members, sm_count(x.device), red)
+                call("tb_edge_update", red, plan.tri_ptr, w["WdT"], w["WgT"], e, E, sm_count(x.device), e_out)
+            else:
+                call("tb_mom_fwd", vec4, G, sig, plan.dst, plan.edge_ptr, plan.tri_ptr, w["r3"], w["WdT"], w["WgT"], e,
+                     plan.N, plan.max_members, sm_count(x.device), red, e_out)
         else:
             bas = _empty((E, D), x)
             call("tb_edge_basis_fwd", vec4, plan.dst, sig, w["consts"], E, L, R, plan.member_edges, plan.n_members,

@@ -20,6 +20,9 @@ from torch_m3gnet_b200.nn.invariant import PAIR_VEC4
 # width-agnostic CSR kernels everywhere
 TB_PATH = os.environ.get("M3G_TB_PATH", "moment")
 RADIAL_CACHE = "_tb_radial"
+# moment path, forward: True (default) = per-atom moment kernel (red only) + a streaming edge-update kernel over all bond
+# rows; False = one fused per-atom kernel
+TB_SPLIT = os.environ.get("M3G_TB_SPLIT", "1") != "0"
 
 __all__ = ["ThreeBodyInteration", "NormalizedSphericalBessel", "SPHERICAL_BESSEL_ZEROS", "spherical_bessel",
            "legendre_cos", "cutoff_function"]
