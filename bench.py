@@ -368,7 +368,8 @@ TRAFFIC_KERNEL = {
     "tb_sigma_bwd": "tb_sigma_bwd_kernel<16>", "tb_radial": "tb_radial33_kernel",
     "tb_sigma64_fwd": "tb_sigma64_fwd_kernel", "tb_sigma64_bwd": "tb_sigma64_bwd_kernel",
     "segment_sum_parts": "segment_sum_parts_kernel", "tb_mom_red": "tb_mom_red_kernel",
-    "tb_edge_update": "tb_edge_update_kernel",
+    "tb_edge_update": "tb_edge_update_kernel", "tb_mlp_adj": "tb_mlp_adj_kernel",
+    "tb_mom_bwd_q": "tb_mom_bwd_kernel<0>",
 }
 
 
@@ -406,7 +407,7 @@ def kernel_model(E, T, N, Em, F=64, R=3):
         # all; `moved` below is what they actually have to move: member bonds only for the per-bond three-body data)
         "threebody_fwd": (("tb_sigma64_fwd", "tb_sigma_fwd", "tb_mom_red", "tb_edge_update", "tb_mom_fwd", "tb_edge_basis_fwd", "tb_reduce_fwd", "tb_reduce_fwd_fast",
                            "tb_atom_fwd"), 4 * T + 536 * E + 36 * N, 512 * E + (16 + 36 + 36 + 4) * Em + 256 * N + 36 * N),
-        "threebody_bwd": (("tb_mom_bwd", "tb_sigma64_bwd", "tb_sigma_bwd", "tb_gate_bwd", "tb_gate_bwd_fast", "tb_reduce_bwd",
+        "threebody_bwd": (("tb_mlp_adj", "tb_mom_bwd_q", "tb_mom_bwd", "tb_sigma64_bwd", "tb_sigma_bwd", "tb_gate_bwd", "tb_gate_bwd_fast", "tb_reduce_bwd",
                            "tb_reduce_bwd_sym", "tb_atom_bwd", "tb_edge_basis_bwd"), 4 * T + 332 * E + 72 * N,
                           256 * Em + (16 + 36 + 36 + 36 + 4) * Em + 16 * E + 36 * E + 36 * E + 256 * N + 72 * N),
     }

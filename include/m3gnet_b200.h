@@ -251,10 +251,23 @@ int m3g_tb_mom_red(const float* vec4, const float* G, const float* sig, const in
                    const int32_t* tri_ptr, float r3, int64_t N, int max_members, int n_sm, float* red, void* stream);
 int m3g_tb_edge_update(const float* red, const int32_t* tri_ptr, const float* WdT, const float* WgT, const float* e_in,
                        int64_t E, int n_sm, float* e_out, void* stream);
+/* the same with e_in = SiLU(h WaT) (the EdgeAdjustor's output, nn/featurizer.py:84-96; h (E,3), WaT (3,64)) formed
+ * in-kernel: the first block of the whole-step executor neither writes nor re-reads e0 (bit-identical to
+ * m3g_edge_adjust_fwd followed by m3g_tb_edge_update) */
+int m3g_tb_edge_update_h(const float* red, const int32_t* tri_ptr, const float* WdT, const float* WgT, const float* h,
+                         const float* WaT, int64_t E, int n_sm, float* e_out, void* stream);
 int m3g_tb_mom_bwd(const float* vec4, const float* G, const float* dG, const float* sig, const int32_t* dst,
                    const float* red, const float* g_e, const int32_t* edge_ptr, const int32_t* tri_ptr, float r3,
                    const float* WdT, const float* WgT, int64_t N, int max_members, int n_sm, int accumulate,
                    float* g_vec4, float* g_sig_e, void* stream);
+/* the backward in two launches (default): m3g_tb_mlp_adj = adjoint of the 9 -> 64 gated MLP (nn/interaction.py:219-220,
+ * nn/core.py:61-62) over the packed member-bond list, q[e] = dL/dred[e] (a lane owns a row: no cross-lane sums; q may
+ * alias red); then m3g_tb_mom_bwd_q = the per-atom moment part of m3g_tb_mom_bwd reading q (no weights, no edge rows) */
+int m3g_tb_mlp_adj(const float* red, const float* g_e, const int32_t* member_edges, int64_t n_members, const float* WdT,
+                   const float* WgT, int n_sm, float* q, void* stream);
+int m3g_tb_mom_bwd_q(const float* vec4, const float* G, const float* dG, const float* sig, const int32_t* dst,
+                     const float* q, const int32_t* edge_ptr, const int32_t* tri_ptr, float r3, int64_t N,
+                     int max_members, int n_sm, int accumulate, float* g_vec4, float* g_sig_e, void* stream);
 
 /* Specialised variants for the default model shape l_max = n_max = 3, F = 64 (compile-time loops, gated-MLP
  * weights in shared memory, vector row I/O, persistent grid of 8 x n_sm blocks).  Same results and buffers as
@@ -341,6 +354,9 @@ int m3g_debug_mma_rate(int N, int a_tmem, int n_mma, int64_t* cycles2, void* str
 /* same for tcgen05.mma.cta_group::2 (M = 256 over a two-CTA cluster, A and B from shared memory): cycles2[0] = issue
  * loop, cycles2[1] = until the multicast commit arrives in the leader CTA. */
 int m3g_debug_mma_rate2(int N, int n_mma, int64_t* cycles2, void* stream);
+/* dev tool (tools/pipe_rate.py): clock cycles of `iters` x 32 instructions of one kind per thread (8 independent
+ * chains) with `threads` threads per SM — kinds in csrc/debug_rate.cu */
+int m3g_debug_pipe_rate(int kind, int threads, int iters, int64_t* cycles, void* stream);
 /* UMMA plumbing self test on one 128-row tile: out (128 x rows) = A (128 x cols) · W^T, W given as its image;
  * a_tmem = 1 feeds A from tensor memory (tcgen05.st + the [a_tmem] operand form) instead of shared memory */
 int m3g_tc_selftest(const float* A, const float* img_hi, const float* img_lo, int rows, int cols, int passes,
@@ -352,10 +368,11 @@ int m3g_conv_tc_fwd(const float* P, int ldp, int po, const int32_t* src, const i
                     const float* h, const float* wimg, const float* b2d, const float* b2g, const float* WhT, int64_t E,
                     int R, int mode, int passes, int n_sm, float* y, float* save, void* stream);
 /* (nn/conv.py:63-89 with nn/core.py:30-62 for m3g_conv_tc_fwd; the two functions below replace its autograd)
- * save (optional): activations for m3g_conv_tc_bwd_saved — ceil(E / 128) * 128 * 256 floats (1 KB per edge:
+ * save (optional): activations for m3g_conv_tc_bwd_saved — m3g_conv_tc_save_floats(E) floats (1 KB per edge:
  * SiLU'(z1) and the layer-2 pre-activations, in a tile-private fragment-major layout).  With them the backward needs
  * neither the forward weights nor P / e: output adjoint -> two 64x64 adjoint GEMM pairs -> g_e, g_z1, g_h (same outputs
  * and conventions as m3g_conv_tc_bwd; src is only read for mode 1, where g_up is indexed by source atom). */
+int64_t m3g_conv_tc_save_floats(int64_t E);
 int m3g_conv_tc_bwd_saved(const int32_t* src, const float* h, const float* wimgT, const float* WhT, const float* save,
                           const float* g_up, const float* g_e_base, int64_t E, int R, int mode, int passes, int n_sm,
                           float* g_e, float* g_z1, float* g_h, void* stream);
@@ -386,6 +403,13 @@ int m3g_readout_bwd(const float* x, const float* W0dT, const float* b0d, const f
                     const float* W0g, const float* W1g, const float* g_atomic, const float* g_scaled_total,
                     const float* g_total, const int32_t* batch, float scale, int64_t N, int F, float* g_x,
                     void* stream);
+/* m3g_readout_fwd and m3g_readout_bwd in ONE launch for a caller that knows the upstream gradient beforehand (the
+ * whole-step executor: g_total is an input): writes atomic (N) and g_x (N,F); same arithmetic as the two calls */
+int m3g_readout_fwd_bwd(const float* x, const float* W0dT, const float* b0d, const float* W1dT, const float* b1d,
+                        const float* w2d, const float* b2d, const float* W0gT, const float* b0g, const float* W1gT,
+                        const float* b1g, const float* w2g, const float* b2g, const float* W0d, const float* W1d,
+                        const float* W0g, const float* W1g, const float* elemental, const float* g_total,
+                        const int32_t* batch, float scale, int64_t N, int F, float* atomic, float* g_x, void* stream);
 /* forces = -g_pos; stresses (B,6) = Voigt(sum_i pos_i (x) F_i)/|det lattice| */
 int m3g_forces_virial(const float* pos, const float* g_pos, const float* lattice, const int32_t* atom_ptr,
                       int64_t N, int64_t B, float* forces, float* stresses, void* stream);
@@ -477,6 +501,8 @@ typedef struct M3GStepDesc {
   int have_g_e;                   /* 0 until the first conv adjoint has produced g_e */
   int msg_reduce;                 /* 1: node MLP sums its messages per atom in-kernel (m3g_conv_tc_fwd mode 2) */
   int tb_split;                   /* 1: three-body forward as m3g_tb_mom_red + m3g_tb_edge_update */
+  int tb_bwd_split;               /* 1: three-body backward as m3g_tb_mlp_adj (q overwrites red) + m3g_tb_mom_bwd_q */
+  int fuse_e0;                    /* 1 (needs tb_split): e0 is formed inside block 0's m3g_tb_edge_update_h, never stored */
   M3GStepBlock blocks[M3G_STEP_MAX_BLOCKS];
 } M3GStepDesc;
 

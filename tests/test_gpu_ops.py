@@ -116,14 +116,18 @@ def _threebody_reference_grads(g, gd):
     return out, red, gx, ge, gv
 
 
-@pytest.fixture(params=["moment", "atom", "fast", "generic"])
+@pytest.fixture(params=["moment", "moment-fused", "atom", "fast", "generic"])
 def tb_path(request):
+    """"moment" = the default split kernels (moments + streaming MLP / MLP adjoint); "moment-fused" = the one-kernel
+    per-atom forms of the same path (M3G_TB_SPLIT=0, M3G_TB_BWD_SPLIT=0)."""
     from torch_m3gnet_b200.nn import interaction
 
-    old = interaction.TB_PATH
-    interaction.TB_PATH = request.param
+    old = interaction.TB_PATH, interaction.TB_SPLIT, interaction.TB_BWD_SPLIT
+    interaction.TB_PATH = request.param.split("-")[0]
+    if request.param == "moment-fused":
+        interaction.TB_SPLIT = interaction.TB_BWD_SPLIT = False
     yield request.param
-    interaction.TB_PATH = old
+    interaction.TB_PATH, interaction.TB_SPLIT, interaction.TB_BWD_SPLIT = old
 
 
 def test_threebody_operator(device, tb_path):

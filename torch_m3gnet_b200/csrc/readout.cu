@@ -1,5 +1,7 @@
 // AtomWiseReadout (nn/readout.py:39-58): 3-layer gated MLP F→F→F→1 per atom, per-structure energy sums,
 // and the hand-written adjoint w.r.t. the node features.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace m3g {
@@ -64,13 +66,14 @@ struct ReadoutW {
 };
 
 // BWD = false: writes atomic[i] = elemental[i]/scale + eps_i
-// BWD = true : writes g_x
-template <int NJ, bool BWD, int EPW, bool SW>
-__global__ void __launch_bounds__(SW ? RO_WARPS_SW * 32 : RO_WARPS * 32)
+// BWD = true : writes g_x (and, when atomic_out is given, the forward result as well: the whole-step executor knows the
+//              upstream gradient before the readout runs, so forward and adjoint are ONE launch there)
+template <int NJ, bool BWD, int EPW, bool SW, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 readout_kernel(const float* __restrict__ x, ReadoutW w, const float* __restrict__ elemental, float scale,
                const float* __restrict__ g_atomic, const float* __restrict__ g_scaled_total,
                const float* __restrict__ g_total, const int32_t* __restrict__ batch, int64_t N, int F,
-               float* __restrict__ out) {
+               float* __restrict__ out, float* __restrict__ atomic_out) {
   extern __shared__ __align__(16) float smem[];
   constexpr int RO_EPW = EPW;  // shadows the namespace constant inside the kernel
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
@@ -164,6 +167,11 @@ readout_kernel(const float* __restrict__ x, ReadoutW w, const float* __restrict_
     }
     continue;
   }
+  if (atomic_out && lane == 0) {
+#pragma unroll
+    for (int q = 0; q < RO_EPW; ++q)
+      if (i0 + q < N) atomic_out[iq[q]] = elemental[iq[q]] / scale + dout[q] * gout[q];
+  }
   __syncwarp();  // a0_s is about to be overwritten with dz1
 #pragma unroll
   for (int q = 0; q < RO_EPW; ++q) {
@@ -240,12 +248,24 @@ __global__ void structure_sum_kernel(const float* __restrict__ atomic, const int
   }
 }
 
+// persistent shape of the shared-weight variant: 8 warps x 8 atoms, or 16 warps x 4 atoms (M3G_RO_WARPS=16: more warps
+// to hide the shared-memory latency of the matvecs at 2x the weight reads per atom)
+static int ro_warps_sw() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("M3G_RO_WARPS");
+    v = (e && atoi(e) == 8) ? 8 : 16;
+  }
+  return v;
+}
+
 template <bool BWD>
 static int launch_readout(const float* x, const ReadoutW& w, const float* elemental, float scale,
                           const float* g_atomic, const float* g_st, const float* g_t, const int32_t* batch, int64_t N,
-                          int F, float* out, cudaStream_t st) {
+                          int F, float* out, float* atomic_out, cudaStream_t st) {
   const int nj = (F + 31) / 32;
-  const size_t smem_sw = ((size_t)RO_WARPS_SW * RO_EPW_SW * 5 * F + (size_t)(BWD ? 8 : 4) * F * F) * sizeof(float);
+  const int sw_warps = ro_warps_sw(), sw_epw = sw_warps == 16 ? 4 : 8;
+  const size_t smem_sw = ((size_t)sw_warps * sw_epw * 5 * F + (size_t)(BWD ? 8 : 4) * F * F) * sizeof(float);
   const bool sw = (F % 4 == 0) && smem_sw <= 227 * 1024 && nj <= 2;
   if (sw) {
     static int n_sm = 0;
@@ -254,16 +274,20 @@ static int launch_readout(const float* x, const ReadoutW& w, const float* elemen
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     }
-    unsigned grid = blocks_for(N, RO_WARPS_SW * RO_EPW_SW);
+    unsigned grid = blocks_for(N, sw_warps * sw_epw);
     if (grid > (unsigned)n_sm) grid = (unsigned)n_sm;
-#define LAUNCH_SW_(NJ)                                                                                              \
+#define LAUNCH_SW_(NJ, EPW_, WARPS_)                                                                                \
   do {                                                                                                              \
-    cudaFuncSetAttribute(readout_kernel<NJ, BWD, RO_EPW_SW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+    cudaFuncSetAttribute(readout_kernel<NJ, BWD, EPW_, true, WARPS_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                          (int)smem_sw);                                                                             \
-    readout_kernel<NJ, BWD, RO_EPW_SW, true><<<grid, RO_WARPS_SW * 32, smem_sw, st>>>(                              \
-        x, w, elemental, scale, g_atomic, g_st, g_t, batch, N, F, out);                                             \
+    readout_kernel<NJ, BWD, EPW_, true, WARPS_><<<grid, WARPS_ * 32, smem_sw, st>>>(                                \
+        x, w, elemental, scale, g_atomic, g_st, g_t, batch, N, F, out, atomic_out);                                 \
   } while (0)
-    if (nj == 1) LAUNCH_SW_(1); else LAUNCH_SW_(2);
+    if (sw_warps == 16) {
+      if (nj == 1) LAUNCH_SW_(1, 4, 16); else LAUNCH_SW_(2, 4, 16);
+    } else {
+      if (nj == 1) LAUNCH_SW_(1, 8, 8); else LAUNCH_SW_(2, 8, 8);
+    }
 #undef LAUNCH_SW_
     return 0;
   }
@@ -272,10 +296,10 @@ static int launch_readout(const float* x, const ReadoutW& w, const float* elemen
 #define LAUNCH_(NJ)                                                                                        \
   do {                                                                                                     \
     if (smem > 48 * 1024)                                                                                  \
-      cudaFuncSetAttribute(readout_kernel<NJ, BWD, RO_EPW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                           (int)smem);                                                                     \
-    readout_kernel<NJ, BWD, RO_EPW, false><<<grid, RO_WARPS * 32, smem, st>>>(x, w, elemental, scale, g_atomic, g_st, \
-                                                                              g_t, batch, N, F, out);      \
+      cudaFuncSetAttribute(readout_kernel<NJ, BWD, RO_EPW, false, RO_WARPS>,                               \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                        \
+    readout_kernel<NJ, BWD, RO_EPW, false, RO_WARPS><<<grid, RO_WARPS * 32, smem, st>>>(                   \
+        x, w, elemental, scale, g_atomic, g_st, g_t, batch, N, F, out, atomic_out);                        \
   } while (0)
   if (nj == 1) LAUNCH_(1); else if (nj == 2) LAUNCH_(2); else if (nj == 3) LAUNCH_(3); else LAUNCH_(4);
 #undef LAUNCH_
@@ -298,7 +322,8 @@ int m3g_readout_fwd(const float* x, const float* W0dT, const float* b0d, const f
               "m3g_readout_fwd: null pointer");
   M3G_REQUIRE(F >= 1 && F <= M3G_MAX_F, "m3g_readout_fwd: F=%d outside [1,%d]", F, M3G_MAX_F);
   ReadoutW w{W0dT, b0d, W1dT, b1d, w2d, b2d, W0gT, b0g, W1gT, b1g, w2g, b2g, nullptr, nullptr, nullptr, nullptr};
-  launch_readout<false>(x, w, elemental, scale, nullptr, nullptr, nullptr, nullptr, N, F, atomic, as_stream(stream));
+  launch_readout<false>(x, w, elemental, scale, nullptr, nullptr, nullptr, nullptr, N, F, atomic, nullptr,
+                        as_stream(stream));
   M3G_LAUNCH_CHECK("m3g_readout_fwd");
   return M3G_OK;
 }
@@ -325,8 +350,25 @@ int m3g_readout_bwd(const float* x, const float* W0dT, const float* b0d, const f
               "m3g_readout_bwd: null pointer");
   M3G_REQUIRE(F >= 1 && F <= M3G_MAX_F, "m3g_readout_bwd: F=%d outside [1,%d]", F, M3G_MAX_F);
   ReadoutW w{W0dT, b0d, W1dT, b1d, w2d, b2d, W0gT, b0g, W1gT, b1g, w2g, b2g, W0d, W1d, W0g, W1g};
-  launch_readout<true>(x, w, nullptr, scale, g_atomic, g_scaled_total, g_total, batch, N, F, g_x, as_stream(stream));
+  launch_readout<true>(x, w, nullptr, scale, g_atomic, g_scaled_total, g_total, batch, N, F, g_x, nullptr,
+                       as_stream(stream));
   M3G_LAUNCH_CHECK("m3g_readout_bwd");
+  return M3G_OK;
+}
+
+int m3g_readout_fwd_bwd(const float* x, const float* W0dT, const float* b0d, const float* W1dT, const float* b1d,
+                        const float* w2d, const float* b2d, const float* W0gT, const float* b0g, const float* W1gT,
+                        const float* b1g, const float* w2g, const float* b2g, const float* W0d, const float* W1d,
+                        const float* W0g, const float* W1g, const float* elemental, const float* g_total,
+                        const int32_t* batch, float scale, int64_t N, int F, float* atomic, float* g_x, void* stream) {
+  if (N == 0) return M3G_OK;
+  M3G_REQUIRE(x && W0dT && b0d && W1dT && b1d && w2d && b2d && W0gT && b0g && W1gT && b1g && w2g && b2g && W0d &&
+                  W1d && W0g && W1g && elemental && g_total && batch && atomic && g_x,
+              "m3g_readout_fwd_bwd: null pointer");
+  M3G_REQUIRE(F >= 1 && F <= M3G_MAX_F, "m3g_readout_fwd_bwd: F=%d outside [1,%d]", F, M3G_MAX_F);
+  ReadoutW w{W0dT, b0d, W1dT, b1d, w2d, b2d, W0gT, b0g, W1gT, b1g, w2g, b2g, W0d, W1d, W0g, W1g};
+  launch_readout<true>(x, w, elemental, scale, nullptr, nullptr, g_total, batch, N, F, g_x, atomic, as_stream(stream));
+  M3G_LAUNCH_CHECK("m3g_readout_fwd_bwd");
   return M3G_OK;
 }
 

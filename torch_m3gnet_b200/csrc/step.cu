@@ -26,7 +26,7 @@ int prologue(M3GStepDesc* d, void* s) {
   if (d->tri_index && d->cos_t) M3G_TRY(m3g_angles_fwd(d->vec4, d->tri_index, d->T, d->cos_t, s));
   M3G_TRY(m3g_embed_fwd(d->embed_W, d->types, d->N, F, d->num_types, d->x0, s));
   M3G_TRY(m3g_radial_fwd(d->dist, d->radial_consts, d->E, R, d->h, s));
-  M3G_TRY(m3g_edge_adjust_fwd(d->h, d->adjust_Wt, d->E, R, F, d->e0, s));
+  if (!(d->fuse_e0 && d->tb_split)) M3G_TRY(m3g_edge_adjust_fwd(d->h, d->adjust_Wt, d->E, R, F, d->e0, s));
   for (int b = 0; b < d->n_blocks; ++b)
     if (d->blocks[b].radial_owner)
       M3G_TRY(m3g_tb_radial(d->vec4, d->blocks[b].tb_consts, d->E, L, R, d->member_edges, d->n_members, d->blocks[b].G,
@@ -43,7 +43,10 @@ int tb_fwd(M3GStepDesc* d, int b, void* s) {
   if (d->tb_split) {
     M3G_TRY(m3g_tb_mom_red(d->vec4, k.G, k.sig, d->dst, d->edge_ptr, d->tri_ptr, d->r3, d->N, d->max_members, d->n_sm,
                            k.red, s));
-    M3G_TRY(m3g_tb_edge_update(k.red, d->tri_ptr, k.WdT, k.WgT, k.e_in, d->E, d->n_sm, k.e_tb, s));
+    if (b == 0 && d->fuse_e0)
+      M3G_TRY(m3g_tb_edge_update_h(k.red, d->tri_ptr, k.WdT, k.WgT, d->h, d->adjust_Wt, d->E, d->n_sm, k.e_tb, s));
+    else
+      M3G_TRY(m3g_tb_edge_update(k.red, d->tri_ptr, k.WdT, k.WgT, k.e_in, d->E, d->n_sm, k.e_tb, s));
   } else {
     M3G_TRY(m3g_tb_mom_fwd(d->vec4, k.G, k.sig, d->dst, d->edge_ptr, d->tri_ptr, d->r3, k.WdT, k.WgT, k.e_in, d->N,
                            d->max_members, d->n_sm, k.red, k.e_tb, s));
@@ -66,13 +69,12 @@ int conv_fwd(M3GStepDesc* d, int b, void* s) {
 
 int readout(M3GStepDesc* d, void* s) {
   const float* x = d->blocks[d->n_blocks - 1].x_out;
-  M3G_TRY(m3g_readout_fwd(x, d->ro_W0dT, d->ro_b0d, d->ro_W1dT, d->ro_b1d, d->ro_w2d, d->ro_b2d, d->ro_W0gT, d->ro_b0g,
-                          d->ro_W1gT, d->ro_b1g, d->ro_w2g, d->ro_b2g, d->elemental, d->energy_scale, d->N, F,
-                          d->atomic, s));
+  // forward and adjoint in one launch: the upstream gradient g_total is an input of the step
+  M3G_TRY(m3g_readout_fwd_bwd(x, d->ro_W0dT, d->ro_b0d, d->ro_W1dT, d->ro_b1d, d->ro_w2d, d->ro_b2d, d->ro_W0gT,
+                              d->ro_b0g, d->ro_W1gT, d->ro_b1g, d->ro_w2g, d->ro_b2g, d->ro_W0d, d->ro_W1d, d->ro_W0g,
+                              d->ro_W1g, d->elemental, d->g_total, d->batch, d->energy_scale, d->N, F, d->atomic,
+                              d->g_x[0], s));
   M3G_TRY(m3g_structure_sum(d->atomic, d->atom_ptr, d->B, d->energy_scale, d->scaled_total, d->total, s));
-  M3G_TRY(m3g_readout_bwd(x, d->ro_W0dT, d->ro_b0d, d->ro_W1dT, d->ro_b1d, d->ro_w2d, d->ro_b2d, d->ro_W0gT, d->ro_b0g,
-                          d->ro_W1gT, d->ro_b1g, d->ro_w2g, d->ro_b2g, d->ro_W0d, d->ro_W1d, d->ro_W0g, d->ro_W1g,
-                          nullptr, nullptr, d->g_total, d->batch, d->energy_scale, d->N, F, d->g_x[0], s));
   d->cur_x = 0;
   d->cur_e = 0;
   d->have_g_e = 0;
@@ -110,8 +112,15 @@ int conv_bwd(M3GStepDesc* d, int b, void* s) {
 int tb_bwd(M3GStepDesc* d, int b, void* s) {
   M3GStepBlock& k = d->blocks[b];
   const bool need_x = b > 0;
-  M3G_TRY(m3g_tb_mom_bwd(d->vec4, k.G, k.dG, k.sig, d->dst, k.red, d->g_e[d->cur_e], d->edge_ptr, d->tri_ptr, d->r3,
-                         k.WdT, k.WgT, d->N, d->max_members, d->n_sm, b != d->n_blocks - 1, d->g_vec4, d->g_sig_e, s));
+  if (d->tb_bwd_split) {
+    // q = dL/dred overwrites this block's red (dead after this phase)
+    M3G_TRY(m3g_tb_mlp_adj(k.red, d->g_e[d->cur_e], d->member_edges, d->n_members, k.WdT, k.WgT, d->n_sm, k.red, s));
+    M3G_TRY(m3g_tb_mom_bwd_q(d->vec4, k.G, k.dG, k.sig, d->dst, k.red, d->edge_ptr, d->tri_ptr, d->r3, d->N,
+                             d->max_members, d->n_sm, b != d->n_blocks - 1, d->g_vec4, d->g_sig_e, s));
+  } else {
+    M3G_TRY(m3g_tb_mom_bwd(d->vec4, k.G, k.dG, k.sig, d->dst, k.red, d->g_e[d->cur_e], d->edge_ptr, d->tri_ptr, d->r3,
+                           k.WdT, k.WgT, d->N, d->max_members, d->n_sm, b != d->n_blocks - 1, d->g_vec4, d->g_sig_e, s));
+  }
   if (need_x) {
     M3G_TRY(m3g_tb_sigma64_bwd(d->g_sig_e, d->in_ptr, d->in_perm, k.sig, k.Ws, d->g_x[d->cur_x], d->N, d->n_sm,
                                d->g_x[d->cur_x ^ 1], s));

@@ -354,12 +354,22 @@ __global__ void __launch_bounds__(32 * MW, 8) tb_mom_red_kernel(
 // atom structure: a warp takes 32 consecutive rows at a time (member flags by ballot, the chunk's red rows staged in
 // shared memory for broadcast reads, 2 x 8 rows of e in flight per warp), lane = two feature columns (FFMA2).  This half
 // is bound by the 512 B per bond it has to move.
+// FROM_H (first block of the model, whole-step executor): the incoming rows are the EdgeAdjustor's output
+// e0 = SiLU(h Wa^T) (nn/featurizer.py:84-96), formed here from the 12-byte h row (same operation order as
+// edge_adjust_fwd4_kernel: bit-identical) instead of being written by one kernel and read back by this one.
 constexpr int UW = 8;  // warps per CTA
+template <bool FROM_H>
 __global__ void __launch_bounds__(32 * UW, 2) tb_edge_update_kernel(
     const float* __restrict__ red, const int32_t* __restrict__ tri_ptr, const float* __restrict__ WdT,
-    const float* __restrict__ WgT, const float* __restrict__ e_in, int64_t E, float* __restrict__ e_out) {
+    const float* __restrict__ WgT, const float* __restrict__ e_in, const float* __restrict__ h,
+    const float* __restrict__ WaT, int64_t E, float* __restrict__ e_out) {
   __shared__ __align__(16) float red_s[UW][32][12];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2 wa[3];
+  if (FROM_H) {
+#pragma unroll
+    for (int m = 0; m < 3; ++m) wa[m] = __ldg(reinterpret_cast<const float2*>(WaT + m * MF) + lane);
+  }
   float2 wd[MD], wg[MD];
 #pragma unroll
   for (int d = 0; d < MD; ++d) {
@@ -373,10 +383,27 @@ __global__ void __launch_bounds__(32 * UW, 2) tb_edge_update_kernel(
     const int64_t e0 = chunk << 5;
     const int rows = (int)min((int64_t)32, E - e0);
     float2 ra[RB], rb[RB];
+    float hv[3] = {0.f, 0.f, 0.f};
+    if (FROM_H && lane < rows) {
+#pragma unroll
+      for (int m = 0; m < 3; ++m) hv[m] = __ldg(h + (e0 + lane) * 3 + m);
+    }
     auto load_rows = [&](float2* row, int r0) {
 #pragma unroll
-      for (int i = 0; i < RB; ++i)
-        if (r0 + i < rows) row[i] = __ldg(reinterpret_cast<const float2*>(e_in + (e0 + r0 + i) * MF) + lane);
+      for (int i = 0; i < RB; ++i) {
+        if (FROM_H) {
+          float2 z = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int m = 0; m < 3; ++m) {
+            const float hm = __shfl_sync(FULL, hv[m], r0 + i);
+            z.x = fmaf(hm, wa[m].x, z.x);
+            z.y = fmaf(hm, wa[m].y, z.y);
+          }
+          row[i] = make_float2(z.x * sigmoid_m(z.x), z.y * sigmoid_m(z.y));
+        } else if (r0 + i < rows) {
+          row[i] = __ldg(reinterpret_cast<const float2*>(e_in + (e0 + r0 + i) * MF) + lane);
+        }
+      }
     };
     load_rows(ra, 0);
     load_rows(rb, RB);
@@ -428,7 +455,10 @@ __global__ void __launch_bounds__(32 * UW, 2) tb_edge_update_kernel(
 // ------------------------------------------------------------------------------------------------
 // backward: g_vec4 (E,4) = d/d(v, r) (zeros for non-member bonds; includes the fc' and the radial-basis chain through
 // dG) and g_sig_e (E,9) = per-bond gradient of sigma[dst] (zeros for non-member bonds)
-__global__ void __launch_bounds__(32 * MW, 4) tb_mom_bwd_kernel(
+// WITH_MLP = false (default, m3g_tb_mom_bwd_q): `red` already holds q = dL/dred (m3g_tb_mlp_adj, below) and the kernel
+// carries no weights: fewer registers, more warps per SM for the staging latency.
+template <bool WITH_MLP>
+__global__ void __launch_bounds__(32 * MW, WITH_MLP ? 4 : 5) tb_mom_bwd_kernel(
     const float4* __restrict__ vec4, const float* __restrict__ G, const float* __restrict__ dG,
     const float* __restrict__ sig, const int32_t* __restrict__ dst, const float* __restrict__ red,
     const float* __restrict__ g_e, const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ tri_ptr, float r3,
@@ -440,10 +470,12 @@ __global__ void __launch_bounds__(32 * MW, 4) tb_mom_bwd_kernel(
   float* mom = ent + cap * ES;
   const LaneRole role = lane_role(lane);
   float2 wd[MD], wg[MD];
+  if (WITH_MLP) {
 #pragma unroll
-  for (int d = 0; d < MD; ++d) {
-    wd[d] = __ldg(reinterpret_cast<const float2*>(WdT + d * MF) + lane);
-    wg[d] = __ldg(reinterpret_cast<const float2*>(WgT + d * MF) + lane);
+    for (int d = 0; d < MD; ++d) {
+      wd[d] = __ldg(reinterpret_cast<const float2*>(WdT + d * MF) + lane);
+      wg[d] = __ldg(reinterpret_cast<const float2*>(WgT + d * MF) + lane);
+    }
   }
   // reduce9 target of this lane: component 5 b4 + 3 b3 + 2 b2 + b1 (bits of the lane id), written by even lanes
   const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1;
@@ -520,15 +552,17 @@ __global__ void __launch_bounds__(32 * MW, 4) tb_mom_bwd_kernel(
         if (writer) en[wslot] = tot;
       }
     };
-    load_g(ga, 0);
-    load_g(gb2, GB);
-    for (int p0 = 0; p0 < n3; p0 += 2 * GB) {
-      process_g(ga, p0);
-      load_g(ga, p0 + 2 * GB);
-      process_g(gb2, p0 + GB);
-      load_g(gb2, p0 + 3 * GB);
+    if (WITH_MLP) {
+      load_g(ga, 0);
+      load_g(gb2, GB);
+      for (int p0 = 0; p0 < n3; p0 += 2 * GB) {
+        process_g(ga, p0);
+        load_g(ga, p0 + 2 * GB);
+        process_g(gb2, p0 + GB);
+        load_g(gb2, p0 + 3 * GB);
+      }
+      __syncwarp();
     }
-    __syncwarp();
     // ---- moments of b and of a (members ascending) ----
     accumulate_side<true, false>(ent, n3, O_B, role, mom);
     accumulate_side<true, true>(ent, n3, O_A, role, mom + M_SIDE);
@@ -583,6 +617,121 @@ __global__ void __launch_bounds__(32 * MW, 4) tb_mom_bwd_kernel(
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// The backward split in two (default), like the forward.  First half: the adjoint of the 9 -> 64 gated MLP over the
+// PACKED list of member bonds, q = dL/dred (E,9).  In the fused kernel above a lane owns two feature columns, so every
+// row pays a 12-shuffle butterfly for its nine sums (~130 issued instructions per row).  Here a LANE OWNS A ROW: its g_e
+// row comes out of a coalesced shared-memory staging tile, the weights are warp-uniform broadcast reads, two feature
+// columns are packed per FFMA2 / FMUL2 and the nine sums stay in registers (~70 instructions per row, no shuffles).
+// Accumulation order (stated): features ascending in two interleaved partial sums (even / odd columns), added at the end.
+// q may alias red (a lane reads its row before it writes it).
+constexpr int AW = 8;    // warps per CTA
+constexpr int GS = 68;   // staging row stride in floats: 16-byte aligned rows, conflict-free row-per-lane LDS.128
+
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(32 * AW, 2) tb_mlp_adj_kernel(
+    const float* red, const float* __restrict__ g_e, const int32_t* __restrict__ members, int64_t n_members,
+    const float* __restrict__ WdT, const float* __restrict__ WgT, float* q) {
+  extern __shared__ __align__(16) float smem_f[];
+  // weight table [column pair p][d]: (wd[d][2p], wd[d][2p+1], wg[d][2p], wg[d][2p+1])
+  float4* wtab = reinterpret_cast<float4*>(smem_f);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* gst = smem_f + 32 * MD * 4 + (size_t)warp * (32 * GS);
+  for (int i = threadIdx.x; i < 32 * MD; i += 32 * AW) {
+    const int p = i / MD, d = i - p * MD;
+    const float2 a = __ldg(reinterpret_cast<const float2*>(WdT + d * MF) + p);
+    const float2 b = __ldg(reinterpret_cast<const float2*>(WgT + d * MF) + p);
+    wtab[i] = make_float4(a.x, a.y, b.x, b.y);
+  }
+  __syncthreads();
+  const int64_t n_chunks = (n_members + 31) >> 5;
+  const int sub = lane >> 4, c16 = lane & 15;
+  const float2 one2 = make_float2(1.0f, 1.0f), mone2 = make_float2(-1.0f, -1.0f);
+  const float2 nl2e = make_float2(-1.4426950408889634f, -1.4426950408889634f);
+  for (int64_t chunk = (int64_t)blockIdx.x * AW + warp; chunk < n_chunks; chunk += (int64_t)gridDim.x * AW) {
+    const int64_t m0 = chunk << 5;
+    const int my_e = (m0 + lane < n_members) ? __ldg(members + m0 + lane) : -1;
+    // ---- this chunk's g_e rows -> staging tile (two rows per instruction, coalesced 256-byte rows) ----
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int er = __shfl_sync(FULL, my_e, 16 * h + 2 * i + sub);
+        v[i] = (er >= 0) ? __ldg(reinterpret_cast<const float4*>(g_e + (int64_t)er * MF) + c16)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(gst + (16 * h + 2 * i + sub) * GS + 4 * c16) = v[i];
+    }
+    // this lane's reduced features, duplicated for the packed scalar operand
+    float2 rd2[MD];
+#pragma unroll
+    for (int d = 0; d < MD; ++d) {
+      const float r = (my_e >= 0) ? red[(int64_t)my_e * MD + d] : 0.0f;
+      rd2[d] = make_float2(r, r);
+    }
+    __syncwarp();
+    float2 acc[MD];
+#pragma unroll
+    for (int d = 0; d < MD; ++d) acc[d] = make_float2(0.f, 0.f);
+    const float* grow = gst + lane * GS;
+#pragma unroll 1
+    for (int c = 0; c < 16; ++c) {
+      const float4 g4 = *reinterpret_cast<const float4*>(grow + 4 * c);
+#pragma unroll
+      for (int hp = 0; hp < 2; ++hp) {
+        const float2 ge = hp ? make_float2(g4.z, g4.w) : make_float2(g4.x, g4.y);
+        const float4* wt = wtab + (2 * c + hp) * MD;
+        float4 w[MD];
+        float2 zd = make_float2(0.f, 0.f), zg = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int d = 0; d < MD; ++d) {
+          w[d] = wt[d];
+          zd = fma2(rd2[d], make_float2(w[d].x, w[d].y), zd);
+          zg = fma2(rd2[d], make_float2(w[d].z, w[d].w), zg);
+        }
+        // su = sigmoid(zd), sg = sigmoid(zg) ; du = ge sg su (1 + zd (1 - su)) ; dg = ge (zd su) sg (1 - sg)
+        const float2 nd = mul2(zd, nl2e), ng = mul2(zg, nl2e);
+        const float2 dd = add2(make_float2(ex2_fast(nd.x), ex2_fast(nd.y)), one2);
+        const float2 dq = add2(make_float2(ex2_fast(ng.x), ex2_fast(ng.y)), one2);
+        const float2 su = make_float2(rcp_fast(dd.x), rcp_fast(dd.y));
+        const float2 sg = make_float2(rcp_fast(dq.x), rcp_fast(dq.y));
+        const float2 a = mul2(ge, mul2(su, sg));
+        const float2 du = mul2(a, fma2(zd, fma2(su, mone2, one2), one2));
+        const float2 dg = mul2(mul2(a, zd), fma2(sg, mone2, one2));
+#pragma unroll
+        for (int d = 0; d < MD; ++d) {
+          acc[d] = fma2(du, make_float2(w[d].x, w[d].y), acc[d]);
+          acc[d] = fma2(dg, make_float2(w[d].z, w[d].w), acc[d]);
+        }
+      }
+    }
+    if (my_e >= 0) {
+      float* qo = q + (int64_t)my_e * MD;
+#pragma unroll
+      for (int d = 0; d < MD; ++d) qo[d] = acc[d].x + acc[d].y;
+    }
+    __syncwarp();
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // sigma = sigmoid(x Ws^T + bs) for F = 64, D = 9 (nn/interaction.py:204-206) and its adjoint.  The generic kernels
@@ -760,9 +909,57 @@ int m3g_tb_edge_update(const float* red, const int32_t* tri_ptr, const float* Wd
   if (E == 0) return M3G_OK;
   M3G_REQUIRE(red && tri_ptr && WdT && WgT && e_in && e_out, "m3g_tb_edge_update: null pointer");
   const int64_t need = ((E + 31) / 32 + UW - 1) / UW, capb = (int64_t)n_sm * 2;
-  tb_edge_update_kernel<<<(unsigned)(need < capb ? need : capb), 32 * UW, 0, as_stream(stream)>>>(red, tri_ptr, WdT, WgT,
-                                                                                               e_in, E, e_out);
+  tb_edge_update_kernel<false><<<(unsigned)(need < capb ? need : capb), 32 * UW, 0, as_stream(stream)>>>(
+      red, tri_ptr, WdT, WgT, e_in, nullptr, nullptr, E, e_out);
   M3G_LAUNCH_CHECK("m3g_tb_edge_update");
+  return M3G_OK;
+}
+
+int m3g_tb_edge_update_h(const float* red, const int32_t* tri_ptr, const float* WdT, const float* WgT, const float* h,
+                         const float* WaT, int64_t E, int n_sm, float* e_out, void* stream) {
+  if (E == 0) return M3G_OK;
+  M3G_REQUIRE(red && tri_ptr && WdT && WgT && h && WaT && e_out, "m3g_tb_edge_update_h: null pointer");
+  const int64_t need = ((E + 31) / 32 + UW - 1) / UW, capb = (int64_t)n_sm * 2;
+  tb_edge_update_kernel<true><<<(unsigned)(need < capb ? need : capb), 32 * UW, 0, as_stream(stream)>>>(
+      red, tri_ptr, WdT, WgT, nullptr, h, WaT, E, e_out);
+  M3G_LAUNCH_CHECK("m3g_tb_edge_update_h");
+  return M3G_OK;
+}
+
+int m3g_tb_mlp_adj(const float* red, const float* g_e, const int32_t* member_edges, int64_t n_members, const float* WdT,
+                   const float* WgT, int n_sm, float* q, void* stream) {
+  if (n_members == 0) return M3G_OK;
+  M3G_REQUIRE(red && g_e && member_edges && WdT && WgT && q, "m3g_tb_mlp_adj: null pointer");
+  const size_t smem = (size_t)(32 * MD * 4 + AW * 32 * GS) * sizeof(float);
+  cudaError_t err = cudaFuncSetAttribute(tb_mlp_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) {
+    set_error("m3g_tb_mlp_adj: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+    return M3G_ERR_CUDA;
+  }
+  const int64_t need = ((n_members + 31) / 32 + AW - 1) / AW, capb = (int64_t)n_sm * 2;
+  tb_mlp_adj_kernel<<<(unsigned)(need < capb ? need : capb), 32 * AW, smem, as_stream(stream)>>>(
+      red, g_e, member_edges, n_members, WdT, WgT, q);
+  M3G_LAUNCH_CHECK("m3g_tb_mlp_adj");
+  return M3G_OK;
+}
+
+int m3g_tb_mom_bwd_q(const float* vec4, const float* G, const float* dG, const float* sig, const int32_t* dst,
+                     const float* q, const int32_t* edge_ptr, const int32_t* tri_ptr, float r3, int64_t N,
+                     int max_members, int n_sm, int accumulate, float* g_vec4, float* g_sig_e, void* stream) {
+  if (N == 0) return M3G_OK;
+  M3G_REQUIRE(vec4 && G && dG && sig && dst && q && edge_ptr && tri_ptr && g_vec4 && g_sig_e,
+              "m3g_tb_mom_bwd_q: null pointer");
+  M3G_REQUIRE(max_members >= 0 && max_members <= 128,
+              "m3g_tb_mom_bwd_q: %d member bonds per atom exceed the capacity 128", max_members);
+  const int cap = pick_cap(max_members);
+  const size_t smem = (size_t)MW * (cap * ES + 2 * M_SIDE) * sizeof(float);
+  unsigned grid;
+  int rc = mom_launch_shape(tb_mom_bwd_kernel<false>, smem, N, n_sm, true, &grid);
+  if (rc != M3G_OK) return rc;
+  tb_mom_bwd_kernel<false><<<grid, 32 * MW, smem, as_stream(stream)>>>(
+      (const float4*)vec4, G, dG, sig, dst, q, nullptr, edge_ptr, tri_ptr, r3, nullptr, nullptr, N, cap, accumulate,
+      (float4*)g_vec4, g_sig_e);
+  M3G_LAUNCH_CHECK("m3g_tb_mom_bwd_q");
   return M3G_OK;
 }
 
@@ -778,9 +975,9 @@ int m3g_tb_mom_bwd(const float* vec4, const float* G, const float* dG, const flo
   const int cap = pick_cap(max_members);
   const size_t smem = (size_t)MW * (cap * ES + 2 * M_SIDE) * sizeof(float);
   unsigned grid;
-  int rc = mom_launch_shape(tb_mom_bwd_kernel, smem, N, n_sm, true, &grid);
+  int rc = mom_launch_shape(tb_mom_bwd_kernel<true>, smem, N, n_sm, true, &grid);
   if (rc != M3G_OK) return rc;
-  tb_mom_bwd_kernel<<<grid, 32 * MW, smem, as_stream(stream)>>>((const float4*)vec4, G, dG, sig, dst, red, g_e, edge_ptr,
+  tb_mom_bwd_kernel<true><<<grid, 32 * MW, smem, as_stream(stream)>>>((const float4*)vec4, G, dG, sig, dst, red, g_e, edge_ptr,
                                                                tri_ptr, r3, WdT, WgT, N, cap, accumulate, (float4*)g_vec4, g_sig_e);
   M3G_LAUNCH_CHECK("m3g_tb_mom_bwd");
   return M3G_OK;

@@ -26,6 +26,8 @@ _fp = ctypes.c_void_p
 
 # set M3G_ENGINE=0 to force the per-operator (autograd) path
 ENABLED = os.environ.get("M3G_ENGINE", "1") != "0"
+# e0 = SiLU(h Wa^T) formed inside block 0's three-body edge update instead of being stored and read back
+FUSE_E0 = os.environ.get("M3G_FUSE_E0", "1") != "0"
 
 
 class _Block(ctypes.Structure):
@@ -52,7 +54,8 @@ class _Desc(ctypes.Structure):
                 + [("g_x", _fp * 2), ("g_e", _fp * 2)]
                 + [(n, _fp) for n in ("ge2", "gz_edge", "gz_node", "gP", "g_h", "g_h2", "g_sig_e", "g_vec4", "g_dist",
                                       "g_pos")]
-                + [(n, ctypes.c_int) for n in ("cur_x", "cur_e", "have_g_e", "msg_reduce", "tb_split")]
+                + [(n, ctypes.c_int) for n in ("cur_x", "cur_e", "have_g_e", "msg_reduce", "tb_split",
+                                               "tb_bwd_split", "fuse_e0")]
                 + [("blocks", _Block * MAX_BLOCKS)])
 
 
@@ -173,7 +176,7 @@ class StepEngine:
             K.SCALED_TOTAL_ENERGY: torch.empty(B, **f32), K.TOTAL_ENERGY: torch.empty(B, **f32),
             K.FORCES: torch.empty((N, 3), **f32), K.STRESSES: torch.empty((B, 6), **f32),
         }
-        n_save = ((E + 127) // 128) * 128 * 256
+        n_save = int(_lib.LIB.load().m3g_conv_tc_save_floats(E))
         # scratch: one allocation carved by offsets (floats, every piece 16-byte aligned)
         sizes: List = [("vec4", 4 * E), ("x0", 64 * N), ("e0", 64 * E), ("P", 512 * N), ("msg", 64 * E),
                        ("g_x0", 64 * N), ("g_x1", 64 * N), ("g_e0", 64 * E), ("g_e1", 64 * E), ("ge2", 64 * E),
@@ -207,6 +210,8 @@ class StepEngine:
         d.passes = 3 if conv_mod.CONV_PATH == "tc3" else 1
         d.msg_reduce = int(conv_mod.MSG_REDUCE)
         d.tb_split = int(interaction.TB_SPLIT)
+        d.tb_bwd_split = int(interaction.TB_BWD_SPLIT)
+        d.fuse_e0 = int(interaction.TB_SPLIT and FUSE_E0)
         d.n_members = int(plan.n_members)
         d.length_scale, d.energy_scale = float(self.scale.length_scale), float(self.readout.scale)
         d.r3 = float(weights[0][0]["r3"])
@@ -280,14 +285,15 @@ class StepEngine:
             raise RuntimeError(f"m3g_step_run failed ({rc}): {lib.m3g_last_error().decode()}")
 
     def launches(self, with_angles: bool = True) -> int:
-        """Kernel launches of one full step (for bench.py's gpu_launches): prologue 8 (+1 for the cos output) + one
-        radial table per distinct constant set, 6 per block forward, 3 for the readout and its adjoint, 7 per block
-        backward (3 for block 0, whose node-feature gradient is dead), 4 in the epilogue, 2 for forces + virial."""
+        """Kernel launches of one full step (for bench.py's gpu_launches): prologue 7 (6 when e0 is formed inside the first three-body edge update; +1 for the cos output) + one
+        radial table per distinct constant set, 6 per block forward, 2 for the readout with its adjoint, 7 per block
+        backward (3 for block 0, whose node-feature gradient is dead; +1 per block with the split three-body adjoint), 4 in the epilogue, 2 for forces + virial."""
         n = self.n_blocks
         tables = len({t._packed.get()["consts_key"] for t in self.tbs})
         from torch_m3gnet_b200.nn import interaction
 
-        return 8 + int(with_angles) + tables + (6 + int(interaction.TB_SPLIT)) * n + 3 + (7 * n - 4) + 4 + 2
+        return (7 - int(interaction.TB_SPLIT and FUSE_E0) + int(with_angles) + tables + (6 + int(interaction.TB_SPLIT)) * n + 2
+                + (7 * n - 4 + int(interaction.TB_BWD_SPLIT) * n) + 4 + 2)
 
     def run(self, graph, plan):
         desc, keep = self.prepare(graph, plan)

@@ -11,6 +11,7 @@ import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
+from torch_m3gnet_b200 import _lib
 from torch_m3gnet_b200._lib import call
 
 
@@ -222,8 +223,17 @@ class ThreeBodyFn(Function):
             G, dG = ctx.radial
             g_vec4 = torch.empty_like(vec4)
             g_sig_e = torch.empty_like(red)
-            call("tb_mom_bwd", vec4, G, dG, sig, plan.dst, red, g_e, plan.edge_ptr, plan.tri_ptr, w["r3"], w["WdT"],
-                 w["WgT"], N, plan.max_members, sm_count(vec4.device), 0, g_vec4, g_sig_e)
+            from torch_m3gnet_b200.nn import interaction
+
+            if interaction.TB_BWD_SPLIT:
+                q = torch.empty_like(red)  # rows of non-member bonds are never read
+                call("tb_mlp_adj", red, g_e, plan.member_edges, plan.n_members, w["WdT"], w["WgT"],
+                     sm_count(vec4.device), q)
+                call("tb_mom_bwd_q", vec4, G, dG, sig, plan.dst, q, plan.edge_ptr, plan.tri_ptr, w["r3"], N,
+                     plan.max_members, sm_count(vec4.device), 0, g_vec4, g_sig_e)
+            else:
+                call("tb_mom_bwd", vec4, G, dG, sig, plan.dst, red, g_e, plan.edge_ptr, plan.tri_ptr, w["r3"], w["WdT"],
+                     w["WgT"], N, plan.max_members, sm_count(vec4.device), 0, g_vec4, g_sig_e)
             g_x = _empty((N, F), vec4)
             call("tb_sigma64_bwd", g_sig_e, plan.in_ptr, plan.in_perm, sig, w["Ws"], None, N, sm_count(vec4.device), g_x)
             return g_x, g_e, g_vec4, None, None, None, None, None
@@ -278,7 +288,7 @@ class ConvFn(Function):
             n_sm = sm_count(x.device)
             if tc_bwd_variant() == 4 and R <= 3 and any(ctx.needs_input_grad[:3]):
                 # activations for the backward (1 KB per edge and MLP): SiLU'(z1) and the layer-2 pre-activations
-                n_save = ((E + 127) // 128) * 128 * 256
+                n_save = int(_lib.LIB.load().m3g_conv_tc_save_floats(E))
                 save_e, save_n = _empty((n_save,), x), _empty((n_save,), x)
             call("conv_tc_fwd", P, 8 * F, 0, plan.src, plan.dst, e, h, ed["wimg"], ed["b2d"], ed["b2g"], ed["WhT"], E, R,
                  0, passes, n_sm, e2, save_e)

@@ -23,6 +23,9 @@ RADIAL_CACHE = "_tb_radial"
 # moment path, forward: True (default) = per-atom moment kernel (red only) + a streaming edge-update kernel over all bond
 # rows; False = one fused per-atom kernel
 TB_SPLIT = os.environ.get("M3G_TB_SPLIT", "1") != "0"
+# moment path, backward: True (default) = gated-MLP adjoint over the packed member-bond list (a lane owns a row) + the
+# per-atom moment kernel reading q = dL/dred; False = one fused per-atom kernel
+TB_BWD_SPLIT = os.environ.get("M3G_TB_BWD_SPLIT", "1") != "0"
 
 __all__ = ["ThreeBodyInteration", "NormalizedSphericalBessel", "SPHERICAL_BESSEL_ZEROS", "spherical_bessel",
            "legendre_cos", "cutoff_function"]
