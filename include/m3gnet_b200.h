@@ -231,7 +231,8 @@ int m3g_tb_atom_bwd(const float* vec4, const float* bas, const float* red, const
  * and dG/dr for the listed member bonds.  m3g_tb_mom_fwd: red (member bonds) and e_out (all bonds) with bas = G *
  * sig[dst] formed in-kernel.  m3g_tb_mom_bwd: g_vec4 (E,4) complete (cos, fc' and radial chain; zeros for
  * non-members; accumulate != 0 adds to the existing rows: the sum over the model's blocks) and g_sig_e (E,9) (zeros for
- * non-members), ready for m3g_tb_sigma_bwd.  The Legendre adjoint follows
+ * non-members, written by the accumulate == 0 call: with accumulate != 0 both buffers must come from such a call on the
+ * same bond list), ready for m3g_tb_sigma_bwd.  The Legendre adjoint follows
  * the reference's quirk (Q3) through second-order moments.  max_members: upper bound of member bonds per atom. */
 int m3g_tb_radial(const float* vec4, const float* tb_consts, int64_t E, int L, int R, const int32_t* edge_list,
                   int64_t n_list, float* G, float* dG, void* stream);

@@ -2,6 +2,7 @@
 (library built with -DM3G_TC_TIMING; the recompute variant carries its own marks: M3G_TC_BWD_VARIANT=2).
 
   M3G_EXTRA_NVCC_FLAGS=-DM3G_TC_TIMING python -m torch_m3gnet_b200.csrc.build -f && python tools/tc_timing.py
+  (or keep the instrumented build beside the product library and point M3G_LIB_PATH at it)
 """
 import ctypes
 import os
@@ -22,7 +23,7 @@ def main():
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     model = m3g.build_model(**bench.HP, device=dev)
-    batch, _, _ = bench.build_inputs(dev, 0)
+    batch = bench.c2_workload(0).build(dev)
     for _ in range(2):
         model(batch)
     buf = (ctypes.c_int64 * 16)()

@@ -15,7 +15,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 HEADER = os.path.join(_ROOT, "include", "m3gnet_b200.h")
-LIB_PATH = os.path.join(_HERE, "lib", "libm3gnet_b200.so")
+# M3G_LIB_PATH: dev tools only (an instrumented build of the same sources, e.g. -DM3G_TC_TIMING for tools/tc_timing.py)
+LIB_PATH = os.environ.get("M3G_LIB_PATH") or os.path.join(_HERE, "lib", "libm3gnet_b200.so")
 
 _CTYPE = {
     "int": ctypes.c_int,

@@ -11,6 +11,8 @@
 // The backward kernel recomputes the forward GEMMs and runs the transposed products (dz2·W2, dz1·W1e) against
 // K-major images of the transposed weights that are staged per tile through a 32 KB buffer (tf32 operands
 // only admit the 32B-atom swizzle in MN-major form, so the forward images cannot be reused transposed).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -408,13 +410,14 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc4_fwd_kernel(ConvTcPara
       }
     }
     // P[dst] row pointers of the four rows this lane serves in the coalesced layout
-    const float* Pj[4];
+    // (32-bit float offsets into P: N * ldp < 2^31 is checked by the host entry; four registers instead of eight)
+    const float* Pb = p.P + p.po + 128 + 4 * cc4;
+    uint32_t Pj[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      Pj[i] = p.P + (int64_t)__shfl_sync(FULL, d_row, 8 * i + cr) * p.ldp + p.po + 128 + 4 * cc4;
+    for (int i = 0; i < 4; ++i) Pj[i] = (uint32_t)__shfl_sync(FULL, d_row, 8 * i + cr) * (uint32_t)p.ldp;
     float4 pj[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pj[i] = __ldg(reinterpret_cast<const float4*>(Pj[i] + c0));
+    for (int i = 0; i < 4; ++i) pj[i] = __ldg(reinterpret_cast<const float4*>(Pb + Pj[i] + c0));
     // ---- X hand-off: the other group's latest GEMM1 must have consumed X ----
     if (grp == 1) mbar_wait_warp(g1_other, par);
     else if (it > 0) mbar_wait_warp(g1_other, par ^ 1);
@@ -441,7 +444,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc4_fwd_kernel(ConvTcPara
       if (sc < 3) {
         const int ncol = (((sc + 1) >> 1) << 6) + c0 + (((sc + 1) & 1) << 4);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) pj[i] = __ldg(reinterpret_cast<const float4*>(Pj[i] + ncol));
+        for (int i = 0; i < 4; ++i) pj[i] = __ldg(reinterpret_cast<const float4*>(Pb + Pj[i] + ncol));
       }
       float4 pi4[4];
 #pragma unroll
@@ -1065,6 +1068,12 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwd2_kernel(ConvTcBwd
 // here the forward leaves SiLU'(z1) and z2 behind (1 KB per edge, fragment-major so that both sides use plain coalesced
 // float4 accesses) and the backward is just   output adjoint -> GEMM3d/3g -> dz1 -> GEMM4a/4b -> outputs:
 // two MMA sync points per tile, no forward weights, all four transposed weight image pairs resident in shared memory.
+// Measured alternative (round 2, removed again): two tiles in flight with two groups of 8 warps and 256 tensor-memory
+// columns per tile (one operand region refilled before each of four 64x64 GEMMs, dz2g parked in the idle D3g columns,
+// D4 aliasing D3d, the four MMA batches issued by four different warps) — bit-identical g_e / g_z1, 0.651 vs 0.638 ms
+// per launch at C2: the chain of one tile is not what bounds the kernel (tools/tc_timing.py: loads 2.5 k + 1.6 k, math
+// 3.7 k, MMA issue 3.3 k + 3.2 k, stores 2.0 k of 18.4 k cycles per tile), the memory system's response to its six
+// concurrent row streams is (ncu: long-scoreboard is the top stall, DRAM 60 %, no pipe above 50 %).
 // TMEM columns: A [0,64)|[64,128) hi|lo, A2 [128,192)|[192,256), D3d [256,320), D3g [320,384), D4 [384,448).
 struct ConvTcBwdSParams {
   const int32_t* src; const float* h;

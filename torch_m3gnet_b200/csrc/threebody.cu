@@ -454,22 +454,43 @@ __device__ __forceinline__ void sincos_bounded(float x, float* sn, float* cs) {
 
 // the same for l_max = n_max = 3 (the shape the moment kernels serve): one reciprocal per argument instead of a
 // division per recurrence step (results within 2 ulp of the generic kernel; x <= 1e-8 keeps the reference's branch)
-__global__ void tb_radial33_kernel(const float4* __restrict__ vec4, const float* __restrict__ consts, int64_t n_work,
-                                   const int32_t* __restrict__ edge_list, float* __restrict__ G,
-                                   float* __restrict__ dG) {
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_work) return;
+// per-block table in shared memory: z (9), z / r_c (9), 1 / factor (9), r_c, 1 / r_c, r3 — the IEEE divisions of uniform
+// data are done once per block by nine threads instead of nine times per bond; x = (z r) / r_c keeps the reference's
+// rounding through one Newton refinement of the quotient (q = z r; x0 = q inv; x = x0 + (q - x0 r_c) inv).
+// Stores: when the 32 bonds of a warp are consecutive rows (always for a dense member list), the 2 x 9 values per bond
+// go through a shared tile and leave as coalesced 128-byte lines instead of 18 scalar stores with a 36-byte stride.
+__global__ void __launch_bounds__(128) tb_radial33_kernel(const float4* __restrict__ vec4, const float* __restrict__ consts,
+                                                          int64_t n_work, const int32_t* __restrict__ edge_list,
+                                                          float* __restrict__ G, float* __restrict__ dG) {
+  __shared__ float tab[32];
+  __shared__ float tile[4][2][9 * 32 + 8];
+  if (threadIdx.x < 9) {
+    const float z = consts[threadIdx.x], rc = consts[18];
+    tab[threadIdx.x] = z;
+    tab[9 + threadIdx.x] = __fdiv_rn(z, rc);
+    tab[18 + threadIdx.x] = __frcp_rn(consts[9 + threadIdx.x]);
+  } else if (threadIdx.x == 9) {
+    tab[27] = consts[18];
+    tab[28] = __frcp_rn(consts[18]);
+    tab[29] = consts[19];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n_work;
+  int64_t e = live ? i : n_work - 1;
   if (edge_list) e = edge_list[e];
   const float r = vec4[e].w;
-  const float rc = consts[18], r3 = consts[19];
+  const float rc = tab[27], inv_rc = tab[28], r3 = tab[29];
   const float c = cutoff_poly(r, r3);
   const float dc = cutoff_poly_grad(r, r3);
   float g[9], dg[9];
 #pragma unroll
   for (int d = 0; d < 9; ++d) {
     const int l = d / 3;
-    const float z = consts[d];
-    const float x = __fdiv_rn(__fmul_rn(z, r), rc);
+    const float q = __fmul_rn(tab[d], r);
+    const float x0 = q * inv_rc;
+    const float x = fmaf(fmaf(-x0, rc, q), inv_rc, x0);
     float j = 1.0f, dj = 0.0f;
     if (x > 1e-8f) {
       float sn, cs;
@@ -488,15 +509,36 @@ __global__ void tb_radial33_kernel(const float4* __restrict__ vec4, const float*
       if (l == 1) { j = jl[1]; dj = djl[1]; }
       if (l == 2) { j = jl[2]; dj = djl[2]; }
     }
-    const float ifac = __frcp_rn(consts[9 + d]);
-    const float chi = j * ifac, dchi = dj * (z / rc) * ifac;
-    g[d] = chi * c;
-    dg[d] = dchi * c + chi * dc;
+    const float ifac = tab[18 + d];
+    const float chi = j * ifac, dchi = dj * tab[9 + d] * ifac;
+    g[d] = (c != 0.0f) ? chi * c : 0.0f;
+    dg[d] = (c != 0.0f) ? dchi * c + chi * dc : 0.0f;
   }
+  // consecutive rows in this warp?
+  const int64_t e_first = __shfl_sync(FULL, e, 0);
+  const bool dense = __all_sync(FULL, live && e == e_first + lane);
+  if (dense) {
+    float* tg = tile[warp][0];
+    float* td = tile[warp][1];
 #pragma unroll
-  for (int d = 0; d < 9; ++d) {
-    G[e * 9 + d] = (c != 0.0f) ? g[d] : 0.0f;
-    dG[e * 9 + d] = (c != 0.0f) ? dg[d] : 0.0f;
+    for (int d = 0; d < 9; ++d) {  // bank (9 lane + d) mod 32: conflict-free
+      tg[lane * 9 + d] = g[d];
+      td[lane * 9 + d] = dg[d];
+    }
+    __syncwarp();
+    float* Go = G + e_first * 9;
+    float* Do = dG + e_first * 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      Go[32 * k + lane] = tg[32 * k + lane];
+      Do[32 * k + lane] = td[32 * k + lane];
+    }
+  } else if (live) {
+#pragma unroll
+    for (int d = 0; d < 9; ++d) {
+      G[e * 9 + d] = g[d];
+      dG[e * 9 + d] = dg[d];
+    }
   }
 }
 

@@ -165,6 +165,8 @@ class StepEngine:
         lat = (lat if lat.dim() == 3 else lat[None]).contiguous()
         dev = pos.device
         N, E, T, B, n = plan.N, plan.E, plan.T, plan.B, self.n_blocks
+        if N * 512 >= 2 ** 32:
+            raise ValueError(f"{N} atoms: the per-atom projection table exceeds the kernels' 32-bit row offsets")
         f32 = dict(dtype=torch.float32, device=dev)
         tri_index = graph[K.TRIPLET_EDGE_INDEX]
         out = {

@@ -283,6 +283,8 @@ class ConvFn(Function):
         path = conv_path()
         save_e = save_n = None
         parts = False
+        if N * 8 * F >= 2 ** 32:
+            raise ValueError(f"{N} atoms: the per-atom projection table exceeds the kernels' 32-bit row offsets")
         if F == 64 and "wimg" in ed and path in ("tc3", "tc1") and R <= 4:
             passes = 3 if path == "tc3" else 1
             n_sm = sm_count(x.device)
