@@ -226,49 +226,12 @@ struct ConvTcParams {
 // private to the kernel pair and "fragment-major": a thread's 16-column slice of its row is four float4 that land,
 // together with the other 31 rows of the warp, in four fully coalesced 512-byte segments:
 //   [tile][block 4][16-column chunk 4][row quadrant 4][float4 index 4][row in quadrant 32][4 floats]
-//
-// M3G_SAVE24 (compile-time experiment, off: measured on B200 the forward grows 0.455 -> 0.515 ms per launch from the
-// packing work and its 12 narrower stores per sub-chunk while the backward only gains 0.638 -> 0.629 ms, so the byte cut
-// costs more than it saves): blocks 0 and 1 kept as 24-bit fixed point.  SiLU'(z) lies in (-0.0998, 1.0998), so
-// u = rint((g + 1/8) 2^24 / 1.25) fits 24 bits with an absolute error <= 5.6e-8 — the level of fp32 rounding for values of
-// that size and below the error of the fast exp / division that produce g.  16 values = 12 words per thread, stored
-// word-major so that every warp store is one coalesced 128-byte line:
-//   [tile][block 2][chunk 4][quadrant 4][float4 index 4][word 3][row in quadrant 32]     (384 words instead of 512)
-// 896 B per edge and MLP instead of 1 KB: -128 B written by the forward and read by the backward.
-#ifndef M3G_SAVE24
-#define M3G_SAVE24 0
-#endif
-#if M3G_SAVE24
-constexpr int SAVE_G_WORDS = 384;                          // per (block < 2, chunk, quadrant)
-#else
-constexpr int SAVE_G_WORDS = 512;
-#endif
-constexpr int SAVE_G_TILE = 2 * 16 * SAVE_G_WORDS;         // blocks 0, 1 of one tile
-constexpr int SAVE_TILE_WORDS = SAVE_G_TILE + 2 * 16 * 512;  // + blocks 2, 3 (fp32)
+// Measured alternative (round 2, removed again): SiLU'(z1) kept as 24-bit fixed point (absolute error <= 5.6e-8, 896
+// instead of 1024 B per edge): the packing work and its narrower stores cost the forward 0.455 -> 0.515 ms per launch
+// (part of it register spills) while the backward only gained 0.638 -> 0.629 ms.
+constexpr int SAVE_TILE_WORDS = TILE_M * 256;
 __device__ __forceinline__ int64_t save_offset(int64_t tile, int block, int chunk, int quadrant) {
-#if M3G_SAVE24
-  if (block < 2) return tile * (int64_t)SAVE_TILE_WORDS + ((block * 4 + chunk) * 4 + quadrant) * SAVE_G_WORDS;
-  return tile * (int64_t)SAVE_TILE_WORDS + SAVE_G_TILE + ((((block - 2) * 4 + chunk) * 4 + quadrant) << 9);
-#else
-  return tile * (int64_t)(TILE_M * 256) + (((block * 4 + chunk) * 4 + quadrant) << 9);
-#endif
-}
-constexpr float SAVE24_SCALE = 13421772.8f;               // 2^24 / 1.25
-constexpr float SAVE24_STEP = 7.450580596923828e-08f;     // 1.25 / 2^24 (exact)
-__device__ __forceinline__ uint32_t save24_q(float g) { return __float2uint_rn(fmaf(g, SAVE24_SCALE, 0.125f * SAVE24_SCALE)); }
-__device__ __forceinline__ float save24_d(uint32_t u) { return fmaf(__uint2float_rn(u), SAVE24_STEP, -0.125f); }
-// four 24-bit values <-> three words
-__device__ __forceinline__ void save24_pack(const float* g, uint32_t* w) {
-  const uint32_t u0 = save24_q(g[0]), u1 = save24_q(g[1]), u2 = save24_q(g[2]), u3 = save24_q(g[3]);
-  w[0] = u0 | (u1 << 24);
-  w[1] = (u1 >> 8) | (u2 << 16);
-  w[2] = (u2 >> 16) | (u3 << 8);
-}
-__device__ __forceinline__ void save24_unpack(uint32_t w0, uint32_t w1, uint32_t w2, float* g) {
-  g[0] = save24_d(w0 & 0xffffffu);
-  g[1] = save24_d(__funnelshift_r(w0, w1, 24) & 0xffffffu);
-  g[2] = save24_d(__funnelshift_r(w1, w2, 16) & 0xffffffu);
-  g[3] = save24_d(w2 >> 8);
+  return tile * (int64_t)SAVE_TILE_WORDS + (((block * 4 + chunk) * 4 + quadrant) << 9);
 }
 
 constexpr int SMEM_W_BYTES = WIMG_FLOATS * 4;         // 131072
@@ -380,6 +343,15 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc4_fwd_kernel(ConvTcPara
   const int64_t n_tiles = (p.E + TILE_M - 1) / TILE_M;
   const int64_t per_iter = 2 * (int64_t)gridDim.x;
   const int64_t n_iter = (n_tiles + per_iter - 1) / per_iter;
+  // this row's bond indices, loaded one tile ahead: P[src] / P[dst] gathers no longer start behind an index load
+  int d_next = 0, s_next = 0;
+  {
+    const int64_t t0 = (int64_t)blockIdx.x * 2 + grp;
+    if (t0 < n_tiles) {
+      d_next = __ldg(p.dst + min(t0 * TILE_M + row, p.E - 1));
+      s_next = __ldg(p.src + min(t0 * TILE_M + row, p.E - 1));
+    }
+  }
   for (int64_t it = 0; it < n_iter; ++it) {
     const int64_t tile = (it * gridDim.x + blockIdx.x) * 2 + grp;
     if (tile >= n_tiles) break;  // tiles are dealt A,B,A,B,...: the other group never waits on a tile that is absent
@@ -394,8 +366,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc4_fwd_kernel(ConvTcPara
       ev[i] = __ldg(reinterpret_cast<const float4*>(p.e + eg_ * TC_F) + (idx & 15));
     }
     const int64_t eg = min(e0 + row, p.E - 1);
-    const int d_row = __ldg(p.dst + eg);
-    const int s_atom = __ldg(p.src + eg);
+    const int d_row = d_next;
+    const int s_atom = s_next;
+    if (tile + per_iter < n_tiles) {
+      const int64_t en_ = min((tile + per_iter) * TILE_M + row, p.E - 1);
+      d_next = __ldg(p.dst + en_);
+      s_next = __ldg(p.src + en_);
+    }
     const float* Pi = p.P + (int64_t)s_atom * p.ldp + p.po;
     // mode 2: source atom of every row of this warp's 32-row block (-1 past the end), for the segmented message sum
     const int s_row = (e0 + row < p.E) ? s_atom : -1;
@@ -457,12 +434,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc4_fwd_kernel(ConvTcPara
       float v[16];
       tmem_ld16(t_lane + D1 + col, v);
       tmem_ld_wait();
-#if M3G_SAVE24
-      uint32_t* sv = p.save ? reinterpret_cast<uint32_t*>(p.save) + save_offset(tile, sc >> 1, 2 * hsel + (sc & 1), q) + lane
-                            : nullptr;
-#else
       float* sv = p.save ? p.save + save_offset(tile, sc >> 1, 2 * hsel + (sc & 1), q) + 4 * lane : nullptr;
-#endif
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float4 b = lds128(stg + stg_off(lane, c));
@@ -475,17 +447,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc4_fwd_kernel(ConvTcPara
           act[16 * (sc & 1) + 4 * c + u] = z[u] * sg;
           g[u] = sg * (1.0f + z[u] * (1.0f - sg));  // SiLU'(z1), kept for the backward pass
         }
-#if M3G_SAVE24
-        if (sv) {
-          uint32_t w[3];
-          save24_pack(g, w);
-          sv[(3 * c) * 32] = w[0];
-          sv[(3 * c + 1) * 32] = w[1];
-          sv[(3 * c + 2) * 32] = w[2];
-        }
-#else
         if (sv) *reinterpret_cast<float4*>(sv + 128 * c) = make_float4(g[0], g[1], g[2], g[3]);
-#endif
       }
       __syncwarp();
       if (sc == 1) {
@@ -1135,6 +1097,11 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
     bulk_g2s(z2buf, p.save + save_offset(blockIdx.x, 2, 0, 0), SMEM_Z2_BYTES, zb);
   }
   uint32_t par = 0;
+  // mode 1 (g_up indexed by source atom): the row's source index is loaded one tile ahead — ncu showed the dependent
+  // chain src[row] -> g_up[src] (a cold 512-byte line per tile, then the gather) as the largest single stall of the
+  // node-MLP launches
+  int s_cur = 0;
+  if (p.mode != 0 && (int64_t)blockIdx.x < n_tiles) s_cur = __ldg(p.src + min((int64_t)blockIdx.x * TILE_M + row, p.E - 1));
 #ifdef M3G_TC_TIMING
   long long tct_prev = clock64();
 #endif
@@ -1143,6 +1110,8 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
     const int64_t e0 = tile * TILE_M;
     const int64_t eg = min(e0 + row, p.E - 1);
     const bool live = (e0 + row) < p.E;
+    const int s_row = s_cur;
+    if (p.mode != 0 && tile + gridDim.x < n_tiles) s_cur = __ldg(p.src + min((tile + gridDim.x) * TILE_M + row, p.E - 1));
     int64_t erow[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) erow[i] = e0 + 32 * q + 8 * i + cr;
@@ -1151,7 +1120,7 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
       const int64_t tn = tile + gridDim.x;
       if (tn < n_tiles) {
         const float* sv = p.save + tn * (int64_t)SAVE_TILE_WORDS;
-        if (tid * 32 < SAVE_G_TILE) prefetch_l2(sv + tid * 32);  // blocks 0, 1 (SiLU'(z1)); blocks 2, 3 arrive by bulk copy
+        prefetch_l2(sv + tid * 32);  // blocks 0, 1 (SiLU'(z1)); blocks 2, 3 arrive by bulk copy
         const int64_t en = tn * TILE_M;
         const int64_t rn = min(en + (tid & 255) / 2, p.E - 1);
         const int half = (tid & 1) * 32;
@@ -1192,7 +1161,7 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
       }
       __syncwarp();
     } else {
-      const float* gr = p.g_up + (int64_t)__ldg(p.src + eg) * TC_F + k0;
+      const float* gr = p.g_up + (int64_t)s_row * TC_F + k0;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float4 b = __ldg(reinterpret_cast<const float4*>(gr + 4 * c));
@@ -1267,21 +1236,6 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
     }
     // saved SiLU'(z1) slices (dense -> zd, gate -> zg), in flight while GEMM3 runs
     {
-#if M3G_SAVE24
-      const uint32_t* s0 = reinterpret_cast<const uint32_t*>(p.save) + save_offset(tile, 0, cs, q) + lane;
-      const uint32_t* s1 = reinterpret_cast<const uint32_t*>(p.save) + save_offset(tile, 1, cs, q) + lane;
-      uint32_t wa[12], wb[12];
-#pragma unroll
-      for (int j = 0; j < 12; ++j) {
-        wa[j] = __ldg(s0 + 32 * j);
-        wb[j] = __ldg(s1 + 32 * j);
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        save24_unpack(wa[3 * c], wa[3 * c + 1], wa[3 * c + 2], zd + 4 * c);
-        save24_unpack(wb[3 * c], wb[3 * c + 1], wb[3 * c + 2], zg + 4 * c);
-      }
-#else
       const float* s0 = p.save + save_offset(tile, 0, cs, q) + 4 * lane;
       const float* s1 = p.save + save_offset(tile, 1, cs, q) + 4 * lane;
 #pragma unroll
@@ -1291,7 +1245,6 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
         zd[4 * c] = a.x; zd[4 * c + 1] = a.y; zd[4 * c + 2] = a.z; zd[4 * c + 3] = a.w;
         zg[4 * c] = b.x; zg[4 * c + 1] = b.y; zg[4 * c + 2] = b.z; zg[4 * c + 3] = b.w;
       }
-#endif
     }
     TCT(5);
     // ---- T6: dz1 = D3 * SiLU'(z1) -> operands A (dense), A2 (gate) ; GEMM4a + GEMM4b ----
