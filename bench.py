@@ -368,8 +368,8 @@ TRAFFIC_KERNEL = {
     "tb_sigma_bwd": "tb_sigma_bwd_kernel<16>", "tb_radial": "tb_radial33_kernel",
     "tb_sigma64_fwd": "tb_sigma64_fwd_kernel", "tb_sigma64_bwd": "tb_sigma64_bwd_kernel",
     "segment_sum_parts": "segment_sum_parts_kernel", "tb_mom_red": "tb_mom_red_kernel",
-    "tb_edge_update": "tb_edge_update_kernel", "tb_mlp_adj": "tb_mlp_adj_kernel",
-    "tb_mom_bwd_q": "tb_mom_bwd_kernel<0>",
+    "tb_edge_update": "tb_edge_update_kernel<", "tb_mlp_adj": "tb_mlp_adj_kernel",
+    "tb_mom_bwd_q": "tb_mom_bwd_kernel<",
 }
 
 

@@ -118,15 +118,19 @@ int m3g_verlet_fill(const double* lattice, const double* cart, const int32_t* at
                     void* stream);
 /* per-atom member degree n3 -> num_triplet_i (N) int64 = n3(n3-1), num_triplet_ij (E) int32,
  * tri_count (E) = triplets whose first bond is e (n3-1 for member edges else 0), and member_list (E):
- * the member edges of atom i compacted (ascending) at positions edge_ptr[i].. */
+ * the member edges of atom i compacted (ascending) at positions edge_ptr[i]..
+ * Optional (NULL to skip): used_count (N) = bonds of atom i that head a triplet (n3 if n3 >= 2 else 0) and
+ * stats int64[3], zeroed by the caller: += T, max n3, += sum of used_count — one read-back sizes tri_e2,
+ * the per-atom kernels' capacity and the member-bond list */
 int m3g_triplet_count(const int32_t* edge_ptr, const int32_t* member, int64_t N, int64_t E,
                       int64_t* num_triplet_i, int32_t* num_triplet_ij, int32_t* tri_count, int32_t* member_list,
-                      void* stream);
+                      int32_t* used_count, int64_t* stats, void* stream);
 /* tri_ptr = exclusive scan of tri_count.  Fills tri_e2 (T) int32 CSR columns and, if triplet_index != NULL,
- * the reference's (2,T) int64 list in the reference's order (atom, e1, e2) */
+ * the reference's (2,T) int64 list in the reference's order (atom, e1, e2).  Optional: member_edges = ascending
+ * list of the bonds that head a triplet, written at used_ptr (N+1) = exclusive scan of used_count */
 int m3g_triplet_fill(const int32_t* edge_ptr, const int32_t* tri_ptr, const int32_t* tri_count,
                      const int32_t* member_list, int64_t N, int64_t T, int32_t* tri_e2, int64_t* triplet_index,
-                     void* stream);
+                     const int32_t* used_ptr, int32_t* member_edges, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Geometry + bases

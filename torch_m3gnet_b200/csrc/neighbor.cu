@@ -362,10 +362,14 @@ verlet_kernel(const double* __restrict__ lattice, const double* __restrict__ car
 }
 
 // one warp per atom: member degree, per-edge triplet counts, compacted member list (ascending edge id)
+// used_count / stats (optional): bonds of atom i that head at least one triplet (n3 if n3 >= 2 else 0), and the totals
+// the host needs to size the next buffers — stats[0] += n3 (n3 - 1) (= T), stats[1] = max n3, stats[2] += used_count —
+// so that ONE read-back replaces three (integer atomics: order-independent)
 __global__ void triplet_count_kernel(const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ member,
                                      int64_t N, int64_t* __restrict__ num_triplet_i,
                                      int32_t* __restrict__ num_triplet_ij, int32_t* __restrict__ tri_count,
-                                     int32_t* __restrict__ member_list) {
+                                     int32_t* __restrict__ member_list, int32_t* __restrict__ used_count,
+                                     unsigned long long* __restrict__ stats) {
   int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (i >= N) return;
@@ -383,7 +387,15 @@ __global__ void triplet_count_kernel(const int32_t* __restrict__ edge_ptr, const
     num_triplet_ij[e] = v;
     tri_count[e] = v;
   }
-  if (lane == 0) num_triplet_i[i] = (int64_t)n3 * (n3 - 1);
+  if (lane == 0) {
+    num_triplet_i[i] = (int64_t)n3 * (n3 - 1);
+    if (used_count) used_count[i] = (n3 >= 2) ? n3 : 0;
+    if (stats && n3 >= 2) {
+      atomicAdd(stats, (unsigned long long)n3 * (unsigned long long)(n3 - 1));
+      atomicMax(stats + 1, (unsigned long long)n3);
+      atomicAdd(stats + 2, (unsigned long long)n3);
+    }
+  }
 }
 
 // one warp per atom: the n3(n3-1) ordered pairs of member edges, ordered by (e1, e2) — the exact order of
@@ -391,7 +403,8 @@ __global__ void triplet_count_kernel(const int32_t* __restrict__ edge_ptr, const
 __global__ void triplet_fill_kernel(const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ tri_ptr,
                                     const int32_t* __restrict__ tri_count, const int32_t* __restrict__ member_list,
                                     int64_t N, int64_t T, int32_t* __restrict__ tri_e2,
-                                    int64_t* __restrict__ triplet_index) {
+                                    int64_t* __restrict__ triplet_index, const int32_t* __restrict__ used_ptr,
+                                    int32_t* __restrict__ member_edges) {
   int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (i >= N) return;
@@ -409,6 +422,9 @@ __global__ void triplet_fill_kernel(const int32_t* __restrict__ edge_ptr, const 
   for (int o = 16; o > 0; o >>= 1) n3m1 = max(n3m1, __shfl_xor_sync(FULL, n3m1, o));
   if (n3m1 <= 0) return;  // 0 or 1 member edges: no triplets
   int n3 = n3m1 + 1;
+  // the global list of bonds that head a triplet (ascending: atoms ascending, members ascending per atom)
+  if (member_edges)
+    for (int k = lane; k < n3; k += 32) member_edges[used_ptr[i] + k] = member_list[b + k];
   int64_t base = tri_ptr[first];
   int total = n3 * n3m1;
   for (int t = lane; t < total; t += 32) {
@@ -522,24 +538,27 @@ int m3g_verlet_fill(const double* lattice, const double* cart, const int32_t* at
 }
 
 int m3g_triplet_count(const int32_t* edge_ptr, const int32_t* member, int64_t N, int64_t E, int64_t* num_triplet_i,
-                      int32_t* num_triplet_ij, int32_t* tri_count, int32_t* member_list, void* stream) {
+                      int32_t* num_triplet_ij, int32_t* tri_count, int32_t* member_list, int32_t* used_count,
+                      int64_t* stats, void* stream) {
   (void)E;
   if (N == 0) return M3G_OK;
   M3G_REQUIRE(edge_ptr && member && num_triplet_i && num_triplet_ij && tri_count && member_list,
               "m3g_triplet_count: null pointer");
-  triplet_count_kernel<<<blocks_for(N * 32, 256), 256, 0, as_stream(stream)>>>(edge_ptr, member, N, num_triplet_i,
-                                                                               num_triplet_ij, tri_count, member_list);
+  triplet_count_kernel<<<blocks_for(N * 32, 256), 256, 0, as_stream(stream)>>>(
+      edge_ptr, member, N, num_triplet_i, num_triplet_ij, tri_count, member_list, used_count,
+      reinterpret_cast<unsigned long long*>(stats));
   M3G_LAUNCH_CHECK("m3g_triplet_count");
   return M3G_OK;
 }
 
 int m3g_triplet_fill(const int32_t* edge_ptr, const int32_t* tri_ptr, const int32_t* tri_count,
                      const int32_t* member_list, int64_t N, int64_t T, int32_t* tri_e2, int64_t* triplet_index,
-                     void* stream) {
+                     const int32_t* used_ptr, int32_t* member_edges, void* stream) {
   if (N == 0 || T == 0) return M3G_OK;
   M3G_REQUIRE(edge_ptr && tri_ptr && tri_count && member_list && tri_e2, "m3g_triplet_fill: null pointer");
-  triplet_fill_kernel<<<blocks_for(N * 32, 256), 256, 0, as_stream(stream)>>>(edge_ptr, tri_ptr, tri_count,
-                                                                              member_list, N, T, tri_e2, triplet_index);
+  M3G_REQUIRE(!member_edges || used_ptr, "m3g_triplet_fill: member_edges needs used_ptr");
+  triplet_fill_kernel<<<blocks_for(N * 32, 256), 256, 0, as_stream(stream)>>>(
+      edge_ptr, tri_ptr, tri_count, member_list, N, T, tri_e2, triplet_index, used_ptr, member_edges);
   M3G_LAUNCH_CHECK("m3g_triplet_fill");
   return M3G_OK;
 }

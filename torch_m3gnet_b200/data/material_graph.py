@@ -247,14 +247,22 @@ class Batch(MaterialGraph):
         ntij = torch.empty(E, **i32)
         tri_count = torch.empty(E, **i32)
         member_list = torch.empty(max(E, 1), **i32)
-        _lib.call("triplet_count", edge_ptr, member, N, E, nti, ntij, tri_count, member_list)
+        used_count = torch.empty(N, **i32)
+        stats = torch.zeros(3, dtype=torch.int64, device=device)
+        _lib.call("triplet_count", edge_ptr, member, N, E, nti, ntij, tri_count, member_list, used_count, stats)
         tri_ptr = torch.empty(E + 1, **i32)
         work = torch.empty(_lib.scan_work_elems(E), **i32)
         _lib.call("exclusive_scan_i32", tri_count, tri_ptr, E, work)
-        T = int(tri_ptr[-1].item())
+        used_ptr = torch.empty(N + 1, **i32)
+        work_n = torch.empty(_lib.scan_work_elems(N), **i32)
+        _lib.call("exclusive_scan_i32", used_count, used_ptr, N, work_n)
+        # one read-back: triplet count, largest member degree, number of bonds that head a triplet
+        T, max_n3, n_used = (int(v) for v in stats.tolist())
         tri_e2 = torch.empty(T, **i32)
         tri_index = torch.empty((2, T), dtype=torch.int64, device=device) if want_triplet_index else None
-        _lib.call("triplet_fill", edge_ptr, tri_ptr, tri_count, member_list, N, T, tri_e2, tri_index)
+        member_edges = torch.empty(n_used, **i32)
+        _lib.call("triplet_fill", edge_ptr, tri_ptr, tri_count, member_list, N, T, tri_e2, tri_index, used_ptr,
+                  member_edges)
         g = cls(
             pos=cart64.to(torch.float32), atom_types=types,
             num_triplet_i=nti, edge_index=edge_index, edge_cell_shift=shift, num_triplet_ij=ntij,
@@ -265,10 +273,9 @@ class Batch(MaterialGraph):
         g._private["edge_distances_build"] = dist
         # the builder already holds the canonical CSR: seed the plan so the model does not re-derive it
         # the builder emits the full off-diagonal pair matrix of every atom's member bonds (the canonical dense layout),
-        # so the plan needs no layout check; the largest member count follows from max n3(n3-1)
-        m = int(nti.max().item()) if N > 0 else 0
-        max_members = 0 if m == 0 else int(round((1.0 + (1.0 + 4.0 * m) ** 0.5) / 2.0))
-        plan = GraphPlan.from_builder(g, atom_ptr, edge_ptr, tri_ptr, tri_e2, max_members=max_members)
+        # so the plan needs no layout check; the largest member count and the member-bond list come from the builder
+        plan = GraphPlan.from_builder(g, atom_ptr, edge_ptr, tri_ptr, tri_e2, max_members=max_n3,
+                                      member_edges=member_edges)
         plan._type_range = type_range
         object.__setattr__(g, "_plan", plan)
         return g
@@ -305,7 +312,8 @@ class Batch(MaterialGraph):
             atom_ptr = torch.as_tensor(atom_ptr_h).to(device)
             edge_ptr, E, edge_index, shift, dist, member = cls._sweep(lattices, lat64, cart64, atom_ptr, B, N, cutoff,
                                                                       threebody_cutoff, device)
-            batch = torch.repeat_interleave(torch.arange(B, device=device), torch.as_tensor(list(sizes), device=device))
+            batch = torch.repeat_interleave(torch.arange(B, device=device), torch.as_tensor(list(sizes), device=device),
+                                            output_size=N)  # (output_size: no read-back of the total)
             if torch.is_tensor(atomic_numbers):
                 z_h = atomic_numbers.reshape(-1)
                 types = (z_h.to(device=device, dtype=torch.int64, non_blocking=True) - 1)
@@ -388,7 +396,8 @@ class GraphPlan:
         return tuple(_sig(g._store.get(k)) for k in _STRUCTURAL)
 
     @classmethod
-    def from_builder(cls, g, atom_ptr, edge_ptr, tri_ptr, tri_e2, max_members: Optional[int] = None) -> "GraphPlan":
+    def from_builder(cls, g, atom_ptr, edge_ptr, tri_ptr, tri_e2, max_members: Optional[int] = None,
+                     member_edges: Optional[torch.Tensor] = None) -> "GraphPlan":
         p = cls()
         p._common(g)
         p.atom_ptr, p.edge_ptr = atom_ptr, edge_ptr
@@ -397,7 +406,7 @@ class GraphPlan:
         p.T = int(tri_e2.numel())  # also when the (2,T) int64 API list was not materialised
         p.trt_ptr, p.trt_e1 = tri_ptr, tri_e2  # builder output is the full off-diagonal: symmetric
         p.tri_symmetric = True
-        p._pick_group(dense_max_members=max_members)
+        p._pick_group(dense_max_members=max_members, member_edges=member_edges)
         p.signature = cls.signature_of(g)
         return p
 
@@ -432,15 +441,17 @@ class GraphPlan:
         work = torch.empty(self.N + 1 + _lib.scan_work_elems(self.N), **i32)
         _lib.call("csr_by_key", self.dst, self.E, self.N, self.in_ptr, self.in_perm, work)
 
-    def _pick_group(self, dense_max_members: Optional[int] = None):
+    def _pick_group(self, dense_max_members: Optional[int] = None, member_edges: Optional[torch.Tensor] = None):
         avg = self.T / max(self.E, 1)
         self.tri_group = 8 if avg <= 12 else (16 if avg <= 28 else 32)
         # bonds that are the first bond of at least one triplet ("member" bonds): the only ones whose Bessel basis
         # is ever read
-        used = self.tri_ptr[1:] > self.tri_ptr[:-1]
-        if self.trt_ptr is not self.tri_ptr:  # non-symmetric list: bonds that only occur as second bond count too
-            used = used | (self.trt_ptr[1:] > self.trt_ptr[:-1])
-        self.member_edges = torch.nonzero(used).flatten().to(torch.int32)
+        if member_edges is None:
+            used = self.tri_ptr[1:] > self.tri_ptr[:-1]
+            if self.trt_ptr is not self.tri_ptr:  # non-symmetric list: bonds that only occur as second bond count too
+                used = used | (self.trt_ptr[1:] > self.trt_ptr[:-1])
+            member_edges = torch.nonzero(used).flatten().to(torch.int32)
+        self.member_edges = member_edges  # (the builder hands over its own list: no compaction pass, no read-back)
         self.n_members = int(self.member_edges.numel())
         # canonical per-atom layout (full off-diagonal of the member-bond pair matrix)?  -> per-atom kernels
         if dense_max_members is not None:  # certified by the builder
