@@ -309,3 +309,80 @@ def test_graph_prep_kernels(device):
     assert flags[:2].tolist() == [0, 1]
     _lib.call("check_sorted", t, n, rows - 1000, flags)
     assert flags[1].item() == 0
+
+
+def test_fused_entry_points_equal_their_two_call_forms(device):
+    """The entry points the whole-step executor uses to fuse across operator boundaries give exactly what the two
+    separate calls give: readout forward + adjoint in one launch, and the first block's three-body edge update that forms
+    the EdgeAdjustor's output in-kernel (nn/featurizer.py:84-96 + nn/interaction.py:219-223)."""
+    from torch_m3gnet_b200 import _lib
+    from torch_m3gnet_b200.nn._functions import sm_count
+    from torch_m3gnet_b200.nn.readout import AtomWiseReadout
+
+    torch.manual_seed(11)
+    N, B, F = 1000, 7, 64
+    f32 = dict(dtype=torch.float32, device=device)
+    ro = AtomWiseReadout(F, 3, scale=1.7).to(device)
+    w = ro._packed.get()
+    x = 0.5 * torch.randn(N, F, **f32)
+    elemental = torch.randn(N, **f32)
+    batch = torch.sort(torch.randint(0, B, (N,), device=device)).values.to(torch.int32)
+    g_total = torch.rand(B, **f32) + 0.5
+    names = ("W0dT", "b0d", "W1dT", "b1d", "w2d", "b2d", "W0gT", "b0g", "W1gT", "b1g", "w2g", "b2g")
+    back = ("W0d", "W1d", "W0g", "W1g")
+    atomic_a, atomic_b = torch.empty(N, **f32), torch.empty(N, **f32)
+    gx_a, gx_b = torch.empty(N, F, **f32), torch.empty(N, F, **f32)
+    _lib.call("readout_fwd", x, *[w[k] for k in names], elemental, 1.7, N, F, atomic_a)
+    _lib.call("readout_bwd", x, *[w[k] for k in names], *[w[k] for k in back], None, None, g_total, batch, 1.7, N, F, gx_a)
+    _lib.call("readout_fwd_bwd", x, *[w[k] for k in names], *[w[k] for k in back], elemental, g_total, batch, 1.7, N, F,
+              atomic_b, gx_b)
+    assert torch.equal(atomic_a, atomic_b) and torch.equal(gx_a, gx_b)
+
+    # e_out = SiLU(h Wa^T) + gated(red): m3g_edge_adjust_fwd + m3g_tb_edge_update  ==  m3g_tb_edge_update_h
+    E = 4099  # not a multiple of 32: the last chunk is ragged
+    h = 0.3 * torch.randn(E, 3, **f32)
+    WaT = 0.4 * torch.randn(3, F, **f32)
+    WdT, WgT = 0.5 * torch.randn(9, F, **f32), 0.5 * torch.randn(9, F, **f32)
+    red = torch.randn(E, 9, **f32)
+    member = torch.rand(E, device=device) < 0.4
+    tri_ptr = torch.zeros(E + 1, dtype=torch.int32, device=device)
+    tri_ptr[1:] = torch.cumsum(member.to(torch.int32) * 3, 0)
+    e0 = torch.empty(E, F, **f32)
+    out_a, out_b = torch.empty(E, F, **f32), torch.empty(E, F, **f32)
+    _lib.call("edge_adjust_fwd", h, WaT, E, 3, F, e0)
+    _lib.call("tb_edge_update", red, tri_ptr, WdT, WgT, e0, E, sm_count(device), out_a)
+    _lib.call("tb_edge_update_h", red, tri_ptr, WdT, WgT, h, WaT, E, sm_count(device), out_b)
+    assert torch.equal(out_a, out_b)
+    # and the gated term itself against torch (member rows only)
+    z_d, z_g = red @ WdT, red @ WgT
+    want = e0 + torch.where(member[:, None], torch.nn.functional.silu(z_d) * torch.sigmoid(z_g), torch.zeros_like(z_d))
+    report("tb_edge_update vs torch", out_a, want, 2e-6, 2e-6)
+
+
+def test_threebody_mlp_adjoint_over_member_list(device):
+    """m3g_tb_mlp_adj (a lane per row over the packed member list, q may overwrite red) against torch autograd of the
+    gated 9 -> 64 MLP (nn/interaction.py:219-220, nn/core.py:61-62); rows outside the list are left untouched."""
+    from torch_m3gnet_b200 import _lib
+    from torch_m3gnet_b200.nn._functions import sm_count
+
+    torch.manual_seed(12)
+    f32 = dict(dtype=torch.float32, device=device)
+    for E, frac in ((4099, 0.4), (257, 1.0), (40, 0.5)):
+        F = 64
+        WdT, WgT = 0.5 * torch.randn(9, F, **f32), 0.5 * torch.randn(9, F, **f32)
+        red = torch.randn(E, 9, **f32)
+        g_e = torch.randn(E, F, **f32)
+        members = torch.nonzero(torch.rand(E, device=device) < frac).flatten().to(torch.int32)
+        r = red.clone().requires_grad_(True)
+        out = torch.nn.functional.silu(r @ WdT) * torch.sigmoid(r @ WgT)
+        (want,) = torch.autograd.grad(out, r, grad_outputs=g_e)
+        q = torch.full((E, 9), 7.0, **f32)
+        _lib.call("tb_mlp_adj", red, g_e, members, int(members.numel()), WdT, WgT, sm_count(device), q)
+        idx = members.long()
+        report(f"tb_mlp_adj E={E}", q[idx], want[idx], 2e-5, 5e-6)
+        rest = torch.ones(E, dtype=torch.bool, device=device)
+        rest[idx] = False
+        assert torch.all(q[rest] == 7.0)
+        alias = red.clone()
+        _lib.call("tb_mlp_adj", alias, g_e, members, int(members.numel()), WdT, WgT, sm_count(device), alias)
+        assert torch.equal(alias[idx], q[idx]) and torch.equal(alias[rest], red[rest])

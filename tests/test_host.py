@@ -27,6 +27,11 @@ def test_library_exports_every_declared_symbol():
     assert len(protos) >= 50
     cdll.m3g_abi_version.restype = ctypes.c_int
     assert cdll.m3g_abi_version() == 1
+    # pure host helpers can be called without a GPU: size of the saved-activation buffer (1 KB per bond, whole tiles)
+    cdll.m3g_conv_tc_save_floats.restype = ctypes.c_int64
+    cdll.m3g_conv_tc_save_floats.argtypes = [ctypes.c_int64]
+    assert cdll.m3g_conv_tc_save_floats(0) == 0
+    assert cdll.m3g_conv_tc_save_floats(1) == 128 * 256 and cdll.m3g_conv_tc_save_floats(129) == 2 * 128 * 256
 
 
 def test_no_cpu_fallback():
