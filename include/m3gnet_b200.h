@@ -303,6 +303,8 @@ int m3g_act_bwd(const float* in, const float* g, int64_t n, int kind, float* out
 int m3g_mul(const float* a, const float* b, int64_t n, float* out, void* stream);
 /* out = a + b (out may alias a or b) */
 int m3g_add(const float* a, const float* b, int64_t n, float* out, void* stream);
+/* out[i] = sum_k slices[k * n + i], k ascending */
+int m3g_sum_slices(const float* slices, int K, int64_t n, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * M3GNetConv (nn/conv.py:63-97, nn/core.py:6-62).  One "gated MLP on edges":
@@ -376,11 +378,13 @@ int m3g_conv_tc_fwd(const float* P, int ldp, int po, const int32_t* src, const i
  * save (optional): activations for m3g_conv_tc_bwd_saved — m3g_conv_tc_save_floats(E) floats (1 KB per edge:
  * SiLU'(z1) and the layer-2 pre-activations, in a tile-private fragment-major layout).  With them the backward needs
  * neither the forward weights nor P / e: output adjoint -> two 64x64 adjoint GEMM pairs -> g_e, g_z1, g_h (same outputs
- * and conventions as m3g_conv_tc_bwd; src is only read for mode 1, where g_up is indexed by source atom). */
+ * and conventions as m3g_conv_tc_bwd; src is only read for mode 1, where g_up is indexed by source atom).
+ * gh_store != 0: the g_h rows are stored instead of added to the rows already there (a caller that gives every launch
+ * its own (E,R) slice and sums them with m3g_sum_slices: no read-modify-write inside the kernel). */
 int64_t m3g_conv_tc_save_floats(int64_t E);
 int m3g_conv_tc_bwd_saved(const int32_t* src, const float* h, const float* wimgT, const float* WhT, const float* save,
                           const float* g_up, const float* g_e_base, int64_t E, int R, int mode, int passes, int n_sm,
-                          float* g_e, float* g_z1, float* g_h, void* stream);
+                          float* g_e, float* g_z1, float* g_h, int gh_store, void* stream);
 
 /* adjoint of m3g_conv_tc_fwd (same outputs as m3g_conv_mlp_bwd; forward recomputed on the tensor cores).
  * wimgT = [W2d^T hi|lo, W2g^T hi|lo, W1e_dense^T hi|lo, W1e_gate^T hi|lo]: four 64x64 image pairs from
@@ -501,7 +505,7 @@ typedef struct M3GStepDesc {
   float *g_x[2];                  /* (N,64) ping-pong; g_x[cur] holds the running adjoint */
   float *g_e[2], *ge2;            /* (E,64) */
   float *gz_edge, *gz_node, *gP;  /* (E,128) x 2, (N,512) */
-  float *g_h, *g_h2, *g_sig_e, *g_vec4, *g_dist, *g_pos; /* (E,3) x 2, (E,9), (E,4), (E), (N,3) */
+  float *g_h, *g_hs, *g_sig_e, *g_vec4, *g_dist, *g_pos; /* (E,3), (2 n_blocks + 1, E, 3) per-launch slices, (E,9), (E,4), (E), (N,3) */
   int cur_x, cur_e;               /* state carried between phases (updated by m3g_step_run) */
   int have_g_e;                   /* 0 until the first conv adjoint has produced g_e */
   int msg_reduce;                 /* 1: node MLP sums its messages per atom in-kernel (m3g_conv_tc_fwd mode 2) */

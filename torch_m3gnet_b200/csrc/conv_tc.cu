@@ -1030,6 +1030,9 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwd2_kernel(ConvTcBwd
 // here the forward leaves SiLU'(z1) and z2 behind (1 KB per edge, fragment-major so that both sides use plain coalesced
 // float4 accesses) and the backward is just   output adjoint -> GEMM3d/3g -> dz1 -> GEMM4a/4b -> outputs:
 // two MMA sync points per tile, no forward weights, all four transposed weight image pairs resident in shared memory.
+// Measured alternative (round 2, removed again): MMA batches issued by warps 15 / 14 (no g_h duty) instead of warp 0,
+// with the issuing warp's SiLU' loads put in flight before it starts issuing — 0.640 vs 0.627 ms: slower, although
+// the phase marks of warp 0 suggest that the issuing warp reaches both barriers ~2 k cycles after the others.
 // Measured alternative (round 2, removed again): two tiles in flight with two groups of 8 warps and 256 tensor-memory
 // columns per tile (one operand region refilled before each of four 64x64 GEMMs, dz2g parked in the idle D3g columns,
 // D4 aliasing D3d, the four MMA batches issued by four different warps) — bit-identical g_e / g_z1, 0.651 vs 0.638 ms
@@ -1044,6 +1047,7 @@ struct ConvTcBwdSParams {
   const float* g_up; const float* g_e_base;
   int64_t E; int R; int mode; int passes;
   float* g_e; float* g_z1; float* g_h;
+  int gh_store;  // 1: g_h rows are stored (the caller sums per-launch slices), 0: added to the rows already there
 };
 constexpr int SMEM_BS_MISC = TC_BWD_MAX_R * 64 * 4 + 32;  // Wh^T, 3 mbarriers, TMEM slot
 constexpr int SMEM_Z2_BYTES = 2 * 16 * 2048;           // blocks 2, 3 of one tile
@@ -1229,9 +1233,16 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
       if (live) {
         float tot[3] = {((ghp[0] + g1.x) + g2.x) + g3.x, ((ghp[1] + g1.y) + g2.y) + g3.y,
                         ((ghp[2] + g1.z) + g2.z) + g3.z};
+        // (store form: no read-modify-write round trip in the four warps every other warp waits for at the next barrier)
+        if (p.gh_store) {
 #pragma unroll
-        for (int m = 0; m < TC_BWD_MAX_R; ++m)
-          if (m < R) p.g_h[eg * R + m] += tot[m];
+          for (int m = 0; m < TC_BWD_MAX_R; ++m)
+            if (m < R) p.g_h[eg * R + m] = tot[m];
+        } else {
+#pragma unroll
+          for (int m = 0; m < TC_BWD_MAX_R; ++m)
+            if (m < R) p.g_h[eg * R + m] += tot[m];
+        }
       }
     }
     // saved SiLU'(z1) slices (dense -> zd, gate -> zg), in flight while GEMM3 runs
@@ -1552,7 +1563,7 @@ int m3g_conv_tc_fwd(const float* P, int ldp, int po, const int32_t* src, const i
 
 int m3g_conv_tc_bwd_saved(const int32_t* src, const float* h, const float* wimgT, const float* WhT, const float* save,
                           const float* g_up, const float* g_e_base, int64_t E, int R, int mode, int passes, int n_sm,
-                          float* g_e, float* g_z1, float* g_h, void* stream) {
+                          float* g_e, float* g_z1, float* g_h, int gh_store, void* stream) {
   if (E == 0) return M3G_OK;
   M3G_REQUIRE(src && h && wimgT && WhT && save && g_up && g_e && g_h, "m3g_conv_tc_bwd_saved: null pointer");
   M3G_REQUIRE(R >= 1 && R <= TC_BWD_MAX_R, "m3g_conv_tc_bwd_saved: R=%d unsupported (max %d)", R, TC_BWD_MAX_R);
@@ -1563,7 +1574,7 @@ int m3g_conv_tc_bwd_saved(const int32_t* src, const float* h, const float* wimgT
     set_error("m3g_conv_tc_bwd_saved: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     return M3G_ERR_CUDA;
   }
-  ConvTcBwdSParams p{src, h, wimgT, WhT, save, g_up, g_e_base, E, R, mode, passes, g_e, g_z1, g_h};
+  ConvTcBwdSParams p{src, h, wimgT, WhT, save, g_up, g_e_base, E, R, mode, passes, g_e, g_z1, g_h, gh_store};
   int64_t n_tiles = (E + TILE_M - 1) / TILE_M;
   unsigned grid = (unsigned)((n_tiles < n_sm) ? n_tiles : n_sm);
   conv_tc_bwds_kernel<<<grid, TCB2_THREADS, SMEM_BWDS_BYTES, as_stream(stream)>>>(p);

@@ -39,6 +39,15 @@ __global__ void add_kernel(const float* a, const float* b, int64_t n, float* out
   if (i < n) out[i] = a[i] + b[i];
 }
 
+// out[i] = sum_k slices[k * n + i], k ascending (the stated order of the per-launch g_h slices of the executor)
+__global__ void sum_slices_kernel(const float* __restrict__ slices, int K, int64_t n, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = slices[i];
+  for (int k = 1; k < K; ++k) acc += slices[(int64_t)k * n + i];
+  out[i] = acc;
+}
+
 }  // namespace m3g
 
 using namespace m3g;
@@ -74,6 +83,14 @@ int m3g_add(const float* a, const float* b, int64_t n, float* out, void* stream)
   M3G_REQUIRE(a && b && out, "m3g_add: null pointer");
   add_kernel<<<blocks_for(n, 256), 256, 0, as_stream(stream)>>>(a, b, n, out);
   M3G_LAUNCH_CHECK("m3g_add");
+  return M3G_OK;
+}
+
+int m3g_sum_slices(const float* slices, int K, int64_t n, float* out, void* stream) {
+  if (n == 0) return M3G_OK;
+  M3G_REQUIRE(slices && out && K >= 1, "m3g_sum_slices: bad argument");
+  sum_slices_kernel<<<blocks_for(n, 256), 256, 0, as_stream(stream)>>>(slices, K, n, out);
+  M3G_LAUNCH_CHECK("m3g_sum_slices");
   return M3G_OK;
 }
 

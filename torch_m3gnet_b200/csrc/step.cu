@@ -78,13 +78,6 @@ int readout(M3GStepDesc* d, void* s) {
   d->cur_x = 0;
   d->cur_e = 0;
   d->have_g_e = 0;
-  if (d->E > 0) {
-    cudaError_t err = cudaMemsetAsync(d->g_h, 0, sizeof(float) * R * d->E, as_stream(s));
-    if (err != cudaSuccess) {
-      set_error("m3g_step_run: cudaMemsetAsync: %s", cudaGetErrorString(err));
-      return M3G_ERR_CUDA;
-    }
-  }
   return M3G_OK;
 }
 
@@ -94,10 +87,13 @@ int conv_bwd(M3GStepDesc* d, int b, void* s) {
   const float* g_x2 = d->g_x[d->cur_x];
   const float* g_e2 = d->have_g_e ? d->g_e[d->cur_e] : nullptr;
   float* g_e_new = d->g_e[d->have_g_e ? (d->cur_e ^ 1) : 0];
+  // every backward launch stores its radial-weight adjoint into its own slice; the epilogue sums the slices
+  float* gh_node = d->g_hs + (int64_t)(2 * (d->n_blocks - 1 - b)) * R * d->E;
+  float* gh_edge = gh_node + (int64_t)R * d->E;
   M3G_TRY(m3g_conv_tc_bwd_saved(d->src, d->h, k.n_wimgT, k.n_WhT, k.save_n, g_x2, g_e2, d->E, R, 1, d->passes, d->n_sm,
-                                d->ge2, need_x ? d->gz_node : nullptr, d->g_h, s));
+                                d->ge2, need_x ? d->gz_node : nullptr, gh_node, 1, s));
   M3G_TRY(m3g_conv_tc_bwd_saved(d->src, d->h, k.e_wimgT, k.e_WhT, k.save_e, d->ge2, d->ge2, d->E, R, 0, d->passes,
-                                d->n_sm, g_e_new, need_x ? d->gz_edge : nullptr, d->g_h, s));
+                                d->n_sm, g_e_new, need_x ? d->gz_edge : nullptr, gh_edge, 1, s));
   d->cur_e = d->have_g_e ? (d->cur_e ^ 1) : 0;
   d->have_g_e = 1;
   if (need_x) {
@@ -130,8 +126,9 @@ int tb_bwd(M3GStepDesc* d, int b, void* s) {
 }
 
 int epilogue(M3GStepDesc* d, void* s) {
-  M3G_TRY(m3g_edge_adjust_bwd(d->h, d->adjust_Wt, d->g_e[d->cur_e], d->E, R, F, d->g_h2, s));
-  M3G_TRY(m3g_add(d->g_h, d->g_h2, (int64_t)R * d->E, d->g_h, s));
+  M3G_TRY(m3g_edge_adjust_bwd(d->h, d->adjust_Wt, d->g_e[d->cur_e], d->E, R, F,
+                              d->g_hs + (int64_t)(2 * d->n_blocks) * R * d->E, s));
+  M3G_TRY(m3g_sum_slices(d->g_hs, 2 * d->n_blocks + 1, (int64_t)R * d->E, d->g_h, s));
   M3G_TRY(m3g_radial_bwd(d->dist, d->radial_consts, d->g_h, d->E, R, d->g_dist, s));
   M3G_TRY(m3g_geometry_bwd(d->vec4, d->g_vec4, d->g_dist, d->edge_ptr, d->in_ptr, d->in_perm, d->N,
                            1.0f / d->length_scale, d->g_pos, s));

@@ -52,7 +52,7 @@ class _Desc(ctypes.Structure):
                                       "scaled_lattice", "elemental", "vec4", "dist", "cos_t", "x0", "h", "e0",
                                       "atomic", "scaled_total", "total", "forces", "stresses", "P", "msg")]
                 + [("g_x", _fp * 2), ("g_e", _fp * 2)]
-                + [(n, _fp) for n in ("ge2", "gz_edge", "gz_node", "gP", "g_h", "g_h2", "g_sig_e", "g_vec4", "g_dist",
+                + [(n, _fp) for n in ("ge2", "gz_edge", "gz_node", "gP", "g_h", "g_hs", "g_sig_e", "g_vec4", "g_dist",
                                       "g_pos")]
                 + [(n, ctypes.c_int) for n in ("cur_x", "cur_e", "have_g_e", "msg_reduce", "tb_split",
                                                "tb_bwd_split", "fuse_e0")]
@@ -182,7 +182,7 @@ class StepEngine:
         # scratch: one allocation carved by offsets (floats, every piece 16-byte aligned)
         sizes: List = [("vec4", 4 * E), ("x0", 64 * N), ("e0", 64 * E), ("P", 512 * N), ("msg", 64 * E),
                        ("g_x0", 64 * N), ("g_x1", 64 * N), ("g_e0", 64 * E), ("g_e1", 64 * E), ("ge2", 64 * E),
-                       ("gz_edge", 128 * E), ("gz_node", 128 * E), ("gP", 512 * N), ("g_h", 3 * E), ("g_h2", 3 * E),
+                       ("gz_edge", 128 * E), ("gz_node", 128 * E), ("gP", 512 * N), ("g_h", 3 * E), ("g_hs", (2 * n + 1) * 3 * E),
                        ("g_sig_e", 9 * E), ("g_vec4", 4 * E), ("g_dist", E), ("g_pos", 3 * N)]
         tables: Dict = {}
         weights = []
@@ -246,7 +246,7 @@ class StepEngine:
         d.atomic, d.scaled_total, d.total = (_p(out[K.SCALED_ATOMIC_ENERGIES]), _p(out[K.SCALED_TOTAL_ENERGY]),
                                              _p(out[K.TOTAL_ENERGY]))
         d.forces, d.stresses = _p(out[K.FORCES]), _p(out[K.STRESSES])
-        for name in ("vec4", "x0", "e0", "P", "msg", "ge2", "gz_edge", "gz_node", "gP", "g_h", "g_h2", "g_sig_e",
+        for name in ("vec4", "x0", "e0", "P", "msg", "ge2", "gz_edge", "gz_node", "gP", "g_h", "g_hs", "g_sig_e",
                      "g_vec4", "g_dist", "g_pos"):
             setattr(d, name, at(name))
         d.g_x[0], d.g_x[1] = at("g_x0"), at("g_x1")

@@ -332,10 +332,11 @@ class ConvFn(Function):
         if save_e is not None:
             passes = 3 if path == "tc3" else 1
             n_sm = sm_count(x.device)
+            # g_h: the node launch stores its rows, the edge launch adds to them (no zero fill needed)
             call("conv_tc_bwd_saved", plan.src, h, nd["wimgT"], nd["WhT"], save_n, g_x2, g_e2, E, R, 1, passes, n_sm, ge2,
-                 gz_node, g_h)
+                 gz_node, g_h, 1)
             call("conv_tc_bwd_saved", plan.src, h, ed["wimgT"], ed["WhT"], save_e, ge2, ge2, E, R, 0, passes, n_sm, g_e,
-                 gz_edge, g_h)
+                 gz_edge, g_h, 0)
             ctx.saved_acts = (None, None)
         elif F == 64 and "wimgT" in ed and path in ("tc3", "tc1") and R <= 3:
             passes = 3 if path == "tc3" else 1
