@@ -1106,6 +1106,24 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
   // node-MLP launches
   int s_cur = 0;
   if (p.mode != 0 && (int64_t)blockIdx.x < n_tiles) s_cur = __ldg(p.src + min((int64_t)blockIdx.x * TILE_M + row, p.E - 1));
+  // the upstream-gradient pieces of a tile (four float4 per thread: the coalesced layout in mode 0, this row's slice of
+  // g_up[src] in mode 1) are requested one tile ahead, while the previous tile's last stores drain: T0 starts with them
+  // in registers instead of an L2 round trip (tools/tc_timing.py: "T0 loads" 2.1 k cycles per tile before)
+  float4 gnext[4];
+  auto load_upstream = [&](int64_t t, int s_atom) {
+    if (p.mode == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t r = min(t * TILE_M + 32 * q + 8 * i + cr, p.E - 1);
+        gnext[i] = __ldg(reinterpret_cast<const float4*>(p.g_up + r * TC_F + k0 + 4 * cc4));
+      }
+    } else {
+      const float* gr = p.g_up + (int64_t)s_atom * TC_F + k0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) gnext[c] = __ldg(reinterpret_cast<const float4*>(gr + 4 * c));
+    }
+  };
+  if ((int64_t)blockIdx.x < n_tiles) load_upstream(blockIdx.x, s_cur);
 #ifdef M3G_TC_TIMING
   long long tct_prev = clock64();
 #endif
@@ -1114,11 +1132,8 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
     const int64_t e0 = tile * TILE_M;
     const int64_t eg = min(e0 + row, p.E - 1);
     const bool live = (e0 + row) < p.E;
-    const int s_row = s_cur;
     if (p.mode != 0 && tile + gridDim.x < n_tiles) s_cur = __ldg(p.src + min((tile + gridDim.x) * TILE_M + row, p.E - 1));
-    int64_t erow[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) erow[i] = e0 + 32 * q + 8 * i + cr;
+    const int64_t ebase = e0 + 32 * q + cr;  // rows ebase + 8 i (i = 0..3): this lane's rows in the coalesced layout
     {
       // next tile: saved activations (128 KB = 1024 lines), upstream rows, residual rows, h into L2
       const int64_t tn = tile + gridDim.x;
@@ -1136,8 +1151,24 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
         }
       }
     }
-    // ---- T0: saved z2 slices, upstream gradient slice, h ----
+    // ---- T0: upstream gradient slice (requested one tile ago), saved z2 slices, h ----
     float zd[16], zg[16], gu[16];
+    if (p.mode == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sts128(stg + stg_off(8 * i + cr, cc4), gnext[i]);
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float4 b = lds128(stg + stg_off(lane, c));
+        gu[4 * c] = b.x; gu[4 * c + 1] = b.y; gu[4 * c + 2] = b.z; gu[4 * c + 3] = b.w;
+      }
+      __syncwarp();
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        gu[4 * c] = gnext[c].x; gu[4 * c + 1] = gnext[c].y; gu[4 * c + 2] = gnext[c].z; gu[4 * c + 3] = gnext[c].w;
+      }
+    }
     {
       mbar_wait_warp(zb, par);  // the bulk copy issued one tile ago has landed
       const uint32_t s2 = z2buf + ((cs * 4 + q) << 11) + 16 * lane;
@@ -1148,28 +1179,6 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
         float4 b = lds128(s3 + 512 * c);
         zd[4 * c] = a.x; zd[4 * c + 1] = a.y; zd[4 * c + 2] = a.z; zd[4 * c + 3] = a.w;
         zg[4 * c] = b.x; zg[4 * c + 1] = b.y; zg[4 * c + 2] = b.z; zg[4 * c + 3] = b.w;
-      }
-    }
-    if (p.mode == 0) {
-      float4 c4v[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        c4v[i] = __ldg(reinterpret_cast<const float4*>(p.g_up + min(erow[i], p.E - 1) * TC_F + k0 + 4 * cc4));
-#pragma unroll
-      for (int i = 0; i < 4; ++i) sts128(stg + stg_off(8 * i + cr, cc4), c4v[i]);
-      __syncwarp();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float4 b = lds128(stg + stg_off(lane, c));
-        gu[4 * c] = b.x; gu[4 * c + 1] = b.y; gu[4 * c + 2] = b.z; gu[4 * c + 3] = b.w;
-      }
-      __syncwarp();
-    } else {
-      const float* gr = p.g_up + (int64_t)s_row * TC_F + k0;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float4 b = __ldg(reinterpret_cast<const float4*>(gr + 4 * c));
-        gu[4 * c] = b.x; gu[4 * c + 1] = b.y; gu[4 * c + 2] = b.z; gu[4 * c + 3] = b.w;
       }
     }
     float hm[TC_BWD_MAX_R], ghp[TC_BWD_MAX_R];
@@ -1291,7 +1300,7 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
     if (p.g_e_base) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        gb[i] = __ldg(reinterpret_cast<const float4*>(p.g_e_base + min(erow[i], p.E - 1) * TC_F + k0 + 4 * cc4));
+        gb[i] = __ldg(reinterpret_cast<const float4*>(p.g_e_base + min(ebase + 8 * i, p.E - 1) * TC_F + k0 + 4 * cc4));
     }
     // g_z1 rows straight from registers (overlaps GEMM4), coalesced through the staging tile; skipped when the caller
     // has no use for them (first block of the model: its node features do not depend on the positions)
@@ -1306,12 +1315,13 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float4 r4 = lds128(stg + stg_off(8 * i + cr, cc4));
-          if (erow[i] < p.E) *reinterpret_cast<float4*>(p.g_z1 + erow[i] * 128 + 64 * hb + k0 + 4 * cc4) = r4;
+          if (ebase + 8 * i < p.E) *reinterpret_cast<float4*>(p.g_z1 + (ebase + 8 * i) * 128 + 64 * hb + k0 + 4 * cc4) = r4;
         }
         __syncwarp();
       }
     }
     TCT(11);
+    if (tile + gridDim.x < n_tiles) load_upstream(tile + gridDim.x, s_cur);
     // ---- T7: g_e ----
     mbar_wait_warp(bar4, par);
     TCT(12);
@@ -1327,9 +1337,9 @@ __global__ void __launch_bounds__(TCB2_THREADS, 1) conv_tc_bwds_kernel(ConvTcBwd
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float4 r4 = lds128(stg + stg_off(8 * i + cr, cc4));
-        if (erow[i] < p.E) {
+        if (ebase + 8 * i < p.E) {
           if (p.g_e_base) { r4.x += gb[i].x; r4.y += gb[i].y; r4.z += gb[i].z; r4.w += gb[i].w; }
-          *reinterpret_cast<float4*>(p.g_e + erow[i] * TC_F + k0 + 4 * cc4) = r4;
+          *reinterpret_cast<float4*>(p.g_e + (ebase + 8 * i) * TC_F + k0 + 4 * cc4) = r4;
         }
       }
       __syncwarp();
